@@ -1,0 +1,141 @@
+"""ctypes binding of oracle/libulcoracle.so (the plain-C restatement in oracle/ulc_oracle.c).
+
+TEST INFRASTRUCTURE ONLY - see the header of ulc_oracle.c.  Importable from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg; never from ulc_codec_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libulcoracle.so")
+_lib = None
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(HERE, "ulc_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.ulco_dct4.argtypes = [_f32p, _f32p, C.c_int]
+        L.ulco_dct2.argtypes = [_f32p, _f32p, C.c_int]
+        L.ulco_imdct.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int]
+        L.ulco_mdct_mdst.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int]
+        L.ulco_subblocks.argtypes = [C.c_int, C.POINTER(C.c_int * 4), C.POINTER(C.c_int)]
+        L.ulco_subblocks.restype = C.c_int
+        L.ulco_decoder_new.argtypes = [C.c_int, C.c_int]
+        L.ulco_decoder_new.restype = C.c_void_p
+        L.ulco_decoder_free.argtypes = [C.c_void_p]
+        L.ulco_decoder_rng.argtypes = [C.c_void_p]
+        L.ulco_decoder_rng.restype = C.c_uint32
+        L.ulco_parse_block.argtypes = [C.c_void_p, C.c_void_p, _f32p, C.POINTER(C.c_int)]
+        L.ulco_parse_block.restype = C.c_int
+        L.ulco_decode_block.argtypes = [C.c_void_p, _f32p, C.c_void_p]
+        L.ulco_decode_block.restype = C.c_int
+        L.ulco_float_to_pcm16.argtypes = [_i16p, _f32p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def dct4(x: np.ndarray) -> np.ndarray:
+    buf = np.ascontiguousarray(x, dtype=np.float32).copy()
+    lib().ulco_dct4(buf, np.empty_like(buf), len(buf))
+    return buf
+
+
+def dct2(x: np.ndarray) -> np.ndarray:
+    buf = np.ascontiguousarray(x, dtype=np.float32).copy()
+    lib().ulco_dct2(buf, np.empty_like(buf), len(buf))
+    return buf
+
+
+def imdct(coefs: np.ndarray, lap: np.ndarray, overlap: int) -> np.ndarray:
+    """Returns out[n]; `lap` (n/2) is updated in place."""
+    n = len(coefs)
+    out = np.empty(n, np.float32)
+    lib().ulco_imdct(out, np.ascontiguousarray(coefs, np.float32), lap, np.empty(n, np.float32), n, overlap)
+    return out
+
+
+def mdct_mdst(fresh: np.ndarray, lap: np.ndarray, overlap: int):
+    """Returns (mdct[n], mdst[n]); `lap` (n) is updated in place."""
+    n = len(fresh)
+    a, b = np.empty(n, np.float32), np.empty(n, np.float32)
+    lib().ulco_mdct_mdst(a, b, np.ascontiguousarray(fresh, np.float32), lap, np.empty(n, np.float32), n, overlap)
+    return a, b
+
+
+def subblocks(window_ctrl: int):
+    sh = (C.c_int * 4)()
+    tr = C.c_int()
+    n = lib().ulco_subblocks(window_ctrl, C.byref(sh), C.byref(tr))
+    return list(sh)[:n], tr.value
+
+
+def float_to_pcm16(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty(x.shape, np.int16)
+    lib().ulco_float_to_pcm16(out.reshape(-1), x.reshape(-1), x.size)
+    return out
+
+
+class Decoder:
+    """Streaming decoder with the semantics of a fresh ULC_DecoderState_Init (+ RNG at 1234567)."""
+
+    def __init__(self, n_chan: int = 2, block_size: int = 2048):
+        self.n_chan, self.block_size = n_chan, block_size
+        self._h = lib().ulco_decoder_new(n_chan, block_size)
+        if not self._h:
+            raise ValueError("bad decoder parameters")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ulco_decoder_free(self._h)
+            self._h = None
+
+    def decode_block(self, buf: np.ndarray, offset: int):
+        """buf must have readable slack after the block.  Returns (float32[N, nChan], bits)."""
+        out = np.empty((self.block_size, self.n_chan), np.float32)
+        bits = lib().ulco_decode_block(self._h, out.reshape(-1), buf.ctypes.data + offset)
+        return out, bits
+
+    def parse_block(self, buf: np.ndarray, offset: int):
+        coefs = np.empty(self.n_chan * self.block_size, np.float32)
+        wc = C.c_int()
+        bits = lib().ulco_parse_block(self._h, buf.ctypes.data + offset, coefs, C.byref(wc))
+        return coefs, wc.value, bits
+
+    def decode_stream(self, data: np.ndarray, n_blocks: int):
+        """Decode n_blocks consecutive blocks (tools/ulcDecodeTool.c:135-165 stepping rule).
+        Returns (float32[nBlocks*N, nChan], int32[nBlocks] bits; 0 marks the corrupt block)."""
+        pad = np.zeros(4 * self.block_size * self.n_chan + 64, np.uint8)
+        buf = np.concatenate([np.ascontiguousarray(data, np.uint8), pad])
+        out = np.zeros((n_blocks * self.block_size, self.n_chan), np.float32)
+        bits = np.zeros(n_blocks, np.int32)
+        pos = 0
+        for b in range(n_blocks):
+            if pos >= len(data):
+                break
+            blk, nb = self.decode_block(buf, pos)
+            bits[b] = nb
+            if nb == 0:
+                break
+            out[b * self.block_size:(b + 1) * self.block_size] = blk
+            pos += (nb + 7) // 8
+        return out, bits
