@@ -1,0 +1,187 @@
+"""ctypes binding of libulcb200.so (include/ulcb200.h) - the host-side mirror of the C ABI.
+
+The product path is the CUDA library; this module only marshals numpy / torch buffers into the
+plain-pointer C calls.  It fails loudly (ImportError / RuntimeError) when the library is missing or
+no sm_100 GPU is present - there is no CPU fallback and nothing here touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libulcb200.so")
+
+FMT_PCM16, FMT_FLOAT32 = 0, 1
+_FMT = {"pcm16": FMT_PCM16, "s16": FMT_PCM16, "f32": FMT_FLOAT32, "float32": FMT_FLOAT32}
+
+# every symbol include/ulcb200.h declares (tests/test_capi_symbols.py checks the header against this)
+EXPORTS = (
+    "ULC_DecoderState_Init", "ULC_DecoderState_Destroy", "ULC_DecodeBlock",
+    "ULCB_ContextCreate", "ULCB_ContextDestroy", "ULCB_LastCudaError", "ULCB_ErrorString",
+    "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_Sync", "ULCB_Stream",
+    "ULCB_LaunchCount", "ULCB_TestDCT4",
+)
+
+
+class ULC_DecoderState_t(C.Structure):
+    """include/ulcb200.h (layout of /root/reference/include/ulcDecoder.h:13-32)."""
+    _fields_ = [("nChan", C.c_int), ("BlockSize", C.c_int), ("LastSubBlockSize", C.c_int),
+                ("BufferData", C.c_void_p), ("TransformBuffer", C.c_void_p),
+                ("TransformTemp", C.c_void_p), ("TransformInvLap", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare prototypes.  Needs no GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing - run `python __graft_entry__.py` (nvcc, sm_100a) first; "
+                          "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError if a declared symbol is not exported
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.ULCB_ContextCreate.argtypes = [C.POINTER(vp), i32, i32, i32, i32, u32]
+    L.ULCB_ContextDestroy.argtypes = [vp]
+    L.ULCB_ContextDestroy.restype = None
+    L.ULCB_LastCudaError.argtypes = [vp]
+    L.ULCB_ErrorString.argtypes = [i32]
+    L.ULCB_ErrorString.restype = C.c_char_p
+    L.ULCB_MaxBlockBytes.argtypes = [i32, i32]
+    L.ULCB_MaxBlockBytes.restype = C.c_size_t
+    L.ULCB_DecodeStreamsDevice.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, i32, vp, vp, u64]
+    L.ULCB_DecodeStreams.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, i32, vp, vp, u64]
+    L.ULCB_Sync.argtypes = [vp]
+    L.ULCB_Stream.argtypes = [vp]
+    L.ULCB_Stream.restype = vp
+    L.ULCB_LaunchCount.argtypes = [vp]
+    L.ULCB_LaunchCount.restype = u64
+    L.ULCB_TestDCT4.argtypes = [vp, vp, i32, i32]
+    L.ULC_DecoderState_Init.argtypes = [C.POINTER(ULC_DecoderState_t)]
+    L.ULC_DecoderState_Destroy.argtypes = [C.POINTER(ULC_DecoderState_t)]
+    L.ULC_DecoderState_Destroy.restype = None
+    L.ULC_DecodeBlock.argtypes = [C.POINTER(ULC_DecoderState_t), vp, vp]
+    _lib = L
+    return L
+
+
+class UlcbError(RuntimeError):
+    pass
+
+
+def _check(L, ctx, rc: int, what: str):
+    if rc != 0:
+        cuda = L.ULCB_LastCudaError(ctx) if ctx else 0
+        raise UlcbError(f"{what}: {L.ULCB_ErrorString(rc).decode()} (status {rc}, cuda error {cuda})")
+
+
+def pack_streams(streams):
+    """list of uint8 arrays -> (concatenated uint8, uint64 offsets[n+1])."""
+    offs = np.zeros(len(streams) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in streams], dtype=np.uint64)
+    data = np.concatenate([np.ascontiguousarray(s, np.uint8) for s in streams]) if streams else np.zeros(0, np.uint8)
+    return data, offs
+
+
+class Context:
+    """ULCB_Context wrapper.  One context = one (rate, channels, block size) configuration on one GPU."""
+
+    def __init__(self, rate_hz: int = 44100, n_chan: int = 2, block_size: int = 2048, *,
+                 max_blocks: int = 4096, device: int = 0):
+        self.L = load()
+        self.rate_hz, self.n_chan, self.block_size, self.max_blocks = rate_hz, n_chan, block_size, max_blocks
+        h = C.c_void_p()
+        rc = self.L.ULCB_ContextCreate(C.byref(h), device, rate_hz, n_chan, block_size, max_blocks)
+        _check(self.L, None, rc, "ULCB_ContextCreate")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ULCB_ContextDestroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.ULCB_LaunchCount(self.h))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self.L.ULCB_Stream(self.h) or 0)
+
+    def sync(self):
+        _check(self.L, self.h, self.L.ULCB_Sync(self.h), "ULCB_Sync")
+
+    # ---- host-pointer batched decode (ULCB_DecodeStreams) ----
+    def decode_streams(self, streams, n_blocks, fmt: str = "pcm16", want_bits: bool = False):
+        """streams: list of uint8 arrays (raw block bytes).  n_blocks: int or per-stream sequence.
+        Returns (pcm[nStreams, maxBlocks*N, nChan], status int32[nStreams], bits uint32[nStreams, maxBlocks] | None)."""
+        data, offs = pack_streams(streams)
+        ns = len(streams)
+        if np.isscalar(n_blocks):
+            nb_arr, nb_all, max_blk = None, int(n_blocks), int(n_blocks)
+        else:
+            nb_arr = np.ascontiguousarray(n_blocks, np.uint32)
+            nb_all, max_blk = 0, int(nb_arr.max()) if ns else 0
+        stride = max_blk * self.block_size * self.n_chan
+        f = _FMT[fmt]
+        out = np.zeros((ns, max_blk * self.block_size, self.n_chan), np.int16 if f == FMT_PCM16 else np.float32)
+        status = np.zeros(ns, np.int32)
+        bits = np.zeros((ns, max_blk), np.uint32) if want_bits else None
+        rc = self.L.ULCB_DecodeStreams(
+            self.h, ns, data.ctypes.data, offs.ctypes.data, nb_arr.ctypes.data if nb_arr is not None else None, nb_all,
+            out.ctypes.data, stride, f, status.ctypes.data, bits.ctypes.data if want_bits else None, max_blk)
+        _check(self.L, self.h, rc, "ULCB_DecodeStreams")
+        return out, status, bits
+
+    # ---- device-pointer batched decode (ULCB_DecodeStreamsDevice); pointers are plain ints ----
+    def decode_streams_device(self, n_streams: int, d_bytes: int, d_offs: int, n_blocks_all: int, d_out: int,
+                              out_stride: int, fmt: str = "pcm16", d_status: int = 0, d_nblocks: int = 0,
+                              d_bits: int = 0, bits_stride: int = 0):
+        rc = self.L.ULCB_DecodeStreamsDevice(self.h, n_streams, d_bytes, d_offs, d_nblocks or None, n_blocks_all,
+                                             d_out, out_stride, _FMT[fmt], d_status or None, d_bits or None, bits_stride)
+        _check(self.L, self.h, rc, "ULCB_DecodeStreamsDevice")
+
+    def test_dct4(self, x: np.ndarray) -> np.ndarray:
+        buf = np.ascontiguousarray(x, np.float32).copy()
+        count, size = (1, buf.shape[0]) if buf.ndim == 1 else buf.shape
+        _check(self.L, self.h, self.L.ULCB_TestDCT4(self.h, buf.ctypes.data, size, count), "ULCB_TestDCT4")
+        return buf
+
+
+class DropinDecoder:
+    """The reference's single-stream API (ULC_DecoderState_Init / ULC_DecodeBlock), through the drop-in symbols."""
+
+    def __init__(self, n_chan: int = 2, block_size: int = 2048):
+        self.L = load()
+        self.st = ULC_DecoderState_t()
+        self.st.nChan, self.st.BlockSize = n_chan, block_size
+        self.ok = self.L.ULC_DecoderState_Init(C.byref(self.st))
+        if self.ok < 0:
+            raise UlcbError("ULC_DecoderState_Init returned -1")
+
+    def decode_block(self, buf: np.ndarray, offset: int = 0):
+        out = np.empty((self.st.BlockSize, self.st.nChan), np.float32)
+        bits = self.L.ULC_DecodeBlock(C.byref(self.st), out.ctypes.data, buf.ctypes.data + offset)
+        return out, bits
+
+    def close(self):
+        if getattr(self, "ok", -1) >= 0:
+            self.L.ULC_DecoderState_Destroy(C.byref(self.st))
+            self.ok = -1
+
+    __del__ = close

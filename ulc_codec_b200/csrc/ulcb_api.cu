@@ -1,0 +1,376 @@
+// ulcb_api.cu - C-ABI layer of libulcb200.so: contexts, host-built tables, the batched entry points
+// and the libulc drop-in API (include/ulcb200.h).  Host code only orchestrates; all codec work runs in
+// the CUDA kernels.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "../../include/ulcb200.h"
+#include "ulcb_dct.cuh"
+#include "ulcb_decode.h"
+
+struct ULCB_Context {
+    int device = 0, rateHz = 0, nChan = 0, N = 0;
+    uint32_t maxBlocks = 0;
+    cudaStream_t stream = nullptr;
+    int lastCuda = 0;
+    uint64_t launches = 0;
+    UlcbTables tb{};
+    std::vector<void *> owned;          // device allocations freed with the context
+    // staging for the host-pointer entry points (grown on demand)
+    void *dIn = nullptr;  size_t dInCap = 0;
+    void *dOut = nullptr; size_t dOutCap = 0;
+    void *dAux = nullptr; size_t dAuxCap = 0;
+};
+
+namespace {
+
+#define CK(ctx, expr)                                                        \
+    do {                                                                     \
+        cudaError_t e_ = (expr);                                             \
+        if (e_ != cudaSuccess) { (ctx)->lastCuda = (int)e_; return ULCB_E_CUDA; } \
+    } while (0)
+
+// ---- window rotation table: the reference's own f32 recurrence, so the decoder's window VALUES are
+// those of the stock scalar build (libfourier/source/Fourier_Helper.h:218-240 minimax polynomials,
+// Fourier_IMDCT_Template.h:76-91 rotation).  Plain mul/add in source order, no contraction.
+float poly_sin(float x) {
+    volatile float x2 = x * x;
+    volatile float r = x2 * 0x1.3C8B08p-13f; r = r + -0x1.3237ECp-8f;
+    r = x2 * r; r = r + 0x1.4667ACp-4f;
+    r = x2 * r; r = r + -0x1.4ABBB8p-1f;
+    r = x2 * r; r = r + 0x1.921FB4p0f;
+    return x * r;
+}
+float poly_cos(float x) {
+    volatile float x2 = x * x;
+    volatile float r = x2 * 0x1.C2EA62p-11f; r = r + -0x1.550810p-6f;
+    r = x2 * r; r = r + 0x1.03BDD6p-2f;
+    r = x2 * r; r = r + -0x1.3BD3B2p0f;
+    r = x2 * r; r = r + 1.0f;
+    return r;
+}
+void build_window(std::vector<float2> &win, int N) {
+    win.assign(N, float2{1.0f, 0.0f});
+    for (int ov = 1; ov <= N; ov <<= 1) {
+        int cnt = ov > 1 ? ov / 2 : 1, base = ov / 2;
+        volatile float c = poly_cos(0.5f / ov), s = poly_sin(0.5f / ov);
+        const float wc = poly_cos(1.0f / ov), ws = poly_sin(1.0f / ov);
+        for (int i = 0; i < cnt; i++) {
+            win[base + i] = float2{c, s};
+            volatile float a = c, b = s;
+            volatile float t0 = wc * a, t1 = ws * b, t2 = ws * a, t3 = wc * b;
+            c = t0 - t1;
+            s = t2 + t3;
+        }
+    }
+}
+
+// slot of Z[k] after the in-place radix-4 (final radix-2 if log2 M odd) DIF FFT of size M
+int fft_slot(int k, int M) {
+    int pos = 0;
+    while (M >= 4) { pos += (k & 3) * (M >> 2); k >>= 2; M >>= 2; }
+    if (M == 2) pos += k & 1;
+    return pos;
+}
+
+template <typename T>
+int upload(ULCB_Context *ctx, const std::vector<T> &h, const T **d) {
+    void *p = nullptr;
+    CK(ctx, cudaMalloc(&p, h.size() * sizeof(T) + 16));
+    ctx->owned.push_back(p);
+    CK(ctx, cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *d = reinterpret_cast<const T *>(p);
+    return ULCB_OK;
+}
+
+int build_tables(ULCB_Context *ctx) {
+    const int N = ctx->N;
+    UlcbTables &tb = ctx->tb;
+    tb.N = N;
+    tb.log2N = 31 - __builtin_clz(N);
+    int rc;
+    {
+        std::vector<float2> w(N / 2);
+        for (int k = 0; k < N / 2; k++) {
+            double a = -2.0 * M_PI * k / (N / 2);
+            w[k] = float2{(float)cos(a), (float)sin(a)};
+        }
+        if ((rc = upload(ctx, w, &tb.fftW))) return rc;
+    }
+    for (int sh = 0; sh < 4; sh++) {
+        int S = N >> sh, M = S / 2;
+        std::vector<float2> e(M);
+        std::vector<uint16_t> pos(M);
+        for (int n = 0; n < M; n++) {
+            double a = -M_PI * (8.0 * n + 1.0) / (8.0 * S);
+            e[n] = float2{(float)cos(a), (float)sin(a)};
+            pos[n] = (uint16_t)fft_slot(n, M);
+        }
+        if ((rc = upload(ctx, e, &tb.dctE[sh]))) return rc;
+        if ((rc = upload(ctx, pos, &tb.fftPos[sh]))) return rc;
+    }
+    {
+        std::vector<float2> win;
+        build_window(win, N);
+        if ((rc = upload(ctx, win, &tb.win))) return rc;
+    }
+    {
+        // running parity of the xorshift32 MSBs (libulc/ulcDecoder.c:75-81): bit m = parity of draws 0..m-1
+        uint64_t nBits = (uint64_t)ctx->maxBlocks * ctx->nChan * N + 64;
+        std::vector<uint32_t> par((nBits + 31) / 32 + 2, 0u);
+        uint32_t seed = 1234567u, p = 0;
+        for (uint64_t m = 1; m < nBits; m++) {
+            seed ^= seed << 13; seed ^= seed >> 17; seed ^= seed << 5;
+            p ^= seed >> 31;
+            par[m >> 5] |= p << (m & 31);
+        }
+        tb.nSignBits = nBits;
+        if ((rc = upload(ctx, par, &tb.signParity))) return rc;
+    }
+    return ULCB_OK;
+}
+
+int grow(ULCB_Context *ctx, void **p, size_t *cap, size_t need) {
+    if (need <= *cap) return ULCB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CK(ctx, cudaMalloc(p, need));
+    *cap = need;
+    return ULCB_OK;
+}
+
+bool supported(int nChan, int N) { return nChan >= 1 && nChan <= 2 && N >= 256 && N <= 8192; }
+bool valid(int nChan, int N) {
+    return nChan >= 1 && nChan <= 255 && N >= 256 && N <= 32768 && (N & (N - 1)) == 0;
+}
+
+__global__ void dct4_test_kernel(float *data, int S, int sh, UlcbTables tb) {
+    extern __shared__ __align__(16) float sbuf[];
+    float *g = data + (size_t)blockIdx.x * S;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sbuf[i] = g[i];
+    __syncthreads();
+    dct4_inplace<8>(sbuf, S, 1, S, sh, tb);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) g[i] = sbuf[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ULCB_ErrorString(int status) {
+    switch (status) {
+        case ULCB_OK: return "ok";
+        case ULCB_E_PARAM: return "bad parameter";
+        case ULCB_E_UNSUPPORTED: return "configuration not supported by this build";
+        case ULCB_E_NOMEM: return "out of memory";
+        case ULCB_E_CUDA: return "CUDA runtime error";
+        case ULCB_E_NODEVICE: return "no sm_100 GPU available (there is no CPU fallback)";
+    }
+    return "unknown";
+}
+
+size_t ULCB_MaxBlockBytes(int nChan, int blockSize) { return (size_t)2 * nChan * blockSize + 8; }
+
+int ULCB_ContextCreate(ULCB_Context **out, int device, int rateHz, int nChan, int blockSize, uint32_t maxBlocksPerStream) {
+    if (!out) return ULCB_E_PARAM;
+    *out = nullptr;
+    if (!valid(nChan, blockSize) || rateHz < 1 || maxBlocksPerStream < 1) return ULCB_E_PARAM;
+    if (!supported(nChan, blockSize)) return ULCB_E_UNSUPPORTED;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || device < 0 || device >= nDev) return ULCB_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return ULCB_E_NODEVICE;
+    ULCB_Context *ctx = new (std::nothrow) ULCB_Context();
+    if (!ctx) return ULCB_E_NOMEM;
+    ctx->device = device; ctx->rateHz = rateHz; ctx->nChan = nChan; ctx->N = blockSize; ctx->maxBlocks = maxBlocksPerStream;
+    int rc = ULCB_OK;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) rc = ULCB_E_CUDA;
+    if (rc == ULCB_OK) rc = build_tables(ctx);
+    if (rc != ULCB_OK) { ULCB_ContextDestroy(ctx); return rc; }
+    *out = ctx;
+    return ULCB_OK;
+}
+
+void ULCB_ContextDestroy(ULCB_Context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->dIn) cudaFree(ctx->dIn);
+    if (ctx->dOut) cudaFree(ctx->dOut);
+    if (ctx->dAux) cudaFree(ctx->dAux);
+    delete ctx;
+}
+
+int ULCB_LastCudaError(const ULCB_Context *ctx) { return ctx ? ctx->lastCuda : 0; }
+void *ULCB_Stream(ULCB_Context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t ULCB_LaunchCount(const ULCB_Context *ctx) { return ctx ? ctx->launches : 0; }
+
+int ULCB_Sync(ULCB_Context *ctx) {
+    if (!ctx) return ULCB_E_PARAM;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ULCB_OK;
+}
+
+static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs,
+                         const uint32_t *dNBlocks, uint32_t nBlocksAll, void *dOut, uint64_t outStrideElems,
+                         int format, int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride,
+                         UlcbStreamState *state, float *statePend) {
+    if (!ctx || nStreams < 0 || !dBytes || !dStreamOffs || !dOut) return ULCB_E_PARAM;
+    if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
+    if (nStreams == 0) return ULCB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    UlcbDecodeArgs a{};
+    a.tb = ctx->tb;
+    a.nStreams = nStreams; a.nBlocksAll = (int)nBlocksAll;
+    a.bytes = dBytes; a.streamOffs = dStreamOffs; a.nBlocks = dNBlocks;
+    a.out = dOut; a.outStride = outStrideElems;
+    a.status = dStatus; a.bytesConsumed = nullptr; a.blockBits = dBlockBits; a.bitsStride = bitsStride;
+    a.state = state; a.statePend = statePend;
+    CK(ctx, ulcb_decode_launch(a, ctx->nChan, format == ULCB_FMT_PCM16, nStreams, ctx->stream));
+    ctx->launches++;
+    return ULCB_OK;
+}
+
+int ULCB_DecodeStreamsDevice(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs,
+                             const uint32_t *dNBlocks, uint32_t nBlocksAll, void *dOut, uint64_t outStrideElems,
+                             int format, int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride) {
+    return decode_device(ctx, nStreams, dBytes, dStreamOffs, dNBlocks, nBlocksAll, dOut, outStrideElems, format,
+                         dStatus, dBlockBits, bitsStride, nullptr, nullptr);
+}
+
+int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, const uint64_t *streamOffs,
+                       const uint32_t *nBlocks, uint32_t nBlocksAll, void *out, uint64_t outStrideElems, int format,
+                       int32_t *status, uint32_t *blockBits, uint64_t bitsStride) {
+    if (!ctx || nStreams < 0 || !bytes || !streamOffs || !out) return ULCB_E_PARAM;
+    if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
+    if (nStreams == 0) return ULCB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t elem = format == ULCB_FMT_PCM16 ? 2 : 4;
+    const size_t nBytes = streamOffs[nStreams];
+    uint32_t maxBlk = nBlocksAll;
+    if (nBlocks) { maxBlk = 0; for (int s = 0; s < nStreams; s++) if (nBlocks[s] > maxBlk) maxBlk = nBlocks[s]; }
+    if (outStrideElems < (uint64_t)maxBlk * ctx->N * ctx->nChan) return ULCB_E_PARAM;
+    const size_t outBytes = (size_t)nStreams * outStrideElems * elem;
+    // aux layout: offs | nBlocks | status | bits
+    const size_t offOffs = 0, offNb = offOffs + sizeof(uint64_t) * (nStreams + 1);
+    const size_t offSt = offNb + sizeof(uint32_t) * nStreams, offBits = (offSt + sizeof(int32_t) * nStreams + 15) & ~(size_t)15;
+    const size_t auxBytes = offBits + (blockBits ? sizeof(uint32_t) * nStreams * bitsStride : 0);
+    int rc;
+    if ((rc = grow(ctx, &ctx->dIn, &ctx->dInCap, nBytes + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, outBytes))) return rc;
+    if ((rc = grow(ctx, &ctx->dAux, &ctx->dAuxCap, auxBytes))) return rc;
+    char *aux = (char *)ctx->dAux;
+    CK(ctx, cudaMemcpyAsync(ctx->dIn, bytes, nBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemsetAsync((char *)ctx->dIn + nBytes, 0, 64, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(aux + offOffs, streamOffs, sizeof(uint64_t) * (nStreams + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nBlocks) CK(ctx, cudaMemcpyAsync(aux + offNb, nBlocks, sizeof(uint32_t) * nStreams, cudaMemcpyHostToDevice, ctx->stream));
+    rc = decode_device(ctx, nStreams, (const uint8_t *)ctx->dIn, (const uint64_t *)(aux + offOffs),
+                       nBlocks ? (const uint32_t *)(aux + offNb) : nullptr, nBlocksAll, ctx->dOut, outStrideElems, format,
+                       (int32_t *)(aux + offSt), blockBits ? (uint32_t *)(aux + offBits) : nullptr, bitsStride, nullptr, nullptr);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(ctx, cudaMemcpyAsync(status, aux + offSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
+    if (blockBits) CK(ctx, cudaMemcpyAsync(blockBits, aux + offBits, sizeof(uint32_t) * nStreams * bitsStride, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ULCB_OK;
+}
+
+int ULCB_TestDCT4(ULCB_Context *ctx, float *data, int size, int count) {
+    if (!ctx || !data || count < 1) return ULCB_E_PARAM;
+    int sh = -1;
+    for (int i = 0; i < 4; i++) if ((ctx->N >> i) == size) sh = i;
+    if (sh < 0) return ULCB_E_PARAM;
+    CK(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = sizeof(float) * (size_t)size * count;
+    int rc;
+    if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, bytes))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->dOut, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaFuncSetAttribute(dct4_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * size)));
+    dct4_test_kernel<<<count, size / 32 < 32 ? 32 : (size / 32 > 256 ? 256 : size / 32), sizeof(float) * size, ctx->stream>>>((float *)ctx->dOut, size, sh, ctx->tb);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(data, ctx->dOut, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ULCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// libulc drop-in: decoder (reference: include/ulcDecoder.h, libulc/ulcDecoder.c)
+// ------------------------------------------------------------------------------------------------
+struct DropinDecoder {
+    ULCB_Context *ctx;
+    UlcbStreamState *dState;
+    float *dPend;
+    uint8_t *dSrc; float *dDst; uint64_t *dOffs; uint32_t *dBits;
+    uint8_t *hSrc; float *hDst; uint32_t *hBits;      // pinned
+    size_t srcBytes;
+};
+
+int ULC_DecoderState_Init(struct ULC_DecoderState_t *State) {
+    State->BufferData = NULL;                                  // ulcDecoder.c:28
+    State->TransformBuffer = State->TransformTemp = State->TransformInvLap = NULL;
+    int nChan = State->nChan, N = State->BlockSize;
+    if (!valid(nChan, N)) return -1;                           // ulcDecoder.c:30-35
+    DropinDecoder *d = (DropinDecoder *)calloc(1, sizeof(DropinDecoder));
+    if (!d) return -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (ULCB_ContextCreate(&d->ctx, dev, 44100, nChan, N, 1u << 14) != ULCB_OK) { free(d); return -1; }
+    size_t cap = ULCB_MaxBlockBytes(nChan, N);
+    d->srcBytes = cap < 16384 ? cap : 16384;
+    bool ok = cudaMalloc(&d->dState, sizeof(UlcbStreamState)) == cudaSuccess &&
+              cudaMalloc(&d->dPend, sizeof(float) * nChan * (N / 2)) == cudaSuccess &&
+              cudaMalloc(&d->dSrc, d->srcBytes + 64) == cudaSuccess &&
+              cudaMalloc(&d->dDst, sizeof(float) * nChan * N) == cudaSuccess &&
+              cudaMalloc(&d->dOffs, 2 * sizeof(uint64_t)) == cudaSuccess &&
+              cudaMalloc(&d->dBits, sizeof(uint32_t)) == cudaSuccess &&
+              cudaMallocHost(&d->hSrc, d->srcBytes) == cudaSuccess &&
+              cudaMallocHost(&d->hDst, sizeof(float) * nChan * N) == cudaSuccess &&
+              cudaMallocHost(&d->hBits, sizeof(uint32_t)) == cudaSuccess;
+    if (ok) {
+        uint64_t offs[2] = {0, d->srcBytes};
+        ok = cudaMemset(d->dState, 0, sizeof(UlcbStreamState)) == cudaSuccess &&
+             cudaMemset(d->dSrc, 0, d->srcBytes + 64) == cudaSuccess &&
+             cudaMemcpy(d->dOffs, offs, sizeof offs, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    State->BufferData = d;
+    if (!ok) { ULC_DecoderState_Destroy(State); return -1; }
+    State->LastSubBlockSize = 0;                               // ulcDecoder.c:52
+    return 1;
+}
+
+void ULC_DecoderState_Destroy(struct ULC_DecoderState_t *State) {
+    DropinDecoder *d = (DropinDecoder *)State->BufferData;
+    if (!d) return;
+    cudaFree(d->dState); cudaFree(d->dPend); cudaFree(d->dSrc); cudaFree(d->dDst); cudaFree(d->dOffs); cudaFree(d->dBits);
+    cudaFreeHost(d->hSrc); cudaFreeHost(d->hDst); cudaFreeHost(d->hBits);
+    ULCB_ContextDestroy(d->ctx);
+    free(d);
+    State->BufferData = NULL;
+}
+
+int ULC_DecodeBlock(struct ULC_DecoderState_t *State, float *DstData, const void *SrcBuffer) {
+    DropinDecoder *d = (DropinDecoder *)State->BufferData;
+    if (!d) return 0;
+    ULCB_Context *ctx = d->ctx;
+    const int n = State->nChan * State->BlockSize;
+    memcpy(d->hSrc, SrcBuffer, d->srcBytes);
+    if (cudaMemcpyAsync(d->dSrc, d->hSrc, d->srcBytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return 0;
+    if (decode_device(ctx, 1, d->dSrc, d->dOffs, nullptr, 1, d->dDst, (uint64_t)n, ULCB_FMT_FLOAT32, nullptr, d->dBits, 1,
+                      d->dState, d->dPend) != ULCB_OK) return 0;
+    cudaMemcpyAsync(d->hDst, d->dDst, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(d->hBits, d->dBits, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+    memcpy(DstData, d->hDst, sizeof(float) * n);
+    UlcbStreamState st;
+    if (cudaMemcpy(&st, d->dState, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess) State->LastSubBlockSize = st.lastSubBlockSize;
+    return (int)*d->hBits;
+}
+
+}  // extern "C"
