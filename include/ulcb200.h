@@ -126,6 +126,8 @@ uint64_t ULCB_LaunchCount(const ULCB_Context *ctx);
 
 /* Stage-level test hooks (host pointers; synchronous).  Used by tests/ only. */
 int ULCB_TestDCT4(ULCB_Context *ctx, float *data, int size, int count);
+/* parse + dequantise + noise-fill only: coefs[nBlocks][nChan*blockSize], blockBits[nBlocks] for ONE stream */
+int ULCB_TestParse(ULCB_Context *ctx, const uint8_t *bytes, uint64_t nBytes, uint32_t nBlocks, float *coefs, uint32_t *blockBits);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,7 @@ static int do_enc(int argc, char **argv) {
 	struct ULC_EncoderState_t st;
 	st.RateHz = rate; st.nChan = nChan; st.BlockSize = N;
 	if(ULC_EncoderState_Init(&st) <= 0) { fprintf(stderr, "encoder init failed\n"); return 3; }
-	float *blk = malloc(sizeof(float) * N * nChan);
+	float *blk = aligned_alloc(64, sizeof(float) * N * nChan);   /* the tools align to 64 B (tools/ulc_Helper.h:6) */
 	for(size_t b = 0; b < nBlocks; b++) {
 		for(size_t i = 0; i < (size_t)N * nChan; i++) {
 			size_t s = b * (size_t)N * nChan + i;
@@ -83,7 +83,8 @@ static int do_dec(int argc, char **argv) {
 	struct ULC_DecoderState_t st;
 	st.nChan = nChan; st.BlockSize = N;
 	if(ULC_DecoderState_Init(&st) <= 0) { fprintf(stderr, "decoder init failed\n"); return 3; }
-	float *out = calloc(sizeof(float), (size_t)N * nChan);
+	float *out = aligned_alloc(64, sizeof(float) * (size_t)N * nChan);  /* AVX build stores with aligned moves */
+	memset(out, 0, sizeof(float) * (size_t)N * nChan);
 	size_t pos = 0; int dead = 0;
 	for(size_t b = 0; b < nBlocks; b++) {
 		int32_t bits = 0;

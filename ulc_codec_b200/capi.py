@@ -22,7 +22,7 @@ EXPORTS = (
     "ULC_DecoderState_Init", "ULC_DecoderState_Destroy", "ULC_DecodeBlock",
     "ULCB_ContextCreate", "ULCB_ContextDestroy", "ULCB_LastCudaError", "ULCB_ErrorString",
     "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_Sync", "ULCB_Stream",
-    "ULCB_LaunchCount", "ULCB_TestDCT4",
+    "ULCB_LaunchCount", "ULCB_TestDCT4", "ULCB_TestParse",
 )
 
 
@@ -64,6 +64,7 @@ def load():
     L.ULCB_LaunchCount.argtypes = [vp]
     L.ULCB_LaunchCount.restype = u64
     L.ULCB_TestDCT4.argtypes = [vp, vp, i32, i32]
+    L.ULCB_TestParse.argtypes = [vp, vp, u64, u32, vp, vp]
     L.ULC_DecoderState_Init.argtypes = [C.POINTER(ULC_DecoderState_t)]
     L.ULC_DecoderState_Destroy.argtypes = [C.POINTER(ULC_DecoderState_t)]
     L.ULC_DecoderState_Destroy.restype = None
@@ -155,6 +156,15 @@ class Context:
         rc = self.L.ULCB_DecodeStreamsDevice(self.h, n_streams, d_bytes, d_offs, d_nblocks or None, n_blocks_all,
                                              d_out, out_stride, _FMT[fmt], d_status or None, d_bits or None, bits_stride)
         _check(self.L, self.h, rc, "ULCB_DecodeStreamsDevice")
+
+    def test_parse(self, data: np.ndarray, n_blocks: int):
+        """(coefs float32[nBlocks, nChan*N], bits uint32[nBlocks]) of one stream: parse + dequantise + noise only."""
+        data = np.ascontiguousarray(data, np.uint8)
+        coefs = np.zeros((n_blocks, self.n_chan * self.block_size), np.float32)
+        bits = np.zeros(n_blocks, np.uint32)
+        rc = self.L.ULCB_TestParse(self.h, data.ctypes.data, len(data), n_blocks, coefs.ctypes.data, bits.ctypes.data)
+        _check(self.L, self.h, rc, "ULCB_TestParse")
+        return coefs, bits
 
     def test_dct4(self, x: np.ndarray) -> np.ndarray:
         buf = np.ascontiguousarray(x, np.float32).copy()

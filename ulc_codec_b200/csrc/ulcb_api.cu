@@ -220,7 +220,7 @@ int ULCB_Sync(ULCB_Context *ctx) {
 static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs,
                          const uint32_t *dNBlocks, uint32_t nBlocksAll, void *dOut, uint64_t outStrideElems,
                          int format, int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride,
-                         UlcbStreamState *state, float *statePend) {
+                         UlcbStreamState *state, float *statePend, float *dbgCoefs = nullptr) {
     if (!ctx || nStreams < 0 || !dBytes || !dStreamOffs || !dOut) return ULCB_E_PARAM;
     if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
@@ -231,7 +231,7 @@ static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes,
     a.bytes = dBytes; a.streamOffs = dStreamOffs; a.nBlocks = dNBlocks;
     a.out = dOut; a.outStride = outStrideElems;
     a.status = dStatus; a.bytesConsumed = nullptr; a.blockBits = dBlockBits; a.bitsStride = bitsStride;
-    a.state = state; a.statePend = statePend;
+    a.state = state; a.statePend = statePend; a.dbgCoefs = dbgCoefs;
     CK(ctx, ulcb_decode_launch(a, ctx->nChan, format == ULCB_FMT_PCM16, nStreams, ctx->stream));
     ctx->launches++;
     return ULCB_OK;
@@ -277,6 +277,30 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) CK(ctx, cudaMemcpyAsync(status, aux + offSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
     if (blockBits) CK(ctx, cudaMemcpyAsync(blockBits, aux + offBits, sizeof(uint32_t) * nStreams * bitsStride, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ULCB_OK;
+}
+
+int ULCB_TestParse(ULCB_Context *ctx, const uint8_t *bytes, uint64_t nBytes, uint32_t nBlocks, float *coefs, uint32_t *blockBits) {
+    if (!ctx || !bytes || !coefs || !blockBits || nBlocks < 1) return ULCB_E_PARAM;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t per = (size_t)ctx->nChan * ctx->N;
+    const size_t cBytes = sizeof(float) * per * nBlocks, auxBytes = 2 * sizeof(uint64_t) + sizeof(uint32_t) * nBlocks;
+    int rc;
+    if ((rc = grow(ctx, &ctx->dIn, &ctx->dInCap, nBytes + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, 2 * cBytes))) return rc;
+    if ((rc = grow(ctx, &ctx->dAux, &ctx->dAuxCap, auxBytes))) return rc;
+    uint64_t offs[2] = {0, nBytes};
+    CK(ctx, cudaMemcpyAsync(ctx->dIn, bytes, nBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemsetAsync((char *)ctx->dIn + nBytes, 0, 64, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(ctx->dAux, offs, sizeof offs, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *dBits = (uint32_t *)((char *)ctx->dAux + 2 * sizeof(uint64_t));
+    float *dCoefs = (float *)((char *)ctx->dOut + cBytes);
+    rc = decode_device(ctx, 1, (const uint8_t *)ctx->dIn, (const uint64_t *)ctx->dAux, nullptr, nBlocks, ctx->dOut, per * nBlocks,
+                       ULCB_FMT_FLOAT32, nullptr, dBits, nBlocks, nullptr, nullptr, dCoefs);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(coefs, dCoefs, cBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(blockBits, dBits, sizeof(uint32_t) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return ULCB_OK;
 }

@@ -23,6 +23,7 @@
 //   4. M/S undo, interleave, float or PCM16 out (ulcDecoder.c:281-297, tools/WavIO_Helper.c:57-63).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "ulcb_dct.cuh"
 #include "ulcb_decode.h"
 
@@ -199,7 +200,7 @@ __device__ void resolve_chain(const Smem<NCH> &sm, int tp, int remain, int qcur,
     int segPh[8], segC[8], segD[8], segQ[8];
     {
         int ph = phIn;
-        bool on = (lane >= lane0) && (phIn != 7);
+        bool on = (lane == lane0) || (lane > lane0 && phIn != 7);   // NB: 7 is also a legal START offset for lane0
         for (int k = 0; k < 8; k++) {
             int s = lane * 8 + k;
             segPh[k] = -1; segC[k] = locCoefs; segD[k] = locDraws; segQ[k] = locQ;
@@ -413,6 +414,12 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                                 if (tid < 32) resolve_chain<NCH>(sm, tp, remain, q, sub0 + (S - remain), (int)blkDraws);
                                 __syncthreads();
                                 int sEnd = sm.ctl[C_SEND];
+#ifdef ULCB_DEBUG_PARSE
+                                if (tid == 0 && args.dbgCoefs && blk <= 2)
+                                    printf("blk %d ch %d S %d page %lld tp %d remain %d q %d base %d | sEnd %d endpos %d kind %d cdone %d ddone %d ok %d exit %d sumc %d\n",
+                                           blk, c, S, curPage, tp, remain, q, sub0 + (S - remain), sEnd, sm.ctl[C_ENDPOS], sm.ctl[C_ENDKIND],
+                                           sm.ctl[C_ENDCOEFS], sm.ctl[C_ENDDRAWS], sm.ctl[C_OK], sm.ctl[C_EXITPH], sm.ctl[C_SUMCOEFS]);
+#endif
                                 if (!sm.ctl[C_OK]) { ok = false; break; }
                                 emit_chain<NCH>(sm, tp, sEnd < 0 ? PAGE_WORDS : sEnd, sm.ctl[C_ENDPOS], maxRuns, drawBase);
                                 if (sEnd >= 0) {
@@ -493,6 +500,10 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                 }
             }
             __syncthreads();
+            if (args.dbgCoefs) {
+                float *dc = args.dbgCoefs + ((size_t)stream * args.nBlocksAll + blk) * NCH * N;
+                for (int i = tid; i < NCH * N; i += nthr) dc[i] = sm.buf[i];
+            }
 
             // ---------------- inverse transform, sub-block by sub-block ----------------
             {

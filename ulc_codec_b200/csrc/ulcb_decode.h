@@ -28,6 +28,7 @@ struct UlcbDecodeArgs {
     uint64_t        bitsStride;
     UlcbStreamState *state;            // [nStreams] nullable: carry state across calls
     float          *statePend;         // [nStreams][nChan*N/2]
+    float          *dbgCoefs;          // test hook: [nStreams][nBlocksAll][nChan*N] dequantised coefficients; nullable
 };
 
 size_t      ulcb_decode_smem_bytes(int N, int nChan);
