@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200-native ulc-codec hot path.
+
+Workload at N=1 (BASELINE.json configs[1], the configuration the metric is quoted on):
+    batched decode-only, 4096 x 60 s stereo 44.1 kHz streams at 128 kbps CBR, BlockSize 2048, PCM16 out.
+A "step" is one pass of the decoder over all streams of the rank.  Streams shard across ranks with no
+data-path collective; per-GPU work is fixed as N grows ("weak").
+
+Arms
+    (default)          the CUDA path through the C ABI (libulcb200.so); `value` = inputs resident in HBM,
+                       `e2e` = same metric through ULCB_DecodeStreams with HOST buffers (H2D + D2H timed).
+    --impl reference   the reference's own CPU decoder (oracle/_ref/ulcdecodetool_avx, unmodified reference
+                       compiled by oracle/Makefile) on all host cores; falls back to the oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATE, NCH, N = 44100, 2, 2048
+STREAM_SECONDS = 60
+BLOCKS_PER_STREAM = (STREAM_SECONDS * RATE + N - 1) // N + 2        # 1294, tools/ulcEncodeTool.c:98
+METRIC = "audio-seconds/sec (xrealtime) decode, batched 60 s stereo 44.1 kHz streams @128 kbps CBR, BlockSize 2048, PCM16 out"
+POOL_FIXTURE = "music_cbr128_bs2048"
+
+
+# ------------------------------------------------------------------------------------------------
+# input construction: real reference-encoded blocks (tests/golden), recombined per stream
+# ------------------------------------------------------------------------------------------------
+def load_pool():
+    from tests.fixtures import load_golden_stream
+    g = load_golden_stream(POOL_FIXTURE)
+    offs = np.concatenate([[0], np.cumsum(g["block_bytes"])]).astype(np.int64)
+    blocks = [g["data"][offs[i]:offs[i + 1]] for i in range(2, len(offs) - 1)]   # skip the two lead-in blocks
+    return blocks
+
+
+def build_stream(blocks, stream_id: int, n_blocks: int = BLOCKS_PER_STREAM) -> np.ndarray:
+    """Any sequence of valid blocks is a valid stream (blocks are self-delimiting, FormatSpecs.md), so a
+    stream is n_blocks blocks drawn from the pool by a per-stream hash.  ~741 B/block like a real CBR-128 file."""
+    rng = np.random.default_rng(0x9E3779B9 * (stream_id + 1) & 0xFFFFFFFF)
+    idx = rng.integers(0, len(blocks), n_blocks)
+    return np.concatenate([blocks[i] for i in idx])
+
+
+def ulc_container(stream: np.ndarray, n_blocks: int) -> bytes:
+    """24-byte .ulc header + payload (tools/ulc_Helper.h:10-20)."""
+    hdr = struct.pack("<IHHIIHHI", 0x32434C55, N, 4096, n_blocks, RATE, NCH, 128, 24)
+    return hdr + stream.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_decode(blocks, target_seconds: float = 12.0):
+    """Times the reference's own decoder on all host cores, one process per core over disjoint streams.
+    Returns dict(value=xrealtime, cores, kind, sample, wall_s)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    tool = os.path.join(ROOT, "oracle", "_ref", "ulcdecodetool_avx")
+    if os.access(tool, os.X_OK):
+        # ~500x realtime per core => STREAMS_PER_FILE 60 s streams take about target_seconds on one core
+        per_file = max(1, int(target_seconds * 450 / STREAM_SECONDS))
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        with tempfile.TemporaryDirectory(dir=shm) as td:
+            nb = BLOCKS_PER_STREAM * per_file
+            files = []
+            base = [build_stream(blocks, 100000 + i) for i in range(min(cores, 8))]
+            for c in range(cores):
+                s = np.concatenate([base[(c + k) % len(base)] for k in range(per_file)])
+                path = os.path.join(td, f"s{c}.ulc")
+                with open(path, "wb") as f:
+                    f.write(ulc_container(s, nb))
+                files.append(path)
+            t0 = time.perf_counter()
+            procs = [subprocess.Popen([tool, p, "/dev/null"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for p in files]
+            rcs = [p.wait() for p in procs]
+            wall = time.perf_counter() - t0
+        if any(rcs):
+            raise RuntimeError(f"reference decode tool failed: {rcs}")
+        audio = cores * nb * N / RATE
+        return {"value": audio / wall, "unit": "xrealtime", "cores": cores, "kind": "reference", "wall_s": wall,
+                "sample": f"{cores} procs x {per_file} x 60 s streams, oracle/_ref/ulcdecodetool_avx (unmodified reference, AVX/FMA build), PCM16 to /dev/null"}
+    # fallback: the oracle port, single core
+    from oracle import oracle
+    s = build_stream(blocks, 100000)
+    nb = 300
+    t0 = time.perf_counter()
+    oracle.Decoder(NCH, N).decode_stream(s, nb)
+    wall = time.perf_counter() - t0
+    return {"value": nb * N / RATE / wall, "unit": "xrealtime", "cores": 1, "kind": "port", "wall_s": wall,
+            "sample": f"{nb} blocks of one stream, oracle/ulc_oracle.c via ctypes (float out, no PCM16 conversion)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (default = BASELINE configs[1])")
+    ap.add_argument("--e2e-streams", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"workload": "configs[1]: batched decode-only, 60 s stereo streams @128 kbps CBR, BlockSize 2048, PCM16 out",
+           "streams_per_gpu": args.streams, "blocks_per_stream": BLOCKS_PER_STREAM, "rate_hz": RATE, "n_chan": NCH, "block_size": N,
+           "input": "reference-encoded (oracle/_ref scalar build) CBR-128 blocks of the synthetic music corpus; each stream = 1294 blocks "
+                    "drawn per stream from the 431-block golden pool tests/golden/music_cbr128_bs2048.npz; 256 distinct streams replicated",
+           "l2": "inputs+outputs per step (>40 GB) far exceed the 126 MB L2; no flush needed"}
+    blocks = load_pool()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_reference_decode(blocks, target_seconds=4.0)
+            if i >= args.warmup:
+                vals.append(r)
+        wall = float(np.mean([v["wall_s"] for v in vals]))
+        value = float(np.mean([v["value"] for v in vals]))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "xrealtime", "n_gpus": 0, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": value, "unit": "xrealtime", "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
+                "e2e": {"value": value, "unit": "xrealtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ulc_codec_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # ---- inputs (untimed): 256 distinct streams, replicated in a rank-dependent order ----
+    n_streams = args.streams
+    n_distinct = min(256, n_streams)
+    distinct = [build_stream(blocks, rank * 100003 + d) for d in range(n_distinct)]
+    order = [(s * 7 + s // n_distinct) % n_distinct for s in range(n_streams)]
+    lens = np.array([len(distinct[o]) for o in order], np.uint64)
+    offs = np.zeros(n_streams + 1, np.uint64)
+    offs[1:] = np.cumsum(lens)
+    total_in = int(offs[-1])
+    d_dist = [torch.from_numpy(d).to(dev) for d in distinct]
+    d_bytes = torch.empty(total_in + 64, dtype=torch.uint8, device=dev)
+    for s, o in enumerate(order):
+        d_bytes[int(offs[s]):int(offs[s + 1])] = d_dist[o]
+    d_bytes[total_in:] = 0
+    del d_dist
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    stride = BLOCKS_PER_STREAM * N * NCH
+    d_out = torch.empty(n_streams * stride, dtype=torch.int16, device=dev)
+    d_status = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+
+    ctx = capi.Context(RATE, NCH, N, max_blocks=BLOCKS_PER_STREAM, device=local)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+
+    def step():
+        ctx.decode_streams_device(n_streams, d_bytes.data_ptr(), d_offs.data_ptr(), BLOCKS_PER_STREAM, d_out.data_ptr(), stride,
+                                  "pcm16", d_status=d_status.data_ptr())
+
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+        t_all0.record(ext)
+        for a, b in evs:
+            a.record(ext); step(); b.record(ext)
+        t_all1.record(ext)
+        ctx.sync()
+        torch.cuda.synchronize()
+    launches = ctx.launches - l0
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        dist.barrier()
+    assert int((d_status != -1).sum().item()) == 0, "decode reported corrupt streams"
+    ms_per_step = total_ms / args.steps
+    audio_per_step = world * n_streams * BLOCKS_PER_STREAM * N / RATE
+    value = audio_per_step / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes / launch duration ----
+    algo_bytes = total_in + n_streams * stride * 2                 # bytes_in + PCM16 out  
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (kern_ms / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": "ulcb_decode_kernel<2,true,256>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)",
+            "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kern_ms, "traffic": None}
+
+    # ---- e2e: through the host-pointer C-ABI call, pinned host buffers, copies inside the timed region ----
+    e2e = None
+    if rank == 0 or world > 1:
+        ne = min(args.e2e_streams, n_streams)
+        h_streams = [distinct[o] for o in order[:ne]]
+        h_data, h_offs = capi.pack_streams(h_streams)
+        pin_in = torch.empty(len(h_data), dtype=torch.uint8).pin_memory()
+        pin_in.numpy()[:] = h_data
+        pin_out = torch.empty(ne * stride, dtype=torch.int16).pin_memory()
+        h_status = np.zeros(ne, np.int32)
+
+        def e2e_step():
+            rc = ctx.L.ULCB_DecodeStreams(ctx.h, ne, pin_in.data_ptr(), h_offs.ctypes.data, None, BLOCKS_PER_STREAM,
+                                          pin_out.data_ptr(), stride, capi.FMT_PCM16, h_status.ctypes.data, None, 0)
+            assert rc == 0, rc
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        reps = max(2, args.steps // 2)
+        for _ in range(reps):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / reps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert (h_status == -1).all()
+        e2e = {"value": world * ne * BLOCKS_PER_STREAM * N / RATE / dt, "unit": "xrealtime", "h2d_bytes_per_step": int(len(h_data)),
+               "d2h_bytes_per_step": int(ne * stride * 2), "streams_per_gpu": ne, "ms_per_step": dt * 1e3,
+               "api": "ULCB_DecodeStreams (host pointers, pinned), bounded to e2e_streams streams per GPU"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        c = cpu_reference_decode(blocks)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {"metric": METRIC, "value": value, "unit": "xrealtime", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
