@@ -323,7 +323,7 @@ __device__ void emit_chain(const Smem<NCH> &sm, int tp, int endSeg, int endPos, 
 
 // ------------------------------------------------------------------------------------------------
 template <int NCH, bool PCM16, int NTHR>
-__global__ void __launch_bounds__(NTHR)
+__global__ void __launch_bounds__(NTHR, (NTHR <= 256 ? 3 : 1))
 ulcb_decode_kernel(UlcbDecodeArgs args) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const UlcbTables &tb = args.tb;
@@ -509,7 +509,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
             {
                 int off = 0, j = 0;
                 for (unsigned pat = kLayout[wc >> 4];; j++) {
-                    const int sh = pat & 7, S = N >> sh, hS = S >> 1;
+                    const int sh = pat & 7, S = N >> sh, hS = S >> 1, lgHS = tb.log2N - sh - 1;
                     dct4_inplace<MAXPAIRS>(sm.buf + off, N, NCH, S, sh, tb);
 
                     int ov = S;
@@ -526,7 +526,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                     for (int r = 0; r < MAXU; r++) {
                         int idx = tid + r * nthr;
                         if (idx < NCH * hS) {
-                            int c = idx / hS, i = idx - c * hS;
+                            int c = idx >> lgHS, i = idx & (hS - 1);
                             const float *t = sm.buf + c * N + off;
                             float a = sm.pend[c * H + held + i], b = t[hS + i];
                             if (i < flat) { uLo[r] = a; uHi[r] = b; }
@@ -543,7 +543,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                     for (int r = 0; r < MAXU; r++) {
                         int idx = tid + r * nthr;
                         if (idx < NCH * hS) {
-                            int c = idx / hS, i = idx - c * hS;
+                            int c = idx >> lgHS, i = idx & (hS - 1);
                             float *t = sm.buf + c * N + off;
                             t[i] = uLo[r]; t[S - 1 - i] = uHi[r];
                             sm.pend[c * H + held + i] = tn[r];
@@ -633,6 +633,8 @@ template <int NCH, int NTHR>
 static cudaError_t launch_t(const UlcbDecodeArgs &args, int pcm16, int gridBlocks, size_t smem, cudaStream_t stream) {
     void (*k)(UlcbDecodeArgs) = pcm16 ? ulcb_decode_kernel<NCH, true, NTHR> : ulcb_decode_kernel<NCH, false, NTHR>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     k<<<gridBlocks, NTHR, smem, stream>>>(args);
     return cudaGetLastError();
