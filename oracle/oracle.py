@@ -49,6 +49,18 @@ def lib():
         L.ulco_decode_block.argtypes = [C.c_void_p, _f32p, C.c_void_p]
         L.ulco_decode_block.restype = C.c_int
         L.ulco_float_to_pcm16.argtypes = [_i16p, _f32p, C.c_size_t]
+        L.ulco_encoder_new.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ulco_encoder_new.restype = C.c_void_p
+        L.ulco_encoder_free.argtypes = [C.c_void_p]
+        L.ulco_encoder_window_ctrl.argtypes = [C.c_void_p]
+        L.ulco_encoder_complexity.argtypes = [C.c_void_p]
+        L.ulco_encoder_complexity.restype = C.c_float
+        L.ulco_encoder_coefs.argtypes = [C.c_void_p]
+        L.ulco_encoder_coefs.restype = C.POINTER(C.c_float)
+        L.ulco_encoder_ranks.argtypes = [C.c_void_p]
+        L.ulco_encoder_ranks.restype = C.POINTER(C.c_int)
+        L.ulco_encode_block.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, C.POINTER(C.POINTER(C.c_uint8))]
+        L.ulco_encode_block.restype = C.c_int
         _lib = L
     return _lib
 
@@ -139,3 +151,63 @@ class Decoder:
             out[b * self.block_size:(b + 1) * self.block_size] = blk
             pos += (nb + 7) // 8
         return out, bits
+
+
+MODES = {"vbr": 0, "cbr": 1, "abr": 2}
+
+
+class Encoder:
+    """Streaming encoder with the semantics of a fresh ULC_EncoderState_Init + ULC_EncodeBlock_{VBR,CBR,ABR}."""
+
+    def __init__(self, rate_hz: int = 44100, n_chan: int = 2, block_size: int = 2048):
+        self.rate_hz, self.n_chan, self.block_size = rate_hz, n_chan, block_size
+        self._h = lib().ulco_encoder_new(rate_hz, n_chan, block_size)
+        if not self._h:
+            raise ValueError("bad encoder parameters")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ulco_encoder_free(self._h)
+            self._h = None
+
+    def encode_block(self, pcm_f32: np.ndarray, mode: str, param: float, avg_complexity: float = 0.0) -> bytes:
+        out = C.POINTER(C.c_uint8)()
+        bits = lib().ulco_encode_block(self._h, np.ascontiguousarray(pcm_f32, np.float32).reshape(-1), MODES[mode],
+                                       param, avg_complexity, C.byref(out))
+        return C.string_at(out, bits // 8)
+
+    @property
+    def window_ctrl(self) -> int:
+        return lib().ulco_encoder_window_ctrl(self._h)
+
+    @property
+    def complexity(self) -> float:
+        return float(lib().ulco_encoder_complexity(self._h))
+
+    def coefs(self) -> np.ndarray:
+        n = self.n_chan * self.block_size
+        return np.ctypeslib.as_array(lib().ulco_encoder_coefs(self._h), (n,)).copy()
+
+    def ranks(self) -> np.ndarray:
+        n = self.n_chan * self.block_size
+        return np.ctypeslib.as_array(lib().ulco_encoder_ranks(self._h), (n,)).copy()
+
+    def encode_stream(self, pcm16: np.ndarray, mode: str, param: float, avg_complexity: float = 0.0, dump: bool = False):
+        """pcm16: int16[nSamples, nChan]; PCM16 -> float by x*2^-15 (tools/WavIO_Helper.c:49-55), zero padded,
+        nBlocks = ceil(n/N)+2 (tools/ulcEncodeTool.c:98).  Returns dict(data, block_bytes, window_ctrl, complexity[, coefs, ranks])."""
+        N, Cn = self.block_size, self.n_chan
+        ns = len(pcm16)
+        nb = (ns + N - 1) // N + 2
+        x = np.zeros((nb * N, Cn), np.float32)
+        x[:ns] = pcm16.astype(np.float32) * np.float32(2.0 ** -15)
+        chunks, sizes, wcs, cxs, coefs, ranks = [], [], [], [], [], []
+        for b in range(nb):
+            by = self.encode_block(x[b * N:(b + 1) * N], mode, param, avg_complexity)
+            chunks.append(by); sizes.append(len(by)); wcs.append(self.window_ctrl); cxs.append(self.complexity)
+            if dump:
+                coefs.append(self.coefs()); ranks.append(self.ranks())
+        r = dict(data=np.frombuffer(b"".join(chunks), np.uint8).copy(), block_bytes=np.array(sizes, np.uint32),
+                 window_ctrl=np.array(wcs, np.int32), complexity=np.array(cxs, np.float32))
+        if dump:
+            r["coefs"] = np.stack(coefs); r["ranks"] = np.stack(ranks)
+        return r

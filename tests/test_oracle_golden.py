@@ -32,3 +32,20 @@ def test_corpus_is_deterministic():
 def test_pcm16_rule():
     x = np.array([0.0, 1.0, -1.0, 0.5 / 32768, 1.5 / 32768, 2.5 / 32768, -0.5 / 32768, 0.99999], np.float32)
     assert oracle.float_to_pcm16(x).tolist() == [0, 32767, -32768, 0, 2, 2, 0, 32767]   # round-half-even, clamped
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_oracle_encoder_matches_reference_golden(name):
+    """The encoder restatement reproduces the reference encoder's bytes, window decisions, complexity,
+    MDCT coefficients and ranks (hashes) for every golden case - VBR, CBR and two-pass ABR."""
+    from tests.fixtures import golden_pcm
+    g = load_golden_stream(name)
+    enc = oracle.Encoder(g["rate_hz"], g["n_chan"], g["block_size"]).encode_stream(
+        golden_pcm(g), g["mode"], g["param"], g["avg_complexity"], dump=True)
+    assert np.array_equal(enc["block_bytes"], g["block_bytes"])
+    assert np.array_equal(enc["data"], g["data"])
+    assert np.array_equal(enc["window_ctrl"], g["window_ctrl"])
+    assert np.array_equal(enc["complexity"], g["complexity"])
+    assert np.array_equal(enc["coefs"][:6], g["coefs_head"])
+    assert sha(enc["coefs"]) == g["coefs_sha256"]
+    assert sha(enc["ranks"]) == g["ranks_sha256"]

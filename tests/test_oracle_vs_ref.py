@@ -59,3 +59,26 @@ def test_decoder_mono_and_corrupt():
     ref, rbits = refbin.decode(bad, 1, n_chan=1)
     out, bits = oracle.Decoder(1, 2048).decode_stream(bad, 1)
     assert rbits[0] == bits[0]
+
+
+@pytest.mark.parametrize("kind,bs,mode,param,avgc", [
+    ("music", 2048, "vbr", 50.0, 0.0), ("music", 2048, "cbr", 128.0, 0.0), ("transient", 2048, "vbr", 75.0, 0.0),
+    ("transient", 256, "cbr", 64.0, 0.0), ("transient", 8192, "vbr", 40.0, 0.0), ("music", 512, "abr", 96.0, 0.8)])
+def test_encoder_bit_identical(kind, bs, mode, param, avgc):
+    pcm = corpus.generate(21, 44100 * 3, kind)
+    ref = refbin.encode(pcm, mode, param, avg_complexity=avgc, block_size=bs, dump=True)
+    o = oracle.Encoder(44100, 2, bs).encode_stream(pcm, mode, param, avgc, dump=True)
+    assert np.array_equal(o["data"], ref.data)
+    assert np.array_equal(o["block_bytes"], ref.block_bytes)
+    assert np.array_equal(o["window_ctrl"], ref.window_ctrl)
+    assert np.array_equal(o["complexity"], ref.complexity)
+    assert np.array_equal(o["coefs"], ref.coefs)
+    assert np.array_equal(o["ranks"], ref.ranks)
+
+
+def test_encoder_mono_and_silence():
+    pcm = corpus.generate(22, 30000, "music")[:, :1]
+    pcm[8000:16000] = 0                              # digital silence: -inf keys, silent sub-blocks (Eh,Fh)
+    ref = refbin.encode(pcm, "vbr", 70.0, dump=True)
+    o = oracle.Encoder(44100, 1, 2048).encode_stream(pcm, "vbr", 70.0, dump=True)
+    assert np.array_equal(o["data"], ref.data) and np.array_equal(o["ranks"], ref.ranks)
