@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------ */
-/* 1. libulc drop-in (decoder half; encoder half is declared further down when built)          */
+/* 1. libulc drop-in                                                                           */
 /* ------------------------------------------------------------------------------------------ */
 
 /* replaces: struct ULC_DecoderState_t, /root/reference/include/ulcDecoder.h:13-32.
@@ -59,6 +59,47 @@ void ULC_DecoderState_Destroy(struct ULC_DecoderState_t *State);
  * stream buffer guarantee, tools/ulcDecodeTool.c:79-81).  Returns bits consumed, 0 on a corrupt
  * block.  Unlike the reference, the noise RNG belongs to the state, not to the process. */
 int ULC_DecodeBlock(struct ULC_DecoderState_t *State, float *DstData, const void *SrcBuffer);
+
+/* replaces: struct ULC_TransientData_t / struct ULC_EncoderState_t, /root/reference/include/ulcEncoder.h:44-78.
+ * Field order and types are identical (default feature flags: ULC_USE_NOISE_CODING = 1).  BufferData
+ * is the library's handle (device state + pinned staging); TransformTemp points at the pinned host
+ * copy of the last encoded block (the reference returns a pointer into TransformTemp too); the other
+ * buffer pointers are NULL because those buffers live on the GPU.  WindowCtrl, NextWindowCtrl and
+ * BlockComplexity are refreshed after every ULC_EncodeBlock_* call (tools/ulcEncodeTool.c:164 reads
+ * BlockComplexity). */
+struct ULC_TransientData_t { float Sum, SumW; };
+struct ULC_EncoderState_t {
+	int    RateHz;
+	int    nChan;
+	int    BlockSize;
+	int    WindowCtrl;
+	int    NextWindowCtrl;
+	float  BlockComplexity;
+	float  TransientFilter[3];
+	void  *BufferData;
+	float *SampleBuffer;
+	float *TransformBuffer;
+	float *TransformNoise;
+	float *TransformFwdLap;
+	float *TransformTemp;
+	int   *TransformIndex;
+	struct ULC_TransientData_t *TransientBuffer;
+};
+
+/* replaces: ULC_EncoderState_Init, include/ulcEncoder.h:85, libulc/ulcEncoder.c:25-80.
+ * Returns 1 on success, -1 on bad parameters, unsupported configuration, allocation failure or no GPU. */
+int ULC_EncoderState_Init(struct ULC_EncoderState_t *State);
+
+/* replaces: ULC_EncoderState_Destroy, include/ulcEncoder.h:88, libulc/ulcEncoder.c:83-88. */
+void ULC_EncoderState_Destroy(struct ULC_EncoderState_t *State);
+
+/* replace: ULC_EncodeBlock_CBR/_ABR/_VBR, include/ulcEncoder.h:135-137, libulc/ulcEncoder.c:117-158.
+ * SrcData = BlockSize*nChan interleaved floats (libulc/ulcEncoder_BlockTransform.c:96-98).  Returns the
+ * encoded bytes of the PREVIOUS block (valid until the next call on this state) and its size in bits
+ * (a multiple of 8) in *Size (may be NULL); NULL on a CUDA failure. */
+const void *ULC_EncodeBlock_CBR(struct ULC_EncoderState_t *State, const float *SrcData, int *Size, float RateKbps);
+const void *ULC_EncodeBlock_ABR(struct ULC_EncoderState_t *State, const float *SrcData, int *Size, float RateKbps, float AvgComplexity);
+const void *ULC_EncodeBlock_VBR(struct ULC_EncoderState_t *State, const float *SrcData, int *Size, float Quality);
 
 /* ------------------------------------------------------------------------------------------ */
 /* 2. Batched-stream API                                                                       */
@@ -117,6 +158,42 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams,
 
 int ULCB_Sync(ULCB_Context *ctx);
 
+/* ---- batched encode ---- */
+enum { ULCB_MODE_VBR = 0, ULCB_MODE_CBR = 1, ULCB_MODE_ABR = 2 };
+typedef struct ULCB_EncodeParams {
+	int   mode;            /* ULCB_MODE_* */
+	float rate;            /* VBR: Quality (0,100]; CBR/ABR: RateKbps */
+	float avgComplexity;   /* ABR only (tools/ulcEncodeTool.c:42,158) */
+} ULCB_EncodeParams;
+
+/* Blocks the reference tool writes for a stream of nSamples sample points: ceil(n/BlockSize)+2
+ * (coding delay + MDCT delay, tools/ulcEncodeTool.c:98). */
+uint32_t ULCB_BlocksForSamples(uint64_t nSamples, int blockSize);
+
+/* Batched encode, DEVICE pointers, asynchronous on the context's stream.
+ *   dPcm          interleaved int16 (ULCB_FMT_PCM16, scaled by 2^-15 as tools/WavIO_Helper.c:49-55)
+ *                 or float samples, [stream][sample][chan]; inStrideElems elements between streams
+ *   dNSamples     [nStreams] valid sample points per stream (input is zero padded beyond, as
+ *                 tools/WavIO_Reader.c:142-145), or NULL = nBlocks*BlockSize
+ *   dNBlocks      [nStreams] blocks to produce per stream, or NULL to produce nBlocksAll for all.
+ *                 Block b of the output describes input block b-1 (libulc's one-block delay).
+ *   dOut          per stream an arena of outStrideBytes bytes; the stream's blocks are written back
+ *                 to back (exactly the .ulc payload, tools/ulcEncodeTool.c:162-168)
+ *   dBlockBytes   [nStreams][metaStride] bytes of each block; dComplexity / dWindowCtrl likewise
+ *                 (State->BlockComplexity / State->WindowCtrl after each call); each may be NULL
+ *   dTotalBytes   [nStreams] payload bytes; dStatus [nStreams] 0 = ok, 1 = arena too small (stream
+ *                 truncated at the first block that did not fit); each may be NULL */
+int ULCB_EncodeStreamsDevice(ULCB_Context *ctx, int nStreams, const void *dPcm, int format, const uint64_t *dNSamples,
+                             uint64_t inStrideElems, const uint32_t *dNBlocks, uint32_t nBlocksAll, const ULCB_EncodeParams *params,
+                             uint8_t *dOut, uint64_t outStrideBytes, uint32_t *dBlockBytes, float *dComplexity, int32_t *dWindowCtrl,
+                             uint64_t metaStride, uint64_t *dTotalBytes, int32_t *dStatus);
+
+/* Same with HOST pointers (metaStride = nBlocksAll).  Synchronous. */
+int ULCB_EncodeStreams(ULCB_Context *ctx, int nStreams, const void *pcm, int format, const uint64_t *nSamples,
+                       uint64_t inStrideElems, uint32_t nBlocksAll, const ULCB_EncodeParams *params,
+                       uint8_t *out, uint64_t outStrideBytes, uint32_t *blockBytes, float *complexity, int32_t *windowCtrl,
+                       uint64_t *totalBytes, int32_t *status);
+
 /* The CUDA stream (cudaStream_t, as an opaque pointer) the context launches on, so callers that
  * own device memory (e.g. through torch) can order their work against it. */
 void *ULCB_Stream(ULCB_Context *ctx);
@@ -128,6 +205,13 @@ uint64_t ULCB_LaunchCount(const ULCB_Context *ctx);
 int ULCB_TestDCT4(ULCB_Context *ctx, float *data, int size, int count);
 /* parse + dequantise + noise-fill only: coefs[nBlocks][nChan*blockSize], blockBits[nBlocks] for ONE stream */
 int ULCB_TestParse(ULCB_Context *ctx, const uint8_t *bytes, uint64_t nBytes, uint32_t nBlocks, float *coefs, uint32_t *blockBits);
+
+/* encode with per-block taps: coefs/keys/noise [nStreams][nBlocksAll][nChan*blockSize], mask [..][blockSize/2],
+ * ranks likewise (int32), counts [..][2] = {codeable coefficients, coefficients requested}; any tap may be NULL */
+int ULCB_TestEncode(ULCB_Context *ctx, int nStreams, const void *pcm, int format, const uint64_t *nSamples, uint64_t inStrideElems,
+                    uint32_t nBlocksAll, const ULCB_EncodeParams *params, uint8_t *out, uint64_t outStrideBytes,
+                    uint32_t *blockBytes, float *complexity, int32_t *windowCtrl,
+                    float *coefs, float *keys, float *noise, float *mask, int32_t *ranks, int32_t *counts);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,11 @@ def lib():
         L.ulco_encoder_coefs.restype = C.POINTER(C.c_float)
         L.ulco_encoder_ranks.argtypes = [C.c_void_p]
         L.ulco_encoder_ranks.restype = C.POINTER(C.c_int)
+        for nm in ("noise", "keys", "mask"):
+            getattr(L, "ulco_encoder_" + nm).argtypes = [C.c_void_p]
+            getattr(L, "ulco_encoder_" + nm).restype = C.POINTER(C.c_float)
+        L.ulco_encoder_n_nz.argtypes = [C.c_void_p]
+        L.ulco_encoder_n_out.argtypes = [C.c_void_p]
         L.ulco_encode_block.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, C.POINTER(C.POINTER(C.c_uint8))]
         L.ulco_encode_block.restype = C.c_int
         _lib = L
@@ -188,6 +193,25 @@ class Encoder:
         n = self.n_chan * self.block_size
         return np.ctypeslib.as_array(lib().ulco_encoder_coefs(self._h), (n,)).copy()
 
+    def noise(self) -> np.ndarray:
+        n = self.n_chan * self.block_size
+        return np.ctypeslib.as_array(lib().ulco_encoder_noise(self._h), (n,)).copy()
+
+    def keys(self) -> np.ndarray:
+        n = self.n_chan * self.block_size
+        return np.ctypeslib.as_array(lib().ulco_encoder_keys(self._h), (n,)).copy()
+
+    def mask(self) -> np.ndarray:
+        return np.ctypeslib.as_array(lib().ulco_encoder_mask(self._h), (self.block_size // 2,)).copy()
+
+    @property
+    def n_nz(self) -> int:
+        return lib().ulco_encoder_n_nz(self._h)
+
+    @property
+    def n_out(self) -> int:
+        return lib().ulco_encoder_n_out(self._h)
+
     def ranks(self) -> np.ndarray:
         n = self.n_chan * self.block_size
         return np.ctypeslib.as_array(lib().ulco_encoder_ranks(self._h), (n,)).copy()
@@ -201,13 +225,20 @@ class Encoder:
         x = np.zeros((nb * N, Cn), np.float32)
         x[:ns] = pcm16.astype(np.float32) * np.float32(2.0 ** -15)
         chunks, sizes, wcs, cxs, coefs, ranks = [], [], [], [], [], []
+        extra = {}
         for b in range(nb):
             by = self.encode_block(x[b * N:(b + 1) * N], mode, param, avg_complexity)
             chunks.append(by); sizes.append(len(by)); wcs.append(self.window_ctrl); cxs.append(self.complexity)
             if dump:
                 coefs.append(self.coefs()); ranks.append(self.ranks())
+                if dump == "all":
+                    extra.setdefault("noise", []).append(self.noise()); extra.setdefault("keys", []).append(self.keys())
+                    extra.setdefault("mask", []).append(self.mask()); extra.setdefault("n_nz", []).append(self.n_nz)
+                    extra.setdefault("n_out", []).append(self.n_out)
         r = dict(data=np.frombuffer(b"".join(chunks), np.uint8).copy(), block_bytes=np.array(sizes, np.uint32),
                  window_ctrl=np.array(wcs, np.int32), complexity=np.array(cxs, np.float32))
         if dump:
             r["coefs"] = np.stack(coefs); r["ranks"] = np.stack(ranks)
+            for k_, v_ in extra.items():
+                r[k_] = np.stack(v_) if np.ndim(v_[0]) else np.array(v_)
         return r

@@ -449,6 +449,8 @@ typedef struct {
 	float *lap;                   /* [C][N] (TransformFwdLap) */
 	float *tmp;                   /* [max(2,C)*N] (TransformTemp) - also the output byte buffer */
 	int   *rank;                  /* [C*N] keys as floats, then ranks (TransformIndex) */
+	float *dbg_key, *dbg_mask;    /* test taps: final sort keys [C*N], masking curve [N/2] */
+	int    dbg_n_nz, dbg_n_out;   /* test taps: codeable coefficients, coefficients requested from the last pass */
 } OracleEncoder;
 
 ORACLE_API void *ulco_encoder_new(int rate_hz, int n_chan, int block_size) {
@@ -464,17 +466,24 @@ ORACLE_API void *ulco_encoder_new(int rate_hz, int n_chan, int block_size) {
 	e->lap     = calloc(cn, sizeof(float));
 	e->tmp     = calloc((size_t)(n_chan < 2 ? 2 : n_chan) * block_size, sizeof(float));
 	e->rank    = calloc(cn, sizeof(int));
+	e->dbg_key = calloc(cn, sizeof(float));
+	e->dbg_mask = calloc(block_size/2, sizeof(float));
 	return e;
 }
 ORACLE_API void ulco_encoder_free(void *p) {
 	OracleEncoder *e = p;
 	if(!e) return;
-	free(e->samples); free(e->coef); free(e->noise); free(e->lap); free(e->tmp); free(e->rank); free(e);
+	free(e->samples); free(e->coef); free(e->noise); free(e->lap); free(e->tmp); free(e->rank); free(e->dbg_key); free(e->dbg_mask); free(e);
 }
 ORACLE_API int   ulco_encoder_window_ctrl(void *p) { return ((OracleEncoder*)p)->window_ctrl; }
 ORACLE_API float ulco_encoder_complexity(void *p)  { return ((OracleEncoder*)p)->complexity; }
 ORACLE_API const float *ulco_encoder_coefs(void *p) { return ((OracleEncoder*)p)->coef; }
 ORACLE_API const int   *ulco_encoder_ranks(void *p) { return ((OracleEncoder*)p)->rank; }
+ORACLE_API const float *ulco_encoder_noise(void *p) { return ((OracleEncoder*)p)->noise; }
+ORACLE_API const float *ulco_encoder_keys(void *p)  { return ((OracleEncoder*)p)->dbg_key; }
+ORACLE_API const float *ulco_encoder_mask(void *p)  { return ((OracleEncoder*)p)->dbg_mask; }
+ORACLE_API int ulco_encoder_n_nz(void *p)  { return ((OracleEncoder*)p)->dbg_n_nz; }
+ORACLE_API int ulco_encoder_n_out(void *p) { return ((OracleEncoder*)p)->dbg_n_out; }
 
 /* ulcHelper.h:127-136 */
 static float fast_log(float x) {
@@ -774,6 +783,9 @@ static int transform_block(OracleEncoder *e, const float *pcm) {
 	for(int c = 0; c < C; c++)                                     /* :337-345 */
 		for(int n = 0; n < N; n++)
 			key[c*N+n] = 2*key[c*N+n] + mask[n/2] + -0x1.62E430p0f*(c & 1);
+	memcpy(e->dbg_key, key, sizeof(float) * C * N);
+	memcpy(e->dbg_mask, mask, sizeof(float) * (N/2));
+	e->dbg_n_nz = n_nz;
 	rank_by_key(e->rank, (const float*)e->rank, (int*)e->tmp, C*N); /* :350-354 */
 	return n_nz;
 }
@@ -905,6 +917,7 @@ static void put_subblock(const OracleEncoder *e, NybWriter *w, int idx, int S, i
 }
 static int encode_pass(const OracleEncoder *e, uint8_t *dst, int n_out) {   /* :319-360 */
 	NybWriter w = { dst, 0 };
+	((OracleEncoder*)e)->dbg_n_out = n_out;
 	int wc = e->window_ctrl;
 	put(&w, wc);
 	if(wc & 8) put(&w, wc >> 4);

@@ -23,7 +23,26 @@ EXPORTS = (
     "ULCB_ContextCreate", "ULCB_ContextDestroy", "ULCB_LastCudaError", "ULCB_ErrorString",
     "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_Sync", "ULCB_Stream",
     "ULCB_LaunchCount", "ULCB_TestDCT4", "ULCB_TestParse",
+    "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
+    "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
 )
+
+MODE_VBR, MODE_CBR, MODE_ABR = 0, 1, 2
+_MODE = {"vbr": MODE_VBR, "cbr": MODE_CBR, "abr": MODE_ABR}
+
+
+class ULCB_EncodeParams(C.Structure):
+    _fields_ = [("mode", C.c_int), ("rate", C.c_float), ("avgComplexity", C.c_float)]
+
+
+class ULC_EncoderState_t(C.Structure):
+    """include/ulcb200.h (layout of /root/reference/include/ulcEncoder.h:47-78)."""
+    _fields_ = [("RateHz", C.c_int), ("nChan", C.c_int), ("BlockSize", C.c_int),
+                ("WindowCtrl", C.c_int), ("NextWindowCtrl", C.c_int), ("BlockComplexity", C.c_float),
+                ("TransientFilter", C.c_float * 3), ("BufferData", C.c_void_p),
+                ("SampleBuffer", C.c_void_p), ("TransformBuffer", C.c_void_p), ("TransformNoise", C.c_void_p),
+                ("TransformFwdLap", C.c_void_p), ("TransformTemp", C.c_void_p), ("TransformIndex", C.c_void_p),
+                ("TransientBuffer", C.c_void_p)]
 
 
 class ULC_DecoderState_t(C.Structure):
@@ -69,6 +88,21 @@ def load():
     L.ULC_DecoderState_Destroy.argtypes = [C.POINTER(ULC_DecoderState_t)]
     L.ULC_DecoderState_Destroy.restype = None
     L.ULC_DecodeBlock.argtypes = [C.POINTER(ULC_DecoderState_t), vp, vp]
+    f32, pp = C.c_float, C.POINTER(ULCB_EncodeParams)
+    L.ULCB_BlocksForSamples.argtypes = [u64, i32]
+    L.ULCB_BlocksForSamples.restype = u32
+    L.ULCB_EncodeStreamsDevice.argtypes = [vp, i32, vp, i32, vp, u64, vp, u32, pp, vp, u64, vp, vp, vp, u64, vp, vp]
+    L.ULCB_EncodeStreams.argtypes = [vp, i32, vp, i32, vp, u64, u32, pp, vp, u64, vp, vp, vp, vp, vp]
+    L.ULCB_TestEncode.argtypes = [vp, i32, vp, i32, vp, u64, u32, pp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    es = C.POINTER(ULC_EncoderState_t)
+    L.ULC_EncoderState_Init.argtypes = [es]
+    L.ULC_EncoderState_Destroy.argtypes = [es]
+    L.ULC_EncoderState_Destroy.restype = None
+    L.ULC_EncodeBlock_CBR.argtypes = [es, vp, C.POINTER(C.c_int), f32]
+    L.ULC_EncodeBlock_ABR.argtypes = [es, vp, C.POINTER(C.c_int), f32, f32]
+    L.ULC_EncodeBlock_VBR.argtypes = [es, vp, C.POINTER(C.c_int), f32]
+    for n in ("ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR"):
+        getattr(L, n).restype = vp
     _lib = L
     return L
 
@@ -157,6 +191,61 @@ class Context:
                                              d_out, out_stride, _FMT[fmt], d_status or None, d_bits or None, bits_stride)
         _check(self.L, self.h, rc, "ULCB_DecodeStreamsDevice")
 
+    # ---- host-pointer batched encode (ULCB_EncodeStreams) ----
+    def blocks_for(self, n_samples: int) -> int:
+        return int(self.L.ULCB_BlocksForSamples(int(n_samples), self.block_size))
+
+    def encode_streams(self, pcm_list, mode: str, rate: float, avg_complexity: float = 0.0, *, n_blocks: int | None = None,
+                       taps: bool = False, out_stride: int | None = None):
+        """pcm_list: list of int16 (or float32) arrays [nSamples, nChan] (all the same dtype).
+        Every stream is coded to n_blocks blocks (default: the tool's ceil(n/N)+2 of the longest stream), zero padded.
+        Returns dict(streams=[uint8 payload per stream], block_bytes[ns, nb], complexity[ns, nb], window_ctrl[ns, nb],
+        status[ns]) plus, with taps=True, coefs/keys/noise [ns, nb, nChan*N], mask [ns, nb, N/2], ranks, counts [ns, nb, 2]."""
+        ns, N, Cn = len(pcm_list), self.block_size, self.n_chan
+        isf = np.asarray(pcm_list[0]).dtype == np.float32
+        dt = np.float32 if isf else np.int16
+        lens = np.array([len(p) for p in pcm_list], np.uint64)
+        nb = int(n_blocks) if n_blocks else self.blocks_for(int(lens.max()))
+        stride = max(1, int(lens.max())) * Cn
+        buf = np.zeros((ns, stride), dt)
+        for i, p in enumerate(pcm_list):
+            a = np.ascontiguousarray(p, dt).reshape(-1)
+            buf[i, :len(a)] = a
+        ostride = int(out_stride) if out_stride else nb * int(self.L.ULCB_MaxBlockBytes(Cn, N))
+        out = np.zeros((ns, ostride), np.uint8)
+        bb = np.zeros((ns, nb), np.uint32); cx = np.zeros((ns, nb), np.float32); wc = np.zeros((ns, nb), np.int32)
+        tot = np.zeros(ns, np.uint64); status = np.zeros(ns, np.int32)
+        prm = ULCB_EncodeParams(_MODE[mode], float(rate), float(avg_complexity))
+        r = {}
+        if taps:
+            per = Cn * N
+            t = dict(coefs=np.zeros((ns, nb, per), np.float32), keys=np.zeros((ns, nb, per), np.float32),
+                     noise=np.zeros((ns, nb, per), np.float32), mask=np.zeros((ns, nb, N // 2), np.float32),
+                     ranks=np.zeros((ns, nb, per), np.int32), counts=np.zeros((ns, nb, 2), np.int32))
+            rc = self.L.ULCB_TestEncode(self.h, ns, buf.ctypes.data, FMT_FLOAT32 if isf else FMT_PCM16, lens.ctypes.data, stride, nb,
+                                        C.byref(prm), out.ctypes.data, ostride, bb.ctypes.data, cx.ctypes.data, wc.ctypes.data,
+                                        *(t[k].ctypes.data for k in ("coefs", "keys", "noise", "mask", "ranks", "counts")))
+            _check(self.L, self.h, rc, "ULCB_TestEncode")
+            tot = bb.sum(axis=1).astype(np.uint64)
+            r.update(t)
+        else:
+            rc = self.L.ULCB_EncodeStreams(self.h, ns, buf.ctypes.data, FMT_FLOAT32 if isf else FMT_PCM16, lens.ctypes.data, stride, nb,
+                                           C.byref(prm), out.ctypes.data, ostride, bb.ctypes.data, cx.ctypes.data, wc.ctypes.data,
+                                           tot.ctypes.data, status.ctypes.data)
+            _check(self.L, self.h, rc, "ULCB_EncodeStreams")
+        r.update(streams=[out[i, :int(tot[i])].copy() for i in range(ns)], block_bytes=bb, complexity=cx, window_ctrl=wc, status=status)
+        return r
+
+    def encode_streams_device(self, n_streams: int, d_pcm: int, fmt: str, in_stride: int, n_blocks_all: int, mode: str, rate: float,
+                              d_out: int, out_stride: int, *, avg_complexity: float = 0.0, d_nsamples: int = 0, d_nblocks: int = 0,
+                              d_block_bytes: int = 0, d_complexity: int = 0, d_window_ctrl: int = 0, meta_stride: int = 0,
+                              d_total: int = 0, d_status: int = 0):
+        prm = ULCB_EncodeParams(_MODE[mode], float(rate), float(avg_complexity))
+        rc = self.L.ULCB_EncodeStreamsDevice(self.h, n_streams, d_pcm, _FMT[fmt], d_nsamples or None, in_stride, d_nblocks or None,
+                                             n_blocks_all, C.byref(prm), d_out, out_stride, d_block_bytes or None, d_complexity or None,
+                                             d_window_ctrl or None, meta_stride, d_total or None, d_status or None)
+        _check(self.L, self.h, rc, "ULCB_EncodeStreamsDevice")
+
     def test_parse(self, data: np.ndarray, n_blocks: int):
         """(coefs float32[nBlocks, nChan*N], bits uint32[nBlocks]) of one stream: parse + dequantise + noise only."""
         data = np.ascontiguousarray(data, np.uint8)
@@ -192,6 +281,38 @@ class DropinDecoder:
     def close(self):
         if getattr(self, "ok", -1) >= 0:
             self.L.ULC_DecoderState_Destroy(C.byref(self.st))
+            self.ok = -1
+
+    __del__ = close
+
+
+class DropinEncoder:
+    """The reference's single-stream API (ULC_EncoderState_Init / ULC_EncodeBlock_*), through the drop-in symbols."""
+
+    def __init__(self, rate_hz: int = 44100, n_chan: int = 2, block_size: int = 2048):
+        self.L = load()
+        self.st = ULC_EncoderState_t()
+        self.st.RateHz, self.st.nChan, self.st.BlockSize = rate_hz, n_chan, block_size
+        self.ok = self.L.ULC_EncoderState_Init(C.byref(self.st))
+        if self.ok < 0:
+            raise UlcbError("ULC_EncoderState_Init returned -1")
+
+    def encode_block(self, pcm_f32: np.ndarray, mode: str, rate: float, avg_complexity: float = 0.0) -> bytes:
+        x = np.ascontiguousarray(pcm_f32, np.float32)
+        size = C.c_int(0)
+        if mode == "vbr":
+            p = self.L.ULC_EncodeBlock_VBR(C.byref(self.st), x.ctypes.data, C.byref(size), rate)
+        elif mode == "abr":
+            p = self.L.ULC_EncodeBlock_ABR(C.byref(self.st), x.ctypes.data, C.byref(size), rate, avg_complexity)
+        else:
+            p = self.L.ULC_EncodeBlock_CBR(C.byref(self.st), x.ctypes.data, C.byref(size), rate)
+        if not p:
+            raise UlcbError("ULC_EncodeBlock_* returned NULL")
+        return C.string_at(p, (size.value + 7) // 8)
+
+    def close(self):
+        if getattr(self, "ok", -1) >= 0:
+            self.L.ULC_EncoderState_Destroy(C.byref(self.st))
             self.ok = -1
 
     __del__ = close

@@ -12,6 +12,7 @@
 #include "../../include/ulcb200.h"
 #include "ulcb_dct.cuh"
 #include "ulcb_decode.h"
+#include "ulcb_encode.h"
 
 struct ULCB_Context {
     int device = 0, rateHz = 0, nChan = 0, N = 0;
@@ -20,6 +21,9 @@ struct ULCB_Context {
     int lastCuda = 0;
     uint64_t launches = 0;
     UlcbTables tb{};
+    UlcbEncTables etb{};
+    int smCount = 148;
+    float *encWs = nullptr; size_t encWsFloats = 0; int encGrid = 0;   // global workspace for large block sizes
     std::vector<void *> owned;          // device allocations freed with the context
     // staging for the host-pointer entry points (grown on demand)
     void *dIn = nullptr;  size_t dInCap = 0;
@@ -135,6 +139,66 @@ int build_tables(ULCB_Context *ctx) {
     return ULCB_OK;
 }
 
+// ---- encoder tables (host libm, so the constants are the reference's own) ----
+// libulc/ulcHelper.h:96-120
+float bark_to_line(float bark, float nyquist, int n) {
+    float hz = 600.0f * sinhf(bark * (1.0f / 6.0f));
+    return (hz * (float)n / nyquist) - 0.5f;
+}
+float line_to_bark(int line, float nyquist, int n) {
+    float hz = ((float)line + 0.5f) * nyquist / (float)n;
+    return 6.0f * asinhf(hz * (1.0f / 600.0f));
+}
+void band_edges(float b0, float b1, float nyq, int n, int *beg, int *end) {   // ulcEncoder_Psyopt.c:83-92,190-199
+    int lo = (int)floorf(bark_to_line(b0, nyq, n)), hi = (int)ceilf(bark_to_line(b1, nyq, n));
+    if (lo < 0) lo = 0;
+    if (hi < 0) hi = 0;
+    if (lo > n - 1) lo = n - 1;
+    if (hi > n) hi = n;
+    *beg = lo; *end = hi;
+}
+
+int build_enc_tables(ULCB_Context *ctx) {
+    const int N = ctx->N, rate = ctx->rateHz;
+    UlcbEncTables &t = ctx->etb;
+    t.N = N; t.log2N = ctx->tb.log2N; t.rateHz = rate;
+    t.rot = ctx->tb.win;
+    // one-pole coefficients of the transient detector (ulcEncoder_WindowControl.c:73-129), as (1 - k)
+    volatile float k;
+    k = expf(-0x1.CC845Cp6f / rate);  t.c1PostHp = 1.0f - k;
+    k = expf(-0x1.596344p8f / rate);  t.c1PostBp = 1.0f - k;
+    k = expf(-0x1.CC845Cp7f / rate);  t.c1PreHp  = 1.0f - k;
+    k = expf(-0x1.596344p8f / rate);  t.c1PreBp  = 1.0f - k;
+    k = expf(-0x1.1AF110p-6f * N / rate); t.c1Blk = 1.0f - k;
+    const float nyq = (float)rate * 0.5f;
+    std::vector<int16_t> edges(4 * 2 * ULCB_NBARK * 2);
+    std::vector<uint8_t> lband;
+    std::vector<float> lfrac;
+    for (int sh = 0; sh < 4; sh++) {
+        const int n = (N >> sh) / 2;
+        for (int kind = 0; kind < 2; kind++)
+            for (int b = 0; b < ULCB_NBARK; b++) {
+                int beg, end;
+                if (kind == 0) band_edges((float)b, (float)b + 2.0f, nyq, n, &beg, &end);
+                else           band_edges((float)b - 0.75f, (float)b + 0.25f, nyq, n, &beg, &end);
+                edges[((sh * 2 + kind) * ULCB_NBARK + b) * 2 + 0] = (int16_t)beg;
+                edges[((sh * 2 + kind) * ULCB_NBARK + b) * 2 + 1] = (int16_t)end;
+            }
+        t.lineOff[sh] = (int)lband.size();
+        for (int i = 0; i < n; i++) {                                  // ulcEncoder_Psyopt.c:136-152
+            float bb = line_to_bark(i, nyq, n);
+            int idx = (int)bb;
+            lband.push_back((uint8_t)(idx > 255 ? 255 : idx));
+            lfrac.push_back(bb - (float)idx);
+        }
+    }
+    int rc;
+    if ((rc = upload(ctx, edges, &t.edges))) return rc;
+    if ((rc = upload(ctx, lband, &t.lineBand))) return rc;
+    if ((rc = upload(ctx, lfrac, &t.lineFrac))) return rc;
+    return ULCB_OK;
+}
+
 int grow(ULCB_Context *ctx, void **p, size_t *cap, size_t need) {
     if (need <= *cap) return ULCB_OK;
     if (*p) cudaFree(*p);
@@ -190,7 +254,9 @@ int ULCB_ContextCreate(ULCB_Context **out, int device, int rateHz, int nChan, in
     ctx->device = device; ctx->rateHz = rateHz; ctx->nChan = nChan; ctx->N = blockSize; ctx->maxBlocks = maxBlocksPerStream;
     int rc = ULCB_OK;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) rc = ULCB_E_CUDA;
+    ctx->smCount = prop.multiProcessorCount;
     if (rc == ULCB_OK) rc = build_tables(ctx);
+    if (rc == ULCB_OK) rc = build_enc_tables(ctx);
     if (rc != ULCB_OK) { ULCB_ContextDestroy(ctx); return rc; }
     *out = ctx;
     return ULCB_OK;
@@ -204,6 +270,7 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->dIn) cudaFree(ctx->dIn);
     if (ctx->dOut) cudaFree(ctx->dOut);
     if (ctx->dAux) cudaFree(ctx->dAux);
+    if (ctx->encWs) cudaFree(ctx->encWs);
     delete ctx;
 }
 
@@ -395,6 +462,236 @@ int ULC_DecodeBlock(struct ULC_DecoderState_t *State, float *DstData, const void
     UlcbStreamState st;
     if (cudaMemcpy(&st, d->dState, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess) State->LastSubBlockSize = st.lastSubBlockSize;
     return (int)*d->hBits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched encoder
+// ------------------------------------------------------------------------------------------------
+uint32_t ULCB_BlocksForSamples(uint64_t nSamples, int blockSize) {       // tools/ulcEncodeTool.c:98
+    return (uint32_t)((nSamples + (uint64_t)blockSize - 1) / (uint64_t)blockSize) + 2u;
+}
+
+struct EncTaps { float *coefs, *keys, *noise, *mask; int32_t *ranks, *counts; };
+
+static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int format, const uint64_t *dNSamples,
+                         uint64_t inStrideElems, const uint32_t *dNBlocks, uint32_t nBlocksAll, const ULCB_EncodeParams *prm,
+                         uint8_t *dOut, uint64_t outStrideBytes, uint32_t *dBlockBytes, float *dComplexity, int32_t *dWindowCtrl,
+                         uint64_t metaStride, uint64_t *dTotalBytes, int32_t *dStatus,
+                         UlcbEncStreamState *state, float *stateSamples, const EncTaps *taps) {
+    if (!ctx || nStreams < 0 || !dPcm || !dOut || !prm) return ULCB_E_PARAM;
+    if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
+    if (prm->mode != ULCB_MODE_VBR && prm->mode != ULCB_MODE_CBR && prm->mode != ULCB_MODE_ABR) return ULCB_E_PARAM;
+    if (prm->mode == ULCB_MODE_VBR && !(prm->rate > 0.0f)) return ULCB_E_PARAM;
+    if (prm->mode == ULCB_MODE_ABR && !(prm->avgComplexity > 0.0f)) return ULCB_E_PARAM;
+    if (nStreams == 0) return ULCB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    UlcbEncodeArgs a{};
+    a.tb = ctx->etb;
+    a.nStreams = nStreams; a.nBlocksAll = (int)nBlocksAll; a.nBlocks = dNBlocks;
+    a.pcm = dPcm; a.pcmFloat = format == ULCB_FMT_FLOAT32; a.inStride = inStrideElems; a.nSamples = dNSamples;
+    a.mode = prm->mode;
+    a.param = prm->rate;
+    if (prm->mode == ULCB_MODE_VBR) {                                   // libulc/ulcEncoder.c:146-148, host libm logf
+        volatile float lg = logf(100.0f / prm->rate);
+        a.param = 0x1.E4EFB8p3f * lg;   // the reference writes 0x1.E4EFB7p3f (25 bits); gcc rounds it to this float
+    }
+    a.avgComplexity = prm->avgComplexity;
+    a.out = dOut; a.outStride = outStrideBytes; a.blockBytes = dBlockBytes; a.complexity = dComplexity; a.windowCtrl = dWindowCtrl;
+    a.metaStride = metaStride; a.totalBytes = dTotalBytes; a.status = dStatus;
+    a.state = state; a.stateSamples = stateSamples;
+    if (taps) { a.dbgCoefs = taps->coefs; a.dbgKeys = taps->keys; a.dbgNoise = taps->noise; a.dbgMask = taps->mask; a.dbgRanks = taps->ranks; a.dbgCounts = taps->counts; }
+    int grid = nStreams;
+    if (ulcb_encode_uses_global_ws(ctx->N, ctx->nChan)) {
+        const int cap = ctx->smCount * 2;
+        if (grid > cap) grid = cap;
+        const size_t per = ulcb_encode_ws_floats(ctx->N, ctx->nChan);
+        if (ctx->encGrid < grid || ctx->encWsFloats != per) {
+            if (ctx->encWs) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->encWs); ctx->encWs = nullptr; }
+            CK(ctx, cudaMalloc(&ctx->encWs, sizeof(float) * per * (size_t)(cap > grid ? cap : grid)));
+            ctx->encGrid = cap > grid ? cap : grid; ctx->encWsFloats = per;
+        }
+        a.workspace = ctx->encWs; a.wsFloats = per;
+    }
+    CK(ctx, ulcb_encode_launch(a, ctx->nChan, grid, ctx->stream));
+    ctx->launches++;
+    return ULCB_OK;
+}
+
+int ULCB_EncodeStreamsDevice(ULCB_Context *ctx, int nStreams, const void *dPcm, int format, const uint64_t *dNSamples,
+                             uint64_t inStrideElems, const uint32_t *dNBlocks, uint32_t nBlocksAll, const ULCB_EncodeParams *params,
+                             uint8_t *dOut, uint64_t outStrideBytes, uint32_t *dBlockBytes, float *dComplexity, int32_t *dWindowCtrl,
+                             uint64_t metaStride, uint64_t *dTotalBytes, int32_t *dStatus) {
+    return encode_device(ctx, nStreams, dPcm, format, dNSamples, inStrideElems, dNBlocks, nBlocksAll, params, dOut, outStrideBytes,
+                         dBlockBytes, dComplexity, dWindowCtrl, metaStride, dTotalBytes, dStatus, nullptr, nullptr, nullptr);
+}
+
+static int encode_host(ULCB_Context *ctx, int nStreams, const void *pcm, int format, const uint64_t *nSamples,
+                       uint64_t inStrideElems, uint32_t nBlocksAll, const ULCB_EncodeParams *params,
+                       uint8_t *out, uint64_t outStrideBytes, uint32_t *blockBytes, float *complexity, int32_t *windowCtrl,
+                       uint64_t *totalBytes, int32_t *status, const EncTaps *hostTaps) {
+    if (!ctx || nStreams < 0 || !pcm || !out || !params || nBlocksAll < 1) return ULCB_E_PARAM;
+    if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
+    if (nStreams == 0) return ULCB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t elem = format == ULCB_FMT_PCM16 ? 2 : 4;
+    const size_t inBytes = (size_t)nStreams * inStrideElems * elem, outBytes = (size_t)nStreams * outStrideBytes;
+    const size_t nMeta = (size_t)nStreams * nBlocksAll;
+    // aux layout: nSamples u64 | totalBytes u64 | blockBytes u32 | complexity f32 | windowCtrl i32 | status i32
+    size_t o = 0;
+    const size_t oNs = o; o += sizeof(uint64_t) * nStreams;
+    const size_t oTot = o; o += sizeof(uint64_t) * nStreams;
+    const size_t oBb = o; o += sizeof(uint32_t) * nMeta;
+    const size_t oCx = o; o += sizeof(float) * nMeta;
+    const size_t oWc = o; o += sizeof(int32_t) * nMeta;
+    const size_t oSt = o; o += sizeof(int32_t) * nStreams;
+    size_t oTap = (o + 255) & ~(size_t)255;
+    const size_t per = (size_t)ctx->nChan * ctx->N;
+    EncTaps dt{};
+    size_t tapBytes = 0;
+    if (hostTaps) tapBytes = nMeta * (sizeof(float) * (3 * per + ctx->N / 2) + sizeof(int32_t) * (per + 2));
+    int rc;
+    if ((rc = grow(ctx, &ctx->dIn, &ctx->dInCap, inBytes + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, outBytes))) return rc;
+    if ((rc = grow(ctx, &ctx->dAux, &ctx->dAuxCap, oTap + tapBytes))) return rc;
+    char *aux = (char *)ctx->dAux;
+    if (hostTaps) {
+        char *p = aux + oTap;
+        dt.coefs = (float *)p; p += sizeof(float) * nMeta * per;
+        dt.keys = (float *)p;  p += sizeof(float) * nMeta * per;
+        dt.noise = (float *)p; p += sizeof(float) * nMeta * per;
+        dt.mask = (float *)p;  p += sizeof(float) * nMeta * (ctx->N / 2);
+        dt.ranks = (int32_t *)p; p += sizeof(int32_t) * nMeta * per;
+        dt.counts = (int32_t *)p;
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->dIn, pcm, inBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (nSamples) CK(ctx, cudaMemcpyAsync(aux + oNs, nSamples, sizeof(uint64_t) * nStreams, cudaMemcpyHostToDevice, ctx->stream));
+    rc = encode_device(ctx, nStreams, ctx->dIn, format, nSamples ? (const uint64_t *)(aux + oNs) : nullptr, inStrideElems, nullptr, nBlocksAll,
+                       params, (uint8_t *)ctx->dOut, outStrideBytes, (uint32_t *)(aux + oBb), (float *)(aux + oCx), (int32_t *)(aux + oWc),
+                       nBlocksAll, (uint64_t *)(aux + oTot), (int32_t *)(aux + oSt), nullptr, nullptr, hostTaps ? &dt : nullptr);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (blockBytes) CK(ctx, cudaMemcpyAsync(blockBytes, aux + oBb, sizeof(uint32_t) * nMeta, cudaMemcpyDeviceToHost, ctx->stream));
+    if (complexity) CK(ctx, cudaMemcpyAsync(complexity, aux + oCx, sizeof(float) * nMeta, cudaMemcpyDeviceToHost, ctx->stream));
+    if (windowCtrl) CK(ctx, cudaMemcpyAsync(windowCtrl, aux + oWc, sizeof(int32_t) * nMeta, cudaMemcpyDeviceToHost, ctx->stream));
+    if (totalBytes) CK(ctx, cudaMemcpyAsync(totalBytes, aux + oTot, sizeof(uint64_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(ctx, cudaMemcpyAsync(status, aux + oSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hostTaps) {
+        if (hostTaps->coefs) CK(ctx, cudaMemcpyAsync(hostTaps->coefs, dt.coefs, sizeof(float) * nMeta * per, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hostTaps->keys)  CK(ctx, cudaMemcpyAsync(hostTaps->keys, dt.keys, sizeof(float) * nMeta * per, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hostTaps->noise) CK(ctx, cudaMemcpyAsync(hostTaps->noise, dt.noise, sizeof(float) * nMeta * per, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hostTaps->mask)  CK(ctx, cudaMemcpyAsync(hostTaps->mask, dt.mask, sizeof(float) * nMeta * (ctx->N / 2), cudaMemcpyDeviceToHost, ctx->stream));
+        if (hostTaps->ranks) CK(ctx, cudaMemcpyAsync(hostTaps->ranks, dt.ranks, sizeof(int32_t) * nMeta * per, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hostTaps->counts) CK(ctx, cudaMemcpyAsync(hostTaps->counts, dt.counts, sizeof(int32_t) * nMeta * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ULCB_OK;
+}
+
+int ULCB_EncodeStreams(ULCB_Context *ctx, int nStreams, const void *pcm, int format, const uint64_t *nSamples,
+                       uint64_t inStrideElems, uint32_t nBlocksAll, const ULCB_EncodeParams *params,
+                       uint8_t *out, uint64_t outStrideBytes, uint32_t *blockBytes, float *complexity, int32_t *windowCtrl,
+                       uint64_t *totalBytes, int32_t *status) {
+    return encode_host(ctx, nStreams, pcm, format, nSamples, inStrideElems, nBlocksAll, params, out, outStrideBytes, blockBytes,
+                       complexity, windowCtrl, totalBytes, status, nullptr);
+}
+
+int ULCB_TestEncode(ULCB_Context *ctx, int nStreams, const void *pcm, int format, const uint64_t *nSamples, uint64_t inStrideElems,
+                    uint32_t nBlocksAll, const ULCB_EncodeParams *params, uint8_t *out, uint64_t outStrideBytes,
+                    uint32_t *blockBytes, float *complexity, int32_t *windowCtrl,
+                    float *coefs, float *keys, float *noise, float *mask, int32_t *ranks, int32_t *counts) {
+    EncTaps t{coefs, keys, noise, mask, ranks, counts};
+    return encode_host(ctx, nStreams, pcm, format, nSamples, inStrideElems, nBlocksAll, params, out, outStrideBytes, blockBytes,
+                       complexity, windowCtrl, nullptr, nullptr, &t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// libulc drop-in: encoder (reference: include/ulcEncoder.h, libulc/ulcEncoder.c)
+// ------------------------------------------------------------------------------------------------
+struct DropinEncoder {
+    ULCB_Context *ctx;
+    UlcbEncStreamState *dState; float *dSamples;
+    float *dSrc; uint8_t *dOut; uint32_t *dBytes; float *dCx; int32_t *dWc;
+    float *hSrc; uint8_t *hOut; uint32_t *hMeta;       // pinned; hMeta = {bytes, cx bits, wc, nextWc}
+    size_t outCap;
+};
+
+int ULC_EncoderState_Init(struct ULC_EncoderState_t *State) {
+    State->BufferData = NULL;                                  // ulcEncoder.c:27
+    State->SampleBuffer = State->TransformBuffer = State->TransformNoise = State->TransformFwdLap = State->TransformTemp = NULL;
+    State->TransformIndex = NULL; State->TransientBuffer = NULL;
+    const int nChan = State->nChan, N = State->BlockSize;
+    if (!valid(nChan, N)) return -1;                           // ulcEncoder.c:29-34
+    DropinEncoder *d = (DropinEncoder *)calloc(1, sizeof(DropinEncoder));
+    if (!d) return -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (State->RateHz < 1 || ULCB_ContextCreate(&d->ctx, dev, State->RateHz, nChan, N, 1) != ULCB_OK) { free(d); return -1; }
+    const size_t cn = (size_t)nChan * N;
+    d->outCap = ULCB_MaxBlockBytes(nChan, N);
+    bool ok = cudaMalloc(&d->dState, sizeof(UlcbEncStreamState)) == cudaSuccess &&
+              cudaMalloc(&d->dSamples, sizeof(float) * 2 * cn) == cudaSuccess &&
+              cudaMalloc(&d->dSrc, sizeof(float) * cn) == cudaSuccess &&
+              cudaMalloc(&d->dOut, d->outCap) == cudaSuccess &&
+              cudaMalloc(&d->dBytes, sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&d->dCx, sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&d->dWc, sizeof(int32_t)) == cudaSuccess &&
+              cudaMallocHost(&d->hSrc, sizeof(float) * cn) == cudaSuccess &&
+              cudaMallocHost(&d->hOut, d->outCap) == cudaSuccess &&
+              cudaMallocHost(&d->hMeta, 4 * sizeof(uint32_t)) == cudaSuccess;
+    if (ok) ok = cudaMemset(d->dState, 0, sizeof(UlcbEncStreamState)) == cudaSuccess;
+    State->BufferData = d;
+    if (!ok) { ULC_EncoderState_Destroy(State); return -1; }
+    State->WindowCtrl = 0; State->NextWindowCtrl = 0x10;       // ulcEncoder.c:70
+    State->BlockComplexity = 0.0f;
+    State->TransientFilter[0] = State->TransientFilter[1] = State->TransientFilter[2] = 0.0f;
+    State->TransformTemp = (float *)d->hOut;                   // the reference returns a pointer into TransformTemp
+    return 1;
+}
+
+void ULC_EncoderState_Destroy(struct ULC_EncoderState_t *State) {
+    DropinEncoder *d = (DropinEncoder *)State->BufferData;
+    if (!d) return;
+    cudaFree(d->dState); cudaFree(d->dSamples); cudaFree(d->dSrc); cudaFree(d->dOut); cudaFree(d->dBytes); cudaFree(d->dCx); cudaFree(d->dWc);
+    cudaFreeHost(d->hSrc); cudaFreeHost(d->hOut); cudaFreeHost(d->hMeta);
+    ULCB_ContextDestroy(d->ctx);
+    free(d);
+    State->BufferData = NULL;
+}
+
+static const void *dropin_encode(struct ULC_EncoderState_t *State, const float *SrcData, int *Size, const ULCB_EncodeParams *prm) {
+    DropinEncoder *d = (DropinEncoder *)State->BufferData;
+    if (Size) *Size = 0;
+    if (!d) return NULL;
+    ULCB_Context *ctx = d->ctx;
+    const size_t cn = (size_t)State->nChan * State->BlockSize;
+    memcpy(d->hSrc, SrcData, sizeof(float) * cn);
+    if (cudaMemcpyAsync(d->dSrc, d->hSrc, sizeof(float) * cn, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return NULL;
+    if (encode_device(ctx, 1, d->dSrc, ULCB_FMT_FLOAT32, nullptr, cn, nullptr, 1, prm, d->dOut, d->outCap, d->dBytes, d->dCx, d->dWc, 1,
+                      nullptr, nullptr, d->dState, d->dSamples, nullptr) != ULCB_OK) return NULL;
+    cudaMemcpyAsync(d->hOut, d->dOut, d->outCap, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&d->hMeta[0], d->dBytes, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&d->hMeta[1], d->dCx, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&d->hMeta[2], d->dWc, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&d->hMeta[3], &d->dState->nextWindowCtrl, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return NULL;
+    memcpy(&State->BlockComplexity, &d->hMeta[1], sizeof(float));
+    State->WindowCtrl = (int)d->hMeta[2];
+    State->NextWindowCtrl = (int)d->hMeta[3];
+    if (Size) *Size = (int)d->hMeta[0] * 8;                    // bits, already a multiple of 8 (ulcEncoder_Encode.c:357-359)
+    return d->hOut;
+}
+
+const void *ULC_EncodeBlock_CBR(struct ULC_EncoderState_t *State, const float *SrcData, int *Size, float RateKbps) {
+    ULCB_EncodeParams p = {ULCB_MODE_CBR, RateKbps, 0.0f};
+    return dropin_encode(State, SrcData, Size, &p);
+}
+const void *ULC_EncodeBlock_ABR(struct ULC_EncoderState_t *State, const float *SrcData, int *Size, float RateKbps, float AvgComplexity) {
+    ULCB_EncodeParams p = {ULCB_MODE_ABR, RateKbps, AvgComplexity};
+    return dropin_encode(State, SrcData, Size, &p);
+}
+const void *ULC_EncodeBlock_VBR(struct ULC_EncoderState_t *State, const float *SrcData, int *Size, float Quality) {
+    ULCB_EncodeParams p = {ULCB_MODE_VBR, Quality, 0.0f};
+    return dropin_encode(State, SrcData, Size, &p);
 }
 
 }  // extern "C"

@@ -1,0 +1,1061 @@
+// ulcb_encode.cu - batched ulc-codec block encoder for sm_100a.
+//
+// One CTA owns one stream and walks it block by block with every intermediate in shared memory
+// (global workspace for the largest block sizes).  Per block (reference: libulc/ulcEncoder.c:93-158):
+//
+//   ingest + M/S                 ulcEncoder_BlockTransform.c:87-111
+//   transient detector           ulcEncoder_WindowControl.c:31-239      -> window control of the NEXT block
+//   fold + window                ulcEncoder_BlockTransform.c:156-237, Fourier_MDCT_Template.h:45-187
+//   DCT-IV x2 per (chan,sub)     Fourier_DCT4_Template.h / Fourier_DCT2_Template.h
+//   normalise, keys, sums        ulcEncoder_BlockTransform.c:243-325
+//   noise spectrum, masking      ulcEncoder_Psyopt.c:60-250
+//   ranks                        ulcEncoder_BlockTransform.c:20-77,350-354
+//   rate control                 ulcEncoder.c:93-158
+//   nybble coder                 ulcEncoder_Encode.c:23-360, ulcEncoder_NoiseFill.c:15-94
+//
+// This is not a translation of the reference's control flow:
+//  * The lapping FIFO + carried lap buffer are replaced by their closed form: every sub-block transform
+//    reads a 2S-sample frame of the M/S sample timeline (two previous blocks are kept) and applies the
+//    left/right sine windows directly.  The lap VALUES are the same single f32 products the reference
+//    stores, so the result is bit-identical (tests/test_encode_gpu.py).
+//  * The recursive DCT-IV/DCT-II pair is evaluated breadth-first: one pass per recursion level down,
+//    8-point leaves, one pass per level up, all nodes of a level in parallel.  Same flow graph, same
+//    rotor values (tabulated from the reference's recurrence), same operation order per node => bit-identical.
+//  * Heapsort is replaced by an LSD radix sort of order-preserving key bits.
+//  * The serial nybble coder becomes: selection -> zone walk (one thread per sub-block) -> per-slot token
+//    strings -> prefix sum of lengths -> parallel nybble scatter.  CBR/ABR run their binary search on the
+//    device with size-only passes.
+//
+// This file is compiled with -fmad=false: float and double expressions keep the reference's operation order.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "ulcb_encode.h"
+
+namespace {
+
+constexpr float kLn2f = 0x1.62E430p-1f;
+
+// Decimation layouts, one nybble per sub-block, LSB first: bits0-2 shift, bit3 transient
+// (libulc/ulcHelper.h:24-46, FormatSpecs.md:35-51)
+__constant__ uint16_t kLayoutE[16] = {
+    0x0000, 0x0008, 0x0019, 0x0091, 0x012A, 0x01A2, 0x02A1, 0x0A21,
+    0x123B, 0x12B3, 0x13B2, 0x1B32, 0x23B1, 0x2B31, 0x3B21, 0xB321,
+};
+
+struct SubInfo { int off, S, lgS, sh, ovL, ovR; };
+
+enum { MAXU = 8, MAXBU = 12 };
+
+struct EncSmall {
+    float   env[3];
+    float   seg[32];                 // {sum,cnt} x 16: [0..7] previous block, [8..15] current
+    SubInfo sub[4];
+    int     nsub;
+    int     wcPrev, wcCur, wcNext;
+    int     nNz;
+    float   cx;
+    int     unitSel[MAXU + 1];
+    int     unitZones[MAXU];
+    int     unitLastQ[MAXU];
+    int     tailLen[MAXU];
+    uint32_t tailTok[MAXU];
+    int     passTotal;
+    int     scan[40];
+    float   band[MAXBU][ULCB_NBARK];
+    double  lo[MAXBU][ULCB_NBARK][3];
+};
+
+// ---- small exact helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float logf_ref(float x) { return (float)log((double)x); }   // libm logf to the last ulp (nearly always)
+// expf as the host libm evaluates it (glibc >= 2.27, sysdeps/ieee754/flt-32/e_expf.c: the Arm optimized-routines
+// algorithm - 32-entry 2^(i/32) table, cubic in f64, one rounding to f32).  Restated from the published algorithm;
+// checked exhaustively on the host against libm expf over every float in [-88, 88]: 2 mismatches in 2.2e9.
+__constant__ uint64_t kExp2Tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+};
+__device__ __forceinline__ float expf_ref(float x) {
+    if (!(fabsf(x) < 88.0f)) return (float)exp((double)x);
+    const double Nn = 32.0;
+    const double InvLn2N = 0x1.71547652b82fep+0 * Nn;
+    const double C0 = 0x1.c6af84b912394p-5 / Nn / Nn / Nn, C1 = 0x1.ebfce50fac4f3p-3 / Nn / Nn, C2 = 0x1.62e42ff0c52d6p-1 / Nn;
+    const double SHIFT = 0x1.8p+52;
+    double z = InvLn2N * (double)x;
+    double kd = z + SHIFT;
+    uint64_t ki = (uint64_t)__double_as_longlong(kd);
+    kd -= SHIFT;
+    double r = z - kd;
+    uint64_t t = kExp2Tab[ki & 31] + (ki << 47);
+    double s = __longlong_as_double((long long)t);
+    z = C0 * r + C1;
+    double r2 = r * r;
+    double y = C2 * r + 1.0;
+    y = z * r2 + y;
+    y = y * s;
+    return (float)y;
+}
+
+__device__ __forceinline__ float fast_log(float x) {              // libulc/ulcHelper.h:127-136
+    uint32_t b = __float_as_uint(x);
+    int e = (int)(b >> 23) - 127;
+    x = __uint_as_float((127u << 23) | (b & 0x7FFFFFu));
+    return -1.7417939f + (2.8212026f + (-1.4699568f + (0.44717955f - 0.056570851f * x) * x) * x) * x + 0.6931471806f * (float)e;
+}
+__device__ __forceinline__ int compand_u(float v) {               // ulcHelper.h:51-60
+    return (v >= 0.5f) ? (int)(0.5f + sqrtf(v - 0.25f)) : 0;
+}
+__device__ __forceinline__ int compand_clip(float v, int limit) { // ulcHelper.h:62-91
+    int q = compand_u(fabsf(v));
+    if (q > limit) q = limit;
+    return v < 0.0f ? -q : q;
+}
+__device__ __forceinline__ int first_overlap(int wc, int N) {
+    unsigned pat = kLayoutE[(wc >> 4) & 15];
+    int ov = N >> (pat & 7);
+    if ((pat & 8) && (wc >> 4) != 0) ov >>= (wc & 7);
+    return ov;
+}
+__device__ __forceinline__ int last_subsize(int wc, int N) {
+    unsigned pat = kLayoutE[(wc >> 4) & 15];
+    int sh = pat & 7;
+    while (pat >>= 4) sh = pat & 7;
+    return N >> sh;
+}
+__device__ __forceinline__ bool node_is_dct4(int d, int node) {   // root = DCT-IV; DCT-IV -> (II, II); DCT-II -> (II, IV)
+    unsigned h = (1u << d) | (unsigned)node;
+    int ones = __ffs(~h) - 1;                                     // trailing ones of the heap index
+    return ones & 1;
+}
+
+// CTA-wide exclusive scans of one int per thread.  `scr` = smem int[NTHR/32 + 2].
+template <int NTHR>
+__device__ __forceinline__ int block_excl_sum(int v, int *scr, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = NTHR / 32;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    __syncthreads();
+    if (lane == 31) scr[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < NW ? scr[lane] : 0, ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += u; }
+        if (lane < NW) scr[lane] = ti - t;
+        if (lane == 31) scr[NW] = ti;
+    }
+    __syncthreads();
+    total = scr[NW];
+    return inc - v + scr[warp];
+}
+template <int NTHR>
+__device__ __forceinline__ int block_excl_max(int v, int *scr) {     // v >= 0; identity 0
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = NTHR / 32;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, t); }
+    int exl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exl = 0;
+    __syncthreads();
+    if (lane == 31) scr[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < NW ? scr[lane] : 0, ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti = max(ti, u); }
+        int te = __shfl_up_sync(0xffffffffu, ti, 1);
+        if (lane == 0) te = 0;
+        if (lane < NW) scr[lane] = te;
+    }
+    __syncthreads();
+    return max(exl, scr[warp]);
+}
+
+// ---- pointers into the per-CTA work area ------------------------------------------------------------
+struct Work {
+    float *R;            // [3][CN] sample timeline, rotating: block k lives at R + (k % 3)*CN (M/S planar)
+    float *XA, *XB;      // DCT "X" buffers: MDCT / MDST, [CN] each; XA becomes the normalised coefficients
+    float *TA, *TB;      // DCT "T" buffers; afterwards TA = keys -> ranks/selection list, TB = noise pairs
+    float *amp2, *mask;  // [N/2]
+    uint16_t *cnt;       // radix counters [16][NTHR]
+};
+
+// ---- transient detector (ulcEncoder_WindowControl.c:140-239) decision on the 16 segment sums ----------
+__device__ int window_decide(const float *seg, int log2N) {
+    const float *cur = seg + 16;                      // entries are {sum,cnt} pairs; cur = entry 8
+    int log2sub = log2N - 3, nSeg = 8, segSz = 1;
+    if (log2sub < 6) { int sh = 6 - log2sub; nSeg >>= sh; segSz <<= sh; log2sub = 6; }
+    int decimation = 1; float trRatio = 0.0f;
+    for (;;) {
+        log2sub++;
+        int best = 0; float maxRatio = -1000.0f;
+        for (int s = 0; s < nSeg; s++) {
+            float Ls = 0.0f, Lc = 0.0f, Rs = 0.0f, Rc = 0.0f;
+            const float *src = cur + 2 * s * segSz;
+            for (int n = 0; n < segSz; n++) {
+                Ls += src[2 * (n - segSz)]; Lc += src[2 * (n - segSz) + 1];
+                Rs += src[2 * n];           Rc += src[2 * n + 1];
+            }
+            float l = (Ls != 0.0f) ? logf_ref(Ls / Lc) : -100.0f;
+            float r = (Rs != 0.0f) ? logf_ref(Rs / Rc) : -100.0f;
+            float ratio = r - l; if (ratio < 0.0f) ratio = -ratio;
+            if (ratio > maxRatio) { best = s; maxRatio = ratio; }
+        }
+        if (maxRatio - trRatio < kLn2f) break;
+        decimation = nSeg + best;
+        trRatio = maxRatio;
+        if (nSeg > 1 && trRatio < kLn2f) { nSeg /= 2; segSz *= 2; } else break;
+    }
+    if (trRatio < 0x1.62E430p-2f) return 0x10;
+    trRatio *= 0x1.715476p0f;
+    int ov = (trRatio < 0.5f) ? 0 : (trRatio >= 6.5f) ? 7 : __float2int_rn(trRatio);
+    if (log2sub - ov < 6) ov = log2sub - 6;
+    return ov + 8 * (decimation != 1) + 16 * decimation;
+}
+
+// ---- 8-point leaves (Fourier_DCT4.c:64-111, Fourier_DCT2.c:64-109) --------------------------------------
+__device__ __forceinline__ void dct4_leaf8(float *x) {
+    const float R = 0x1.6A09E6p-1f, C13 = 0x1.D906BCp-1f, S13 = 0x1.87DE2Ap-2f;
+    const float CK0 = 0x1.FD88DAp-1f, CK1 = 0x1.E9F416p-1f, CK2 = 0x1.C38B30p-1f, CK3 = 0x1.8BC806p-1f;
+    const float SK0 = 0x1.917A6Cp-4f, SK1 = 0x1.294062p-2f, SK2 = 0x1.E2B5D4p-2f, SK3 = 0x1.44CF32p-1f;
+    float x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3], x4 = x[4], x5 = x[5], x6 = x[6], x7 = x[7];
+    float p0 = CK0 * x0 + SK0 * x7, q0 = SK0 * x0 - CK0 * x7;
+    float p1 = CK1 * x1 + SK1 * x6, q1 = -SK1 * x1 + CK1 * x6;
+    float p2 = CK2 * x2 + SK2 * x5, q2 = SK2 * x2 - CK2 * x5;
+    float p3 = CK3 * x3 + SK3 * x4, q3 = -SK3 * x3 + CK3 * x4;
+    float pa = p0 + p3, pd = p0 - p3, pb = p1 + p2, pe = p1 - p2;
+    float qa = q3 + q0, qd = q3 - q0, qb = q2 + q1, qe = q2 - q1;
+    float sx = pa + pb, sy = pa - pb;
+    float tx = C13 * pd + S13 * pe, ty = S13 * pd - C13 * pe;
+    float ux = qa + qb, uy = qa - qb;
+    float vx = C13 * qd + S13 * qe, vy = S13 * qd - C13 * qe;
+    x[0] = sx; x[1] = tx - vy; x[2] = tx + vy; x[3] = (sy + uy) * R;
+    x[4] = (sy - uy) * R; x[5] = ty - vx; x[6] = ty + vx; x[7] = ux;
+}
+__device__ __forceinline__ void dct2_leaf8(float *x) {
+    const float R = 0x1.6A09E6p-1f;
+    const float C14 = 0x1.F6297Cp-1f, S14 = 0x1.8F8B84p-3f, C34 = 0x1.A9B662p-1f, S34 = 0x1.1C73B4p-1f;
+    const float C64 = 0x1.87DE2Ap-2f, S64 = 0x1.D906BCp-1f;
+    float x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3], x4 = x[4], x5 = x[5], x6 = x[6], x7 = x[7];
+    float s0 = x0 + x7, d0 = x0 - x7, s1 = x1 + x6, d1 = x1 - x6;
+    float s2 = x2 + x5, d2 = x2 - x5, s3 = x3 + x4, d3 = x3 - x4;
+    float ee = s0 + s3, eo = s0 - s3, fe = s1 + s2, fo = s1 - s2;
+    float gx = C34 * d3 + S34 * d0, gy = -S34 * d3 + C34 * d0;
+    float hx = C14 * d2 + S14 * d1, hy = -S14 * d2 + C14 * d1;
+    float a0 = ee + fe, b0 = ee - fe;
+    float c0 = C64 * fo + S64 * eo, e0 = -S64 * fo + C64 * eo;
+    float a1 = gy + hx, c1 = gy - hx, e1 = gx + hy, b1 = gx - hy;
+    x[0] = a0; x[4] = b0 * R; x[2] = c0; x[6] = e0;
+    x[1] = (a1 + e1) * R; x[5] = b1; x[3] = c1; x[7] = (a1 - e1) * R;
+}
+
+__device__ __forceinline__ int find_sub(const EncSmall &sm, int n) {     // sub-block holding in-channel index n
+    int j = 0;
+    while (j + 1 < sm.nsub && n >= sm.sub[j + 1].off) j++;
+    return j;
+}
+
+// ---- nybble sinks ----------------------------------------------------------------------------------
+struct CountSink { int n; __device__ __forceinline__ void put(int) { n++; } };
+struct WriteSink {
+    uint32_t *words; int pos, cap;
+    __device__ __forceinline__ void put(int x) {
+        if (pos < cap) atomicOr(&words[pos >> 3], (uint32_t)(x & 15) << ((pos & 7) * 4));
+        pos++;
+    }
+};
+
+// noise amplitude code of a run (ulcEncoder_NoiseFill.c:15-36)
+__device__ int noise_q(const float *pairs, int band, int n, float q) {
+    pairs += band & ~1;
+    n = (n + (band & 1) + 1) >> 1;
+    float s = 0.0f, sw = 0.0f;
+    for (int i = 0; i < n; i++) { float2 p = *reinterpret_cast<const float2 *>(pairs + 2 * i); s += p.y; sw += p.x; }
+    if (s == 0.0f) return 0;
+    float amp = expf_ref(s / sw);
+    int r = compand_u(amp * q);
+    return r < 8 ? r : 8;
+}
+// HF extension fit (ulcEncoder_NoiseFill.c:41-94)
+__device__ void hf_ext_params(const float *pairs, int band, int n, float q, int &nq, int &dq) {
+    pairs += band & ~1;
+    n = (n + (band & 1) + 1) >> 1;
+    float sx = 0.0f, sx2 = 0.0f, sxy = 0.0f, sy = 0.0f, sw = 0.0f;
+    for (int i = 0; i < n; i++) {
+        float2 p = *reinterpret_cast<const float2 *>(pairs + 2 * i);
+        float x = (float)i * 2.0f, w = p.x, wy = p.y;
+        sx += w * x; sx2 += w * x * x; sxy += x * wy; sy += wy; sw += w;
+    }
+    float det = sw * sx2 - sx * sx;
+    if (det == 0.0f) { nq = dq = 0; return; }
+    float amp = (sx2 * sy - sx * sxy) / det, dec = (sw * sxy - sx * sy) / det;
+    amp = expf_ref(amp);
+    dec = (dec < 0.0f) ? expf_ref(dec) : 1.0f;
+    int a = compand_u(amp * q * 4.0f); if (a > 16) a = 16;
+    int d = compand_u((dec - 1.0f) * -0x1.0p19f);
+    if (!d) return;
+    if (d > 0xFF) d = 0xFF;
+    nq = a; dq = d;
+}
+
+// tokens of one kept coefficient: the gap [nc, cur) then the coefficient (ulcEncoder_Encode.c:114-192)
+template <class Sink>
+__device__ void put_item(Sink &w, const float *coef, const float *pairs, int nc, int cur, float q) {
+    int gap = cur - nc;
+    while (gap) {
+        int n, v = 0;
+        if (gap <= 2) {
+            int q1 = compand_clip(coef[nc] * q, 7), q2 = 0;
+            if (gap >= 2) q2 = compand_clip(coef[nc + 1] * q, 7);
+            if (abs(q1) > 1 && (gap < 2 || abs(q2) > 1)) {
+                w.put(q1);
+                if (gap >= 2) w.put(q2);
+                break;
+            }
+        }
+        int nq = 0;
+        n = 0;
+        if (gap >= 16) {
+            v = gap - 16; if (v > 0x1FF) v = 0x1FF;
+            n = v + 16;
+            nq = noise_q(pairs, nc, n, q);
+        }
+        if (nq) { w.put(0x8); w.put(v >> 5); w.put(v >> 1); w.put((v & 1) | ((nq - 1) << 1)); }
+        else if (gap < 33) { v = gap - 1; if (v > 0xF) v = 0xF; n = v + 1; w.put(0x0); w.put(v); }
+        else { v = gap - 33; if (v > 0xFF) v = 0xFF; n = v + 33; w.put(0x1); w.put(v >> 4); w.put(v); }
+        nc += n; gap -= n;
+    }
+    w.put(compand_clip(coef[cur] * q, 7));
+}
+
+// slot info byte: bits0-4 quantiser index (5..31, so non-zero = selected), bit5 emit quantiser, bit6 first zone of its sub-block
+enum { INF_Q = 31, INF_HDR = 32, INF_FIRST = 64 };
+
+template <class Sink>
+__device__ __forceinline__ void put_quant(Sink &w, int inf) {            // ulcEncoder_Encode.c:32-45
+    int s = (inf & INF_Q) - 5;
+    if (!(inf & INF_FIRST)) w.put(0xF);
+    if (s < 0xE) w.put(s);
+    else { w.put(0xE); w.put(s - 0xE); }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NCH, int NTHR>
+struct Encoder {
+    const UlcbEncodeArgs &args;
+    const UlcbEncTables &tb;
+    EncSmall &sm;
+    Work w;
+    const int N, CN, H, tid;
+
+    __device__ Encoder(const UlcbEncodeArgs &a, EncSmall &s, const Work &wk)
+        : args(a), tb(a.tb), sm(s), w(wk), N(a.tb.N), CN(NCH * a.tb.N), H(a.tb.N >> 1), tid(threadIdx.x) {}
+
+    __device__ __forceinline__ float *blk(int k) const { return w.R + ((k + 3) % 3) * CN; }
+
+    // ---------------- ingest ----------------
+    __device__ void ingest(int k, const void *pcm, long long validSamples) {
+        float *R0 = blk(k);
+        for (int n = tid; n < N; n += NTHR) {
+            float v[NCH];
+            bool ok = n < validSamples;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                float x = 0.0f;
+                if (ok) {
+                    if (args.pcmFloat) x = reinterpret_cast<const float *>(pcm)[(size_t)n * NCH + c];
+                    else x = (float)reinterpret_cast<const int16_t *>(pcm)[(size_t)n * NCH + c] * 0x1.0p-15f;   // tools/WavIO_Helper.c:49-55
+                }
+                v[c] = x;
+            }
+#pragma unroll
+            for (int c = 1; c < NCH; c += 2) {                       // M/S (ulcEncoder_BlockTransform.c:102-111)
+                float a = v[c - 1], b = v[c];
+                v[c - 1] = (a + b) * 0.5f;
+                v[c]     = (a - b) * 0.5f;
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; c++) R0[c * N + n] = v[c];
+        }
+    }
+
+    // ---------------- transient detector ----------------
+    __device__ void window_control(int k) {
+        const float *R0 = blk(k), *R1 = blk(k - 1);
+        float2 *E = reinterpret_cast<float2 *>(w.TA);
+        for (int n = tid; n < N; n += NTHR) {
+            float ehp = 0.0f, ebp = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                auto z = [&](int i) -> float { return (i < H) ? R1[c * N + H + i] : R0[c * N + i - H]; };
+                float t0 = z(n - 1), t1 = z(n), t2 = z(n + 1);
+                float hp = (-t0 + 2.0f * t1) - t2, bp = -t0 + t2;
+                ehp += hp * hp; ebp += bp * bp;
+            }
+            E[n] = make_float2(sqrtf(ehp), sqrtf(ebp));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float php = sm.env[0], pbp = sm.env[1];
+            const float a1 = tb.c1PostHp, a2 = tb.c1PostBp;
+            for (int n = 0; n < N; n++) {                            // post-masking envelopes (:73-88)
+                float2 e = E[n];
+                float dh = e.x - php, db = e.y - pbp;
+                php += dh * a1; pbp += db * a2;
+                E[n] = make_float2(php, pbp);
+            }
+            sm.env[0] = php; sm.env[1] = pbp;
+            float qhp = php, qbp = pbp;
+            const float b1 = tb.c1PreHp, b2 = tb.c1PreBp;
+            for (int n = N - 1; n >= 0; n--) {                       // pre-masking, backwards (:92-104)
+                float2 e = E[n];
+                float dh = e.x - qhp, db = e.y - qbp;
+                qhp += dh * b1; qbp += db * b2;
+                float a = dh * qbp, b = db * qhp;
+                E[n].x = a * a + b * b;
+            }
+            const int bin = N >> 3;
+            const float cb = tb.c1Blk;
+            float m = sm.env[2];
+            for (int s = 0; s < 8; s++) {                            // block-mask envelope into 8 segment sums (:107-134)
+                sm.seg[2 * s] = sm.seg[16 + 2 * s]; sm.seg[2 * s + 1] = sm.seg[16 + 2 * s + 1];
+                float acc = 0.0f, cnt = 0.0f;
+                for (int n = 0; n < bin; n++) {
+                    float d = E[s * bin + n].x - m;
+                    m += d * cb;
+                    acc += m; cnt += 1.0f;
+                }
+                sm.seg[16 + 2 * s] = acc; sm.seg[16 + 2 * s + 1] = cnt;
+            }
+            sm.env[2] = m;
+            sm.wcPrev = sm.wcCur;
+            sm.wcCur  = sm.wcNext;
+            sm.wcNext = window_decide(sm.seg, tb.log2N);
+            // sub-block table of the block being coded now (ulcEncoder_BlockTransform.c:156-172)
+            const int wc = sm.wcCur;
+            unsigned pat = kLayoutE[(wc >> 4) & 15];
+            int j = 0, off = 0;
+            int trs[4];
+            do {
+                SubInfo &s = sm.sub[j];
+                s.sh = pat & 7; s.S = N >> s.sh; s.lgS = tb.log2N - s.sh; s.off = off;
+                trs[j] = ((pat & 8) && (wc >> 4) != 0) ? (wc & 7) : 0;
+                off += s.S; j++;
+            } while (pat >>= 4);
+            sm.nsub = j;
+            for (int i = 0; i < j; i++) {
+                int ov = (i + 1 < j) ? (sm.sub[i + 1].S >> trs[i + 1]) : first_overlap(sm.wcNext, N);
+                if (ov > sm.sub[i].S) ov = sm.sub[i].S;
+                sm.sub[i].ovR = ov;
+            }
+            for (int i = 0; i < j; i++) {
+                if (i > 0) sm.sub[i].ovL = sm.sub[i - 1].ovR;
+                else { int ov = first_overlap(wc, N), sp = last_subsize(sm.wcPrev, N); sm.sub[0].ovL = ov < sp ? ov : sp; }
+            }
+            sm.nNz = 0;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- fold + window (closed form of the lapping FIFO and Fourier_MDCT_Template.h:45-187) ----------------
+    __device__ __forceinline__ float lap_value(const float *R2, const float *R1, int c, int rel, int u, int ovL) const {
+        // rel = index on the 2N timeline [block k-2 | block k-1]; u = offset from the fold point
+        const int hv = ovL >> 1;
+        if (u < -hv) return 0.0f;
+        float x = (rel < N) ? R2[c * N + rel] : R1[c * N + rel - N];
+        if (u >= hv) return x;
+        if (u < 0) return __ldg(&tb.rot[hv + (u + hv)]).y * x;
+        return __ldg(&tb.rot[hv + (hv - 1 - u)]).x * x;
+    }
+    __device__ void fold(int k) {
+        const float *R1 = blk(k - 1), *R2 = blk(k - 2);
+        for (int P = tid; P < NCH * H; P += NTHR) {
+            const int c = P / H, r = P - c * H;
+            const int j = find_sub(sm, 2 * r);
+            const SubInfo s = sm.sub[j];
+            const int hS = s.S >> 1, i = r - (s.off >> 1);
+            const int hrel = H + s.off;                               // fold point on the 2N timeline
+            float a  = lap_value(R2, R1, c, hrel - hS + i, i - hS, s.ovL);
+            float br = lap_value(R2, R1, c, hrel + hS - 1 - i, hS - 1 - i, s.ovL);
+            auto fresh = [&](int q) -> float { int rel = hrel + hS + q; return (rel < N) ? R2[c * N + rel] : R1[c * N + rel - N]; };
+            float cc = fresh(i), dr = fresh(s.S - 1 - i);
+            const int flat = (s.S - s.ovR) >> 1;
+            float mc, ms;
+            if (i < flat) { mc = cc; ms = cc; }
+            else {
+                float2 rt = __ldg(&tb.rot[(s.ovR >> 1) + (i - flat)]);
+                float c2 = cc * rt.x, d2 = dr * rt.y;
+                mc = c2 + d2; ms = c2 - d2;
+            }
+            float mc2 = -a + br, ms2 = a + br;
+            const int base = c * N + s.off;
+            const int lo = hS - 1 - i, hi = hS + i;
+            w.XA[base + lo] = mc;
+            w.XA[base + hi] = mc2;
+            w.XB[base + lo] = (lo & 1) ? -ms : ms;                    // odd-index sign flip of the MDST input (:170-176)
+            w.XB[base + hi] = (hi & 1) ? -ms2 : ms2;
+        }
+    }
+
+    // ---------------- breadth-first DCT-IV of every (buffer, channel, sub-block) ----------------
+    __device__ __forceinline__ void locate(int P, int &hb, int &cbase, int &j, int &lp) const {
+        // pair index P in [0, CN) -> buffer half, channel base, sub-block, local pair index
+        const int half = CN >> 1;
+        hb = P >= half; int pp = P - (hb ? half : 0);
+        int c = pp / H, r = pp - c * H;
+        j = find_sub(sm, 2 * r);
+        lp = r - (sm.sub[j].off >> 1);
+        cbase = c * N + sm.sub[j].off;
+    }
+    __device__ void dct_down(int m, int lgm) {
+        const int hm = m >> 1;
+        for (int P = tid; P < CN; P += NTHR) {
+            int hb, cbase, j, lp; locate(P, hb, cbase, j, lp);
+            const int lgS = sm.sub[j].lgS;
+            if (lgS < lgm) continue;
+            const int d = lgS - lgm, node = lp >> (lgm - 1), i = lp & (hm - 1);
+            float *X = hb ? w.XB : w.XA, *T = hb ? w.TB : w.TA;
+            const float *src = ((d & 1) ? T : X) + cbase + node * m;
+            float *dst = ((d & 1) ? X : T) + cbase + node * m;
+            float a = src[i], b = src[m - 1 - i];
+            if (node_is_dct4(d, node)) {                              // Fourier_DCT4_Template.h:49-68
+                float2 rt = __ldg(&tb.rot[hm + i]);
+                dst[i] = rt.x * a + rt.y * b;
+                float p = rt.y * a, q = rt.x * b;
+                dst[hm + i] = (i & 1) ? (q - p) : (p - q);
+            } else {                                                  // Fourier_DCT2_Template.h:24-40
+                dst[i] = a + b;
+                dst[hm + i] = a - b;
+            }
+        }
+    }
+    __device__ void dct_leaves() {
+        for (int Lf = tid; Lf < (CN >> 2); Lf += NTHR) {              // 2*CN/8 leaves
+            const int half = CN >> 3;
+            int hb = Lf >= half; int q = Lf - (hb ? half : 0);
+            int pos = q << 3;                                         // element position in [0, CN)
+            int c = pos / N, n = pos - c * N;
+            int j = find_sub(sm, n);
+            const SubInfo &s = sm.sub[j];
+            int d = s.lgS - 3, node = (n - s.off) >> 3;
+            float *buf = (hb ? ((d & 1) ? w.TB : w.XB) : ((d & 1) ? w.TA : w.XA)) + pos;
+            if (node_is_dct4(d, node)) dct4_leaf8(buf); else dct2_leaf8(buf);
+        }
+    }
+    __device__ void dct_up(int m, int lgm) {
+        const int hm = m >> 1;
+        for (int P = tid; P < CN; P += NTHR) {
+            int hb, cbase, j, lp; locate(P, hb, cbase, j, lp);
+            const int lgS = sm.sub[j].lgS;
+            if (lgS < lgm) continue;
+            const int d = lgS - lgm, node = lp >> (lgm - 1), i = lp & (hm - 1);
+            float *X = hb ? w.XB : w.XA, *T = hb ? w.TB : w.TA;
+            const float *src = ((d & 1) ? X : T) + cbase + node * m;  // children live at depth d+1
+            float *dst = ((d & 1) ? T : X) + cbase + node * m;
+            if (node_is_dct4(d, node)) {                              // Fourier_DCT4_Template.h:100-114
+                if (i == hm - 1) { dst[0] = src[0]; dst[m - 1] = src[hm]; }
+                else {
+                    float a = src[i + 1], b = src[m - 1 - i];
+                    dst[2 * i + 1] = a + b;
+                    dst[2 * i + 2] = a - b;
+                }
+            } else {                                                  // Fourier_DCT2_Template.h:62-77
+                dst[2 * i] = src[i];
+                dst[2 * i + 1] = src[hm + i];
+            }
+        }
+    }
+    __device__ void transform() {
+        const int lgN = tb.log2N;
+        for (int lgm = lgN; lgm >= 4; lgm--) { dct_down(1 << lgm, lgm); __syncthreads(); }
+        dct_leaves();
+        __syncthreads();
+        for (int lgm = 4; lgm <= lgN; lgm++) { dct_up(1 << lgm, lgm); __syncthreads(); }
+    }
+
+    // ---------------- normalise, keys, line sums (ulcEncoder_BlockTransform.c:243-281) ----------------
+    __device__ void analyse(int k) {
+        float *lgN = blk(k - 2);                                      // dead sample block: log of the noise line sums
+        int nz = 0;
+        for (int p = tid; p < H; p += NTHR) {
+            const int j = find_sub(sm, 2 * p);
+            const SubInfo s = sm.sub[j];
+            const float norm = 2.0f / (float)s.S;
+            const int n0 = 2 * p - s.off;                             // even local index
+            float amp = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int base = c * N + s.off;
+                float re0 = w.XA[base + n0] * norm, re1 = w.XA[base + n0 + 1] * norm;
+                float im0 = w.XB[base + s.S - 1 - n0] * norm, im1 = w.XB[base + s.S - 2 - n0] * norm;   // MDST is stored reversed (:184-186)
+                w.XA[base + n0] = re0; w.XA[base + n0 + 1] = re1;
+                float a0 = re0 * re0 + im0 * im0, a1 = re1 * re1 + im1 * im1;
+                float k0, k1;
+                if (fabsf(re0) < 0.5f * 0x1.0p-31f) k0 = -INFINITY; else { k0 = fast_log(re0 * re0); nz++; }
+                if (fabsf(re1) < 0.5f * 0x1.0p-31f) k1 = -INFINITY; else { k1 = fast_log(re1 * re1); nz++; }
+                w.TA[base + n0] = k0; w.TA[base + n0 + 1] = k1;
+                float ns = a0 + a1;
+                amp += a0; amp += a1;
+                w.TB[base + (n0 >> 1)] = ns;
+                lgN[c * H + (s.off >> 1) + (n0 >> 1)] = fast_log(0x1.0p-126f + ns);
+            }
+            w.amp2[p] = amp;
+            w.mask[p] = fast_log(0x1.0p-126f + amp);
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, d);
+        if ((tid & 31) == 0 && nz) atomicAdd(&sm.nNz, nz);
+    }
+
+    // ---------------- serial sums: complexity + Bark band analysis ----------------
+    __device__ void band_unit(int unit, const float *v, const float *lg, int n, int sh, int kind) {
+        // running f64 sums in index order (struct LineSum_t, ulcEncoder_Psyopt.c:16-51), sampled at the band edges
+        const int16_t *ed = tb.edges + ((sh * 2 + kind) * ULCB_NBARK) * 2;
+        double sLg = 0.0, sWlg = 0.0, sW = 0.0;
+        int pb = 0, pe = 0;
+        float level = kind ? 0.0f : -100.0f;
+        for (int i = 0; i <= n; i++) {
+            while (pb < ULCB_NBARK && ed[2 * pb] == i) { sm.lo[unit][pb][0] = sLg; sm.lo[unit][pb][1] = sWlg; sm.lo[unit][pb][2] = sW; pb++; }
+            while (pe < ULCB_NBARK && ed[2 * pe + 1] == i) {
+                // band pe is complete (its begin edge was passed earlier or just now)
+                double dLg = sLg - sm.lo[unit][pe][0], dWlg = sWlg - sm.lo[unit][pe][1], dW = sW - sm.lo[unit][pe][2];
+                int beg = ed[2 * pe], end = ed[2 * pe + 1];
+                if (dW > 0.0) {
+                    if (kind == 0) {                                  // noise level (ulcEncoder_Psyopt.c:206-222)
+                        double inv = 1.0 / (double)(end - beg);
+                        dWlg = dWlg / dW;
+                        dLg = dLg * inv;
+                        level = 0.5f * (float)(log(dW * inv) + dLg - dWlg);
+                    } else {                                          // masking (ulcEncoder_Psyopt.c:117-131)
+                        dWlg = dWlg / dW;
+                        dLg = dLg / (double)(end - beg);
+                        level = (float)(dWlg - dLg - log(dW));
+                    }
+                }
+                sm.band[unit][pe] = level;
+                pe++;
+            }
+            if (i < n) {
+                double x = (double)v[i], l = (double)lg[i];
+                sLg += l; sWlg += l * x; sW += x;
+            }
+        }
+        // bands whose edges were never reached cannot exist: every edge is clamped to [0, n]
+    }
+    __device__ void serial_sums(int k) {
+        const float *lgN = blk(k - 2);
+        const int U = NCH * sm.nsub;
+        if (tid == 0) {                                               // block complexity (ulcEncoder_BlockTransform.c:310-325)
+            float sq = 0.0f, ab = 0.0f;
+            for (int i = 0; i < CN; i++) { float re = w.XA[i]; sq += re * re; ab += fabsf(re); }
+            float cx = sq;
+            if (cx != 0.0f) {
+                float scale = kLn2f * (float)tb.log2N;
+                cx = logf_ref(ab * ab / sq) / scale;
+                if (cx < 0.0f) cx = 0.0f;
+                if (cx > 1.0f) cx = 1.0f;
+            }
+            sm.cx = cx;
+        } else if (tid >= 32 && tid < 32 + U + sm.nsub) {
+            int u = tid - 32;
+            if (u < U) {
+                int c = u / sm.nsub, j = u - c * sm.nsub;
+                const SubInfo &s = sm.sub[j];
+                band_unit(u, w.TB + c * N + s.off, lgN + c * H + (s.off >> 1), s.S >> 1, s.sh, 0);
+            } else {
+                int j = u - U;
+                const SubInfo &s = sm.sub[j];
+                band_unit(u, w.amp2 + (s.off >> 1), w.mask + (s.off >> 1), s.S >> 1, s.sh, 1);
+            }
+        }
+    }
+    __device__ __forceinline__ float bark_interp(const float *band, int sh, int line) const {    // ulcEncoder_Psyopt.c:136-152
+        const int t = tb.lineOff[sh] + line;
+        const int idx = __ldg(&tb.lineBand[t]);
+        const float fr = __ldg(&tb.lineFrac[t]);
+        float l = (idx < ULCB_NBARK) ? band[idx] : band[ULCB_NBARK - 1];
+        float r = (idx + 1 < ULCB_NBARK) ? band[idx + 1] : l;
+        return l * (1.0f - fr) + r * fr;
+    }
+    __device__ void spread() {
+        const int U = NCH * sm.nsub;
+        for (int p = tid; p < H; p += NTHR) {
+            const int j = find_sub(sm, 2 * p);
+            const SubInfo &s = sm.sub[j];
+            const int line = p - (s.off >> 1);
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                float v = bark_interp(sm.band[c * sm.nsub + j], s.sh, line);
+                float wgt = expf_ref(0.5f * v);
+                float *dst = w.TB + c * N + s.off + 2 * line;
+                dst[0] = wgt;
+                dst[1] = wgt * (v + kLn2f);
+            }
+            w.mask[p] = bark_interp(sm.band[U + j], s.sh, line);
+        }
+    }
+
+    // ---------------- final keys + ranks ----------------
+    __device__ void make_keys(float *dbgKeys) {
+        uint32_t *uk = reinterpret_cast<uint32_t *>(w.TA);
+        uint16_t *idxA = reinterpret_cast<uint16_t *>(w.XB);
+        for (int i = tid; i < CN; i += NTHR) {
+            const int c = i / N, n = i - c * N;
+            float key = w.TA[i];
+            key = 2.0f * key + w.mask[n >> 1] + -0x1.62E430p0f * (float)(c & 1);     // ulcEncoder_BlockTransform.c:337-345
+            if (dbgKeys) dbgKeys[i] = key;
+            uint32_t b = __float_as_uint(key);
+            b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);          // ascending order-preserving
+            uk[i] = ~b;                                               // descending importance
+            idxA[i] = (uint16_t)i;
+        }
+    }
+    __device__ void rank_sort() {
+        // LSD radix sort, 4 bits per pass, stable: equal keys stay in index order
+        const uint32_t *uk = reinterpret_cast<const uint32_t *>(w.TA);
+        uint16_t *src = reinterpret_cast<uint16_t *>(w.XB), *dst = src + CN;
+        const int E = CN / NTHR;
+        for (int shift = 0; shift < 32; shift += 4) {
+#pragma unroll
+            for (int d = 0; d < 16; d++) w.cnt[d * NTHR + tid] = 0;
+            for (int e = 0; e < E; e++) {
+                int dg = (uk[src[tid * E + e]] >> shift) & 15;
+                w.cnt[dg * NTHR + tid]++;
+            }
+            __syncthreads();
+            int loc = 0;
+#pragma unroll
+            for (int q = 0; q < 16; q++) loc += w.cnt[tid * 16 + q];
+            int tot, base = block_excl_sum<NTHR>(loc, sm.scan, tot);
+#pragma unroll
+            for (int q = 0; q < 16; q++) { int t = w.cnt[tid * 16 + q]; w.cnt[tid * 16 + q] = (uint16_t)base; base += t; }
+            __syncthreads();
+            for (int e = 0; e < E; e++) {
+                uint16_t ix = src[tid * E + e];
+                int dg = (uk[ix] >> shift) & 15;
+                int pos = w.cnt[dg * NTHR + tid]++;
+                dst[pos] = ix;
+            }
+            __syncthreads();
+            uint16_t *t = src; src = dst; dst = t;
+        }
+        // 8 passes: the sorted order is back in the first array.  Turn order into ranks (uint16 at TA).
+        __syncthreads();
+        uint16_t *rank = reinterpret_cast<uint16_t *>(w.TA);
+        // keys are dead now; but rank[] aliases them, so stage through registers
+        const uint16_t *ord = reinterpret_cast<const uint16_t *>(w.XB);
+        __syncthreads();
+        for (int r = tid; r < CN; r += NTHR) rank[ord[r]] = (uint16_t)r;
+        __syncthreads();
+    }
+
+    // ---------------- one coder pass (ulcEncoder_Encode.c:319-360); returns the size in bits ----------------
+    __device__ int encode_pass(int k, int nOut, bool write) {
+        const uint16_t *rank = reinterpret_cast<const uint16_t *>(w.TA);
+        uint16_t *selList = reinterpret_cast<uint16_t *>(w.TA) + CN;
+        uint8_t  *info = reinterpret_cast<uint8_t *>(w.XB);                       // [CN]
+        uint16_t *zoneStart = reinterpret_cast<uint16_t *>(info + CN);           // [CN]
+        uint8_t  *zoneQi = info + 3 * CN;                                         // [CN]
+        uint32_t *outW = reinterpret_cast<uint32_t *>(blk(k - 2));               // packed nybbles
+        const float *coef = w.XA, *pairs = w.TB;
+        const int E = CN / NTHR, U = NCH * sm.nsub, i0 = tid * E;
+        const int capNyb = 8 * ((CN >> 1) + 4);                                   // 2*CN + 16 bytes
+
+        // G1: selection, compaction in index order
+        int cntSel = 0;
+        for (int e = 0; e < E; e++) { info[i0 + e] = 0; cntSel += (int)rank[i0 + e] < nOut; }
+        int nSel, base = block_excl_sum<NTHR>(cntSel, sm.scan, nSel);
+        {
+            int b = base;
+            for (int e = 0; e < E; e++) {
+                const int i = i0 + e;
+                const int c = i / N, n = i - c * N;
+                for (int j = 0; j < sm.nsub; j++) if (n == sm.sub[j].off) sm.unitSel[c * sm.nsub + j] = b;
+                if ((int)rank[i] < nOut) selList[b++] = (uint16_t)i;
+            }
+            if (tid == 0) sm.unitSel[U] = nSel;
+        }
+        if (write) for (int i = tid; i < (CN >> 1) + 4; i += NTHR) outW[i] = 0u;
+        __syncthreads();
+
+        // G2: greedy quantiser zones, one thread per (channel, sub-block) (ulcEncoder_Encode.c:200-269)
+        if (tid < U) {
+            const int m0 = sm.unitSel[tid], m1 = sm.unitSel[tid + 1];
+            float lo = 1000.0f, hi = -1000.0f;
+            int z = 0, zs = -1, prevQ = -1;
+            for (int m = m0; m <= m1; m++) {
+                float newLo = 0.0f, newHi = hi, level = 0.0f;
+                if (m < m1) {
+                    level = fabsf(coef[selList[m]]);
+                    newLo = level < lo ? level : lo;
+                    newHi = level > hi ? level : hi;
+                    if (zs == -1) zs = m;
+                }
+                if (newHi > newLo * 4.0f) {
+                    int q = (int)(0x1.657006p2f + -0x1.715476p0f * logf_ref(hi));     // :83-88
+                    if (q < 5) q = 5;
+                    if (q > 31) q = 31;
+                    zoneStart[m0 + z] = (uint16_t)zs;
+                    zoneQi[m0 + z] = (uint8_t)q;
+                    z++;
+                    prevQ = q;
+                    zs = m;
+                    lo = hi = level;
+                } else { lo = newLo; hi = newHi; }
+            }
+            sm.unitZones[tid] = z;
+            sm.unitLastQ[tid] = prevQ;
+        }
+        __syncthreads();
+
+        // G2b: per selected coefficient, its zone's quantiser and header flags
+        for (int m = tid; m < nSel; m += NTHR) {
+            int u = 0;
+            while (m >= sm.unitSel[u + 1]) u++;
+            const int zb = sm.unitSel[u];
+            int loz = 0, hiz = sm.unitZones[u] - 1;                   // last zone whose start <= m
+            while (loz < hiz) { int mid = (loz + hiz + 1) >> 1; if ((int)zoneStart[zb + mid] <= m) loz = mid; else hiz = mid - 1; }
+            int q = zoneQi[zb + loz];
+            int inf = q;
+            if ((int)zoneStart[zb + loz] == m) {
+                if (loz == 0) inf |= INF_HDR | INF_FIRST;
+                else if (zoneQi[zb + loz - 1] != q) inf |= INF_HDR;
+            }
+            info[selList[m]] = (uint8_t)inf;
+        }
+        __syncthreads();
+
+        // G3: kept coefficients and the last kept index before each thread's slots
+        uint32_t keptMask = 0; int lastKeptP1 = 0;
+        for (int e = 0; e < E; e++) {
+            const int i = i0 + e, inf = info[i];
+            if (inf) {
+                float sc = coef[i] * (float)(1u << (inf & INF_Q));
+                if (!(fabsf(sc) < 2.5f)) { keptMask |= 1u << e; lastKeptP1 = i + 1; }   // :114
+            }
+        }
+        const int prevKeptP1 = block_excl_max<NTHR>(lastKeptP1, sm.scan);
+
+        // unit of this thread's slots (a thread's slots never straddle a sub-block: E divides every sub-block size)
+        const int c = i0 / N, nloc = i0 - c * N, j = find_sub(sm, nloc), u = c * sm.nsub + j;
+        const int uOff = c * N + sm.sub[j].off, uEnd = uOff + sm.sub[j].S;
+        const bool ownsTail = (i0 + E == uEnd);
+
+        auto walk = [&](auto &sink, bool cacheTail) {
+            int nc = prevKeptP1 > uOff ? prevKeptP1 : uOff;
+            for (int e = 0; e < E; e++) {
+                const int i = i0 + e, inf = info[i];
+                if (inf & INF_HDR) put_quant(sink, inf);
+                if (keptMask & (1u << e)) { put_item(sink, coef, pairs, nc, i, (float)(1u << (inf & INF_Q))); nc = i + 1; }
+            }
+            if (ownsTail) {                                           // :273-312
+                if (cacheTail) {
+                    uint32_t tok = 0; int len = 0;
+                    auto tput = [&](int x) { tok |= (uint32_t)(x & 15) << (4 * len); len++; };
+                    const int n = uEnd - nc, pq = sm.unitLastQ[u];
+                    if (n > 4) {
+                        if (pq != -1) tput(0xF);
+                        int nq = 0, dq = 0;
+                        if (pq != -1 && n >= 16) hf_ext_params(pairs, nc, n, (float)(1u << pq), nq, dq);
+                        if (nq) { tput(0xF); tput(nq - 1); tput(dq >> 4); tput(dq); }
+                        else { tput(0xE); tput(0xF); }
+                    } else if (n > 0) { tput(0x0); tput(n - 1); }
+                    sm.tailTok[u] = tok; sm.tailLen[u] = len;
+                }
+                const uint32_t tok = sm.tailTok[u]; const int len = sm.tailLen[u];
+                for (int q = 0; q < len; q++) sink.put((tok >> (4 * q)) & 15);
+            }
+        };
+
+        CountSink cs{0};
+        walk(cs, true);
+        int total, offs = block_excl_sum<NTHR>(cs.n, sm.scan, total);
+        const int hdr = (sm.wcCur & 8) ? 2 : 1;
+        if (write) {
+            WriteSink ws{outW, hdr + offs, capNyb};
+            walk(ws, false);
+            if (tid == 0) { WriteSink h{outW, 0, capNyb}; h.put(sm.wcCur); if (sm.wcCur & 8) h.put(sm.wcCur >> 4); }
+        }
+        __syncthreads();
+        return ((hdr + total) * 4 + 7) & ~7;
+    }
+};
+
+template <int NCH, int NTHR, bool GWS>
+__global__ void __launch_bounds__(NTHR, 1) ulcb_encode_kernel(UlcbEncodeArgs args) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int N = args.tb.N, CN = NCH * N, H = N >> 1;
+    const int tid = threadIdx.x;
+    EncSmall &sm = *reinterpret_cast<EncSmall *>(smraw);
+    Work wk;
+    {
+        unsigned char *p = smraw + ((sizeof(EncSmall) + 15) & ~(size_t)15);
+        wk.cnt = reinterpret_cast<uint16_t *>(p); p += 32 * NTHR;
+        wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
+        wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H;
+        float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
+        wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
+    }
+    Encoder<NCH, NTHR> enc(args, sm, wk);
+
+    for (int stream = blockIdx.x; stream < args.nStreams; stream += gridDim.x) {
+        const int nBlocks = args.nBlocks ? (int)args.nBlocks[stream] : args.nBlocksAll;
+        const long long nSamples = args.nSamples ? (long long)args.nSamples[stream] : (long long)nBlocks * N;
+        const size_t elem = args.pcmFloat ? 4 : 2;
+        const unsigned char *pcm = reinterpret_cast<const unsigned char *>(args.pcm) + (size_t)stream * args.inStride * elem;
+        UlcbEncStreamState *st = args.state ? args.state + stream : nullptr;
+        uint8_t *out = args.out + (size_t)stream * args.outStride;
+        uint64_t outPos = 0;
+        int overflow = 0;
+        uint32_t k0 = 0;
+
+        // ---- stream state ----
+        __syncthreads();
+        if (st && st->valid) {
+            k0 = st->calls;
+            const float *ss = args.stateSamples + (size_t)stream * 2 * CN;
+            for (int i = tid; i < CN; i += NTHR) { enc.blk((int)(k0 % 3) - 2)[i] = ss[i]; enc.blk((int)(k0 % 3) - 1)[i] = ss[CN + i]; }
+            if (tid == 0) {
+                for (int i = 0; i < 3; i++) sm.env[i] = st->env[i];
+                for (int i = 0; i < 16; i++) { sm.seg[i] = 0.0f; sm.seg[16 + i] = st->seg[i]; }
+                sm.wcNext = st->nextWindowCtrl; sm.wcCur = st->windowCtrl; sm.wcPrev = st->prevWindowCtrl;
+            }
+        } else {
+            for (int i = tid; i < 3 * CN; i += NTHR) wk.R[i] = 0.0f;
+            if (tid == 0) {
+                for (int i = 0; i < 3; i++) sm.env[i] = 0.0f;
+                for (int i = 0; i < 32; i++) sm.seg[i] = 0.0f;
+                sm.wcNext = 0x10; sm.wcCur = 0x10; sm.wcPrev = 0x10;          // libulc/ulcEncoder.c:70
+            }
+        }
+        const int kb = (int)(k0 % 3);                                         // only k mod 3 matters for the rotating buffers
+        __syncthreads();
+
+        for (int b = 0; b < nBlocks; b++) {
+            const int k = kb + b;
+            long long valid = nSamples - (long long)b * N;
+            enc.ingest(k, pcm + (size_t)b * N * NCH * elem, valid < 0 ? 0 : valid);
+            __syncthreads();
+            enc.window_control(k);
+            enc.fold(k);
+            __syncthreads();
+            enc.transform();
+            enc.analyse(k);
+            __syncthreads();
+            const size_t dbgBlk = ((size_t)stream * args.nBlocksAll + b);
+            if (args.dbgCoefs) for (int i = tid; i < CN; i += NTHR) args.dbgCoefs[dbgBlk * CN + i] = wk.XA[i];
+            enc.serial_sums(k);
+            __syncthreads();
+            enc.spread();
+            __syncthreads();
+            if (args.dbgNoise) for (int i = tid; i < CN; i += NTHR) args.dbgNoise[dbgBlk * CN + i] = wk.TB[i];
+            if (args.dbgMask) for (int i = tid; i < H; i += NTHR) args.dbgMask[dbgBlk * H + i] = wk.mask[i];
+            enc.make_keys(args.dbgKeys ? args.dbgKeys + dbgBlk * CN : nullptr);
+            __syncthreads();
+            enc.rank_sort();
+            if (args.dbgRanks) for (int i = tid; i < CN; i += NTHR) args.dbgRanks[dbgBlk * CN + i] = reinterpret_cast<const uint16_t *>(wk.TA)[i];
+
+            // ---- rate control (libulc/ulcEncoder.c:93-158) ----
+            const int maxCoef = sm.nNz;
+            const float cx = sm.cx;
+            int size, nOutUsed;
+            if (args.mode == ULCB_ENC_VBR) {
+                int nOut = maxCoef;
+                if (args.param > 0.0f) {
+                    float f = (float)(NCH * N) * cx / args.param;
+                    if (f < (float)maxCoef) nOut = (int)f;
+                }
+                nOutUsed = nOut;
+                size = enc.encode_pass(k, nOut, true);
+            } else {
+                float kbps = args.param;
+                if (args.mode == ULCB_ENC_ABR) kbps = args.param * cx / args.avgComplexity;
+                const int budget = (int)(((float)N * kbps) * 1000.0f / (float)args.tb.rateHz);
+                int lo = 0, hi = maxCoef, nOut = -1;
+                if (lo < hi) do {
+                    nOut = (int)((unsigned)(lo + hi) / 2u);
+                    size = enc.encode_pass(k, nOut, false);
+                    if (size < budget) lo = nOut;
+                    else if (size > budget) hi = nOut - 1;
+                    else { lo = nOut; break; }
+                } while (lo < hi - 1);
+                nOutUsed = lo;
+                size = enc.encode_pass(k, lo, true);
+            }
+            if (args.dbgCounts && tid == 0) { args.dbgCounts[dbgBlk * 2] = maxCoef; args.dbgCounts[dbgBlk * 2 + 1] = nOutUsed; }
+
+            // ---- emit ----
+            const int nBytes = size >> 3;
+            if (!overflow && outPos + (uint64_t)nBytes > args.outStride) overflow = 1;
+            if (!overflow) {
+                const uint8_t *ob = reinterpret_cast<const uint8_t *>(enc.blk(k - 2));
+                for (int i = tid; i < nBytes; i += NTHR) out[outPos + i] = ob[i];
+            }
+            if (tid == 0) {
+                const size_t mi = (size_t)stream * args.metaStride + b;
+                if (args.blockBytes) args.blockBytes[mi] = overflow ? 0u : (uint32_t)nBytes;
+                if (args.complexity) args.complexity[mi] = cx;
+                if (args.windowCtrl) args.windowCtrl[mi] = sm.wcCur;
+            }
+            if (!overflow) outPos += (uint64_t)nBytes;
+            __syncthreads();
+        }
+
+        // ---- save state ----
+        if (st) {
+            const int k = kb + nBlocks;
+            float *ss = args.stateSamples + (size_t)stream * 2 * CN;
+            for (int i = tid; i < CN; i += NTHR) { ss[i] = enc.blk(k - 2)[i]; ss[CN + i] = enc.blk(k - 1)[i]; }
+            if (tid == 0) {
+                st->valid = 1; st->calls = k0 + (uint32_t)nBlocks;
+                for (int i = 0; i < 3; i++) st->env[i] = sm.env[i];
+                for (int i = 0; i < 16; i++) st->seg[i] = sm.seg[16 + i];
+                st->nextWindowCtrl = sm.wcNext; st->windowCtrl = sm.wcCur; st->prevWindowCtrl = sm.wcPrev;
+                st->complexity = sm.cx;
+            }
+        }
+        if (tid == 0) {
+            if (args.totalBytes) args.totalBytes[stream] = outPos;
+            if (args.status) args.status[stream] = overflow;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4096; }
+int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }
+size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)7 * nChan * N + 64; }
+size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs) {
+    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N;
+    if (!globalWs) s += sizeof(float) * ulcb_encode_ws_floats(N, nChan);
+    return s + 16;
+}
+
+template <int NCH, int NTHR>
+static cudaError_t launch_e(const UlcbEncodeArgs &args, int gridBlocks, cudaStream_t stream) {
+    const bool gws = args.workspace != nullptr;
+    void (*k)(UlcbEncodeArgs) = gws ? ulcb_encode_kernel<NCH, NTHR, true> : ulcb_encode_kernel<NCH, NTHR, false>;
+    size_t smem = ulcb_encode_smem_bytes(args.tb.N, NCH, NTHR, gws);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<gridBlocks, NTHR, smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+cudaError_t ulcb_encode_launch(const UlcbEncodeArgs &args, int nChan, int gridBlocks, cudaStream_t stream) {
+    const int nthr = ulcb_encode_threads(args.tb.N, nChan);
+    if (nChan == 2) return nthr == 512 ? launch_e<2, 512>(args, gridBlocks, stream) : launch_e<2, 256>(args, gridBlocks, stream);
+    if (nChan == 1) return nthr == 512 ? launch_e<1, 512>(args, gridBlocks, stream) : launch_e<1, 256>(args, gridBlocks, stream);
+    return cudaErrorInvalidValue;
+}
