@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Aggregate an ncu report's source page by CUDA source line: python scripts/ncu_lines.py <rep> [top]"""
-import csv, subprocess, sys
+import csv, os, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
@@ -16,7 +16,7 @@ print(f"total samples {ts}, total warp-instructions {ti}")
 by_file = {}
 for o in out: by_file.setdefault(o[2], [0, 0]); by_file[o[2]][0] += o[0]; by_file[o[2]][1] += o[1]
 for f, (s, i) in by_file.items(): print(f"  {f}: {100*s/ts:.1f}% samples, {100*i/ti:.1f}% instructions")
-out.sort(key=lambda o: -o[0])
+out.sort(key=lambda o: -o[1] if os.environ.get("BY_INSTR") else -o[0])
 for s, i, f, ln, src, st in out[:top]:
     big = sorted(st.items(), key=lambda kv: -kv[1])[:3]
     print(f"{100*s/ts:5.1f}%smp {100*i/ti:5.1f}%ins {f[:14]:>14}:{ln:>4} {src[:80]:80} | " + " ".join(f"{k.replace('stall_','')}={v}" for k, v in big if v))

@@ -1,0 +1,47 @@
+"""GPU: time the batched encoder on replicated synthetic streams (device-resident input)."""
+import sys, os, time, argparse
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ulc_codec_b200 import capi, corpus
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--streams", type=int, default=296)
+ap.add_argument("--seconds", type=float, default=10.0)
+ap.add_argument("--bs", type=int, default=2048)
+ap.add_argument("--mode", default="vbr")
+ap.add_argument("--rate", type=float, default=50.0)
+ap.add_argument("--distinct", type=int, default=8)
+ap.add_argument("--kind", default="music")
+ap.add_argument("--reps", type=int, default=2)
+a = ap.parse_args()
+N, C = a.bs, 2
+ns = int(a.seconds * 44100)
+dev = torch.device("cuda", 0)
+with capi.Context(44100, C, N) as ctx:
+    nb = ctx.blocks_for(ns)
+    stride = ns * C
+    base = [torch.from_numpy(corpus.generate(1000 + d, ns, a.kind).reshape(-1)).to(dev) for d in range(a.distinct)]
+    pcm = torch.empty(a.streams * stride, dtype=torch.int16, device=dev)
+    for s in range(a.streams):
+        pcm[s * stride:(s + 1) * stride] = base[s % a.distinct]
+    ostride = nb * 1200 if a.mode == "vbr" else nb * 2048
+    out = torch.empty(a.streams * ostride, dtype=torch.uint8, device=dev)
+    bb = torch.zeros(a.streams * nb, dtype=torch.int32, device=dev)
+    st = torch.zeros(a.streams, dtype=torch.int32, device=dev)
+    nsamp = torch.full((a.streams,), ns, dtype=torch.int64, device=dev)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+    def step():
+        ctx.encode_streams_device(a.streams, pcm.data_ptr(), "pcm16", stride, nb, a.mode, a.rate, out.data_ptr(), ostride,
+                                  avg_complexity=0.8, d_nsamples=nsamp.data_ptr(), d_block_bytes=bb.data_ptr(), meta_stride=nb, d_status=st.data_ptr())
+    torch.cuda.synchronize()
+    step(); ctx.sync()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(a.reps): step()
+    e1.record(ext); ctx.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.reps
+    audio = a.streams * nb * N / 44100
+    byts = int(bb.sum().item())
+    print(f"encode {a.mode} {a.rate} N={N} streams={a.streams} blocks/stream={nb}: {ms:.1f} ms/launch, {audio / (ms / 1e3):.0f} x realtime, "
+          f"{ms * 1e3 / (nb * a.streams) * min(a.streams, 148):.1f} us per block per SM-slot, avg {byts / (a.streams * nb):.1f} B/block, status bad {int((st != 0).sum())}")

@@ -1,0 +1,166 @@
+"""GPU parity tests for the batched encoder (through the C ABI) against the reference-generated golden
+fixtures and the oracle.
+
+Bar (BASELINE.json north_star, criterion 2): MDCT coefficients within 1e-5, the nybble stream byte-identical
+whenever the quantised coefficients match.  This implementation evaluates the reference's own DCT flow graph
+and operation order, so the tests demand more: coefficients, window decisions, keys, noise spectra and the
+encoded BYTES are bit-identical to the stock scalar reference build.  The only freedom left is libm's last ulp
+in logf (BlockComplexity may differ by 1 ulp in rare blocks) and the order of EQUAL sort keys (a heapsort
+artefact in the reference).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.fixtures import GOLDEN_NAMES, golden_pcm, load_golden_stream, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from ulc_codec_b200 import capi as m
+    return m
+
+
+def _ulps(a, b):
+    return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_encode_golden_bytes(capi, name):
+    """Bytes, block sizes, window control, complexity against the fixture the compiled reference produced."""
+    g = load_golden_stream(name)
+    pcm = golden_pcm(g)
+    with capi.Context(g["rate_hz"], g["n_chan"], g["block_size"]) as ctx:
+        r = ctx.encode_streams([pcm], g["mode"], g["param"], g["avg_complexity"])
+    assert r["status"][0] == 0
+    assert np.array_equal(r["block_bytes"][0], g["block_bytes"])
+    assert np.array_equal(r["window_ctrl"][0], g["window_ctrl"])
+    assert np.array_equal(r["streams"][0], g["data"])                      # byte-identical stream
+    assert _ulps(r["complexity"][0], g["complexity"]).max() <= 1
+
+
+@pytest.mark.parametrize("name", ["music_vbr50_bs2048", "transient_vbr50_bs2048", "transient_abr64_bs256", "music_vbr60_bs4096",
+                                  "transient_abr64_bs8192"])
+def test_encode_stages(capi, name):
+    """Stage taps: MDCT coefficients (golden SHA), noise spectrum, masking curve, sort keys, counts, ranks."""
+    g = load_golden_stream(name)
+    pcm = golden_pcm(g)
+    N, Cn = g["block_size"], g["n_chan"]
+    o = oracle.Encoder(g["rate_hz"], Cn, N).encode_stream(pcm, g["mode"], g["param"], g["avg_complexity"], dump="all")
+    with capi.Context(g["rate_hz"], Cn, N) as ctx:
+        r = ctx.encode_streams([pcm], g["mode"], g["param"], g["avg_complexity"], taps=True)
+    assert sha(r["coefs"][0]) == g["coefs_sha256"]                         # criterion 2, at 0 tolerance
+    assert np.array_equal(r["coefs"][0], o["coefs"])
+    assert np.array_equal(r["mask"][0], o["mask"])
+    assert np.array_equal(r["keys"][0], o["keys"])
+    assert np.array_equal(r["counts"][0][:, 0], o["n_nz"])
+    assert np.array_equal(r["counts"][0][:, 1], o["n_out"])
+    assert _ulps(r["noise"][0], o["noise"]).max() <= 1                     # expf last ulp
+    assert (r["noise"][0] != o["noise"]).mean() < 1e-6
+    # ranks: a permutation that sorts the keys in descending order; identical to the reference wherever keys are unique
+    for b in range(len(o["ranks"])):
+        rk, keys = r["ranks"][0][b], o["keys"][b]
+        assert np.array_equal(np.sort(rk), np.arange(Cn * N))
+        by_gpu, by_ref = keys[np.argsort(rk)], keys[np.argsort(o["ranks"][b])]
+        nz = o["n_nz"][b]
+        assert np.array_equal(by_gpu[:nz], by_ref[:nz])
+        assert np.all(np.diff(by_gpu[:nz]) <= 0)
+    assert np.array_equal(r["streams"][0], o["data"])
+
+
+def test_encode_batch_ragged(capi):
+    """Many streams in one call: different lengths (zero padded to the common block count), music and transients."""
+    from ulc_codec_b200 import corpus
+    pcms = [corpus.generate(100 + i, 9000 + 3777 * i, "music" if i % 2 else "transient") for i in range(11)]
+    pcms.append(np.zeros((5000, 2), np.int16))                              # digital silence
+    with capi.Context(44100, 2, 2048) as ctx:
+        nb = ctx.blocks_for(max(len(p) for p in pcms))
+        r = ctx.encode_streams(pcms, "vbr", 55.0)
+    for i, p in enumerate(pcms):
+        pad = np.zeros(((nb - 2) * 2048, 2), np.int16)
+        pad[:len(p)] = p
+        o = oracle.Encoder(44100, 2, 2048).encode_stream(pad, "vbr", 55.0)
+        assert len(o["block_bytes"]) == nb
+        assert np.array_equal(r["block_bytes"][i], o["block_bytes"]), i
+        assert np.array_equal(r["streams"][i], o["data"]), i
+        assert np.array_equal(r["window_ctrl"][i], o["window_ctrl"]), i
+
+
+def test_encode_mono_and_float_input(capi):
+    from ulc_codec_b200 import corpus
+    pcm = corpus.generate(22, 30000, "music")[:, :1].copy()
+    pcm[8000:16000] = 0                                                     # -inf keys, silent sub-blocks (Eh,Fh)
+    o = oracle.Encoder(44100, 1, 2048).encode_stream(pcm, "vbr", 70.0)
+    with capi.Context(44100, 1, 2048) as ctx:
+        a = ctx.encode_streams([pcm], "vbr", 70.0)
+        b = ctx.encode_streams([pcm.astype(np.float32) * np.float32(2.0 ** -15)], "vbr", 70.0)
+    assert np.array_equal(a["streams"][0], o["data"])
+    assert np.array_equal(b["streams"][0], o["data"])                       # float input path, same samples
+
+
+@pytest.mark.parametrize("mode,rate,avgc,bs", [("cbr", 96.0, 0.0, 1024), ("abr", 80.0, 0.75, 2048), ("vbr", 35.0, 0.0, 512)])
+def test_encode_rate_modes(capi, mode, rate, avgc, bs):
+    """CBR/ABR binary search on the device (libulc/ulcEncoder.c:93-135) and VBR at other block sizes."""
+    from ulc_codec_b200 import corpus
+    pcm = corpus.generate(31, 44100 * 2, "music")
+    o = oracle.Encoder(44100, 2, bs).encode_stream(pcm, mode, rate, avgc)
+    with capi.Context(44100, 2, bs) as ctx:
+        r = ctx.encode_streams([pcm], mode, rate, avgc)
+    assert np.array_equal(r["block_bytes"][0], o["block_bytes"])
+    assert np.array_equal(r["streams"][0], o["data"])
+    if mode == "cbr":
+        budget = int(np.float32(np.float32(np.float32(bs) * np.float32(rate)) * np.float32(1000.0)) / np.float32(44100))
+        assert (r["block_bytes"][0] * 8 <= budget).all()                    # CBR never exceeds the target (include/ulcEncoder.h:103-107)
+
+
+def test_dropin_encoder_api(capi):
+    """ULC_EncoderState_Init / ULC_EncodeBlock_VBR / _CBR with the reference's calling convention
+    (tools/ulcEncodeTool.c:133-168): one interleaved float block per call, state carried on the device."""
+    g = load_golden_stream("transient_vbr50_bs2048")
+    pcm = golden_pcm(g)
+    nb, N = 20, 2048
+    x = np.zeros((nb * N, 2), np.float32)
+    x[:] = pcm[:nb * N].astype(np.float32) * np.float32(2.0 ** -15)
+    ref = oracle.Encoder(44100, 2, N)
+    e = capi.DropinEncoder(44100, 2, N)
+    for b in range(nb):
+        mode, rate = ("vbr", 50.0) if b % 5 else ("cbr", 112.0)            # modes may change from call to call
+        want = ref.encode_block(x[b * N:(b + 1) * N], mode, rate)
+        got = e.encode_block(x[b * N:(b + 1) * N], mode, rate)
+        assert got == want, b
+        assert e.st.WindowCtrl == ref.window_ctrl
+        assert abs(e.st.BlockComplexity - ref.complexity) < 1e-6
+    e.close()
+
+
+def test_encode_arena_overflow_is_flagged(capi):
+    from ulc_codec_b200 import corpus
+    pcm = corpus.generate(40, 30000, "music")
+    with capi.Context(44100, 2, 2048) as ctx:
+        full = ctx.encode_streams([pcm], "vbr", 60.0)
+        small = ctx.encode_streams([pcm], "vbr", 60.0, out_stride=int(full["block_bytes"][0][:5].sum()) + 3)
+    assert full["status"][0] == 0 and small["status"][0] == 1
+    assert np.array_equal(small["block_bytes"][0][:5], full["block_bytes"][0][:5])
+    assert not small["block_bytes"][0][5:].any()
+    n = int(full["block_bytes"][0][:5].sum())
+    assert np.array_equal(small["streams"][0][:n], full["streams"][0][:n])
+
+
+def test_roundtrip_gpu_encode_gpu_decode(capi):
+    """Criterion 3 in its strongest form: the GPU-encoded stream IS the reference-encoded stream (byte-identical),
+    so the decoded SNR gap is 0 dB; here the full GPU round trip is checked against the input."""
+    from ulc_codec_b200 import corpus
+    pcm = corpus.generate(50, 44100 * 2, "music")
+    N = 2048
+    with capi.Context(44100, 2, N) as ctx:
+        enc = ctx.encode_streams([pcm], "vbr", 80.0)
+        nb = enc["block_bytes"].shape[1]
+        dec, status, _ = ctx.decode_streams([enc["streams"][0]], nb, fmt="f32")
+    assert status[0] == -1
+    x = pcm.astype(np.float64) / 32768.0
+    y = dec[0][2 * N:2 * N + len(x)].astype(np.float64)                    # codec delay = 2 blocks
+    n = min(len(x), len(y)) - N
+    snr = 10 * np.log10((x[:n] ** 2).sum() / ((x[:n] - y[:n]) ** 2).sum())
+    assert snr > 12.0, snr

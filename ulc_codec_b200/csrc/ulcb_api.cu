@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -172,6 +173,7 @@ int build_enc_tables(ULCB_Context *ctx) {
     k = expf(-0x1.1AF110p-6f * N / rate); t.c1Blk = 1.0f - k;
     const float nyq = (float)rate * 0.5f;
     std::vector<int16_t> edges(4 * 2 * ULCB_NBARK * 2);
+    std::vector<int16_t> events(4 * 2 * 2 * ULCB_NBARK * 2);
     std::vector<uint8_t> lband;
     std::vector<float> lfrac;
     for (int sh = 0; sh < 4; sh++) {
@@ -184,6 +186,16 @@ int build_enc_tables(ULCB_Context *ctx) {
                 edges[((sh * 2 + kind) * ULCB_NBARK + b) * 2 + 0] = (int16_t)beg;
                 edges[((sh * 2 + kind) * ULCB_NBARK + b) * 2 + 1] = (int16_t)end;
             }
+        for (int kind = 0; kind < 2; kind++) {
+            // the 50 band edges in walking order: by position; at equal positions begins first (an empty band's begin
+            // must be recorded before its end is evaluated), then by band so that levels carry over in band order
+            const int16_t *ed = &edges[((sh * 2 + kind) * ULCB_NBARK) * 2];
+            std::vector<int> key;
+            for (int b = 0; b < ULCB_NBARK; b++) { key.push_back((ed[2 * b] << 8) | (0 << 7) | b); key.push_back((ed[2 * b + 1] << 8) | (1 << 7) | b); }
+            std::sort(key.begin(), key.end());
+            int16_t *ev = &events[((sh * 2 + kind) * 2 * ULCB_NBARK) * 2];
+            for (size_t e = 0; e < key.size(); e++) { ev[2 * e] = (int16_t)(key[e] >> 8); ev[2 * e + 1] = (int16_t)(key[e] & 0xFF); }
+        }
         t.lineOff[sh] = (int)lband.size();
         for (int i = 0; i < n; i++) {                                  // ulcEncoder_Psyopt.c:136-152
             float bb = line_to_bark(i, nyq, n);
@@ -194,6 +206,7 @@ int build_enc_tables(ULCB_Context *ctx) {
     }
     int rc;
     if ((rc = upload(ctx, edges, &t.edges))) return rc;
+    if ((rc = upload(ctx, events, &t.events))) return rc;
     if ((rc = upload(ctx, lband, &t.lineBand))) return rc;
     if ((rc = upload(ctx, lfrac, &t.lineFrac))) return rc;
     return ULCB_OK;

@@ -260,7 +260,11 @@ __device__ __forceinline__ void dct2_leaf8(float *x) {
 
 __device__ __forceinline__ int find_sub(const EncSmall &sm, int n) {     // sub-block holding in-channel index n
     int j = 0;
-    while (j + 1 < sm.nsub && n >= sm.sub[j + 1].off) j++;
+    const int ns = sm.nsub;
+    if (ns > 1) {
+        j = (n >= sm.sub[1].off);
+        if (ns > 2) { j += (n >= sm.sub[2].off); if (ns > 3) j += (n >= sm.sub[3].off); }
+    }
     return j;
 }
 
@@ -407,6 +411,7 @@ struct Encoder {
         if (tid == 0) {
             float php = sm.env[0], pbp = sm.env[1];
             const float a1 = tb.c1PostHp, a2 = tb.c1PostBp;
+#pragma unroll 4
             for (int n = 0; n < N; n++) {                            // post-masking envelopes (:73-88)
                 float2 e = E[n];
                 float dh = e.x - php, db = e.y - pbp;
@@ -416,6 +421,7 @@ struct Encoder {
             sm.env[0] = php; sm.env[1] = pbp;
             float qhp = php, qbp = pbp;
             const float b1 = tb.c1PreHp, b2 = tb.c1PreBp;
+#pragma unroll 4
             for (int n = N - 1; n >= 0; n--) {                       // pre-masking, backwards (:92-104)
                 float2 e = E[n];
                 float dh = e.x - qhp, db = e.y - qbp;
@@ -429,6 +435,7 @@ struct Encoder {
             for (int s = 0; s < 8; s++) {                            // block-mask envelope into 8 segment sums (:107-134)
                 sm.seg[2 * s] = sm.seg[16 + 2 * s]; sm.seg[2 * s + 1] = sm.seg[16 + 2 * s + 1];
                 float acc = 0.0f, cnt = 0.0f;
+#pragma unroll 4
                 for (int n = 0; n < bin; n++) {
                     float d = E[s * bin + n].x - m;
                     m += d * cb;
@@ -479,7 +486,7 @@ struct Encoder {
     __device__ void fold(int k) {
         const float *R1 = blk(k - 1), *R2 = blk(k - 2);
         for (int P = tid; P < NCH * H; P += NTHR) {
-            const int c = P / H, r = P - c * H;
+            const int c = P >> (tb.log2N - 1), r = P & (H - 1);
             const int j = find_sub(sm, 2 * r);
             const SubInfo s = sm.sub[j];
             const int hS = s.S >> 1, i = r - (s.off >> 1);
@@ -509,9 +516,9 @@ struct Encoder {
     // ---------------- breadth-first DCT-IV of every (buffer, channel, sub-block) ----------------
     __device__ __forceinline__ void locate(int P, int &hb, int &cbase, int &j, int &lp) const {
         // pair index P in [0, CN) -> buffer half, channel base, sub-block, local pair index
-        const int half = CN >> 1;
-        hb = P >= half; int pp = P - (hb ? half : 0);
-        int c = pp / H, r = pp - c * H;
+        const int lgH = tb.log2N - 1;
+        const int cc = P >> lgH, r = P & (H - 1);                     // cc = hb*NCH + c
+        hb = cc >= NCH; const int c = hb ? cc - NCH : cc;
         j = find_sub(sm, 2 * r);
         lp = r - (sm.sub[j].off >> 1);
         cbase = c * N + sm.sub[j].off;
@@ -543,7 +550,7 @@ struct Encoder {
             const int half = CN >> 3;
             int hb = Lf >= half; int q = Lf - (hb ? half : 0);
             int pos = q << 3;                                         // element position in [0, CN)
-            int c = pos / N, n = pos - c * N;
+            int c = pos >> tb.log2N, n = pos & (N - 1);
             int j = find_sub(sm, n);
             const SubInfo &s = sm.sub[j];
             int d = s.lgS - 3, node = (n - s.off) >> 3;
@@ -618,18 +625,35 @@ struct Encoder {
 
     // ---------------- serial sums: complexity + Bark band analysis ----------------
     __device__ void band_unit(int unit, const float *v, const float *lg, int n, int sh, int kind) {
-        // running f64 sums in index order (struct LineSum_t, ulcEncoder_Psyopt.c:16-51), sampled at the band edges
+        // running f64 sums in index order (struct LineSum_t, ulcEncoder_Psyopt.c:16-51), sampled at the band edges.
+        // The 50 edges are walked in position order from a host-sorted list, so the inner loop is a bare accumulation.
+        const int16_t *ev = tb.events + ((sh * 2 + kind) * 2 * ULCB_NBARK) * 2;
         const int16_t *ed = tb.edges + ((sh * 2 + kind) * ULCB_NBARK) * 2;
         double sLg = 0.0, sWlg = 0.0, sW = 0.0;
-        int pb = 0, pe = 0;
         float level = kind ? 0.0f : -100.0f;
-        for (int i = 0; i <= n; i++) {
-            while (pb < ULCB_NBARK && ed[2 * pb] == i) { sm.lo[unit][pb][0] = sLg; sm.lo[unit][pb][1] = sWlg; sm.lo[unit][pb][2] = sW; pb++; }
-            while (pe < ULCB_NBARK && ed[2 * pe + 1] == i) {
-                // band pe is complete (its begin edge was passed earlier or just now)
-                double dLg = sLg - sm.lo[unit][pe][0], dWlg = sWlg - sm.lo[unit][pe][1], dW = sW - sm.lo[unit][pe][2];
-                int beg = ed[2 * pe], end = ed[2 * pe + 1];
+        int i = 0;
+        for (int e = 0; e < 2 * ULCB_NBARK; e++) {
+            const int pos = __ldg(&ev[2 * e]), code = __ldg(&ev[2 * e + 1]);
+            for (; i + 4 <= pos; i += 4) {
+                float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
+                float l0 = lg[i], l1 = lg[i + 1], l2 = lg[i + 2], l3 = lg[i + 3];
+                double X0 = (double)x0, X1 = (double)x1, X2 = (double)x2, X3 = (double)x3;
+                double L0 = (double)l0, L1 = (double)l1, L2 = (double)l2, L3 = (double)l3;
+                double p0 = L0 * X0, p1 = L1 * X1, p2 = L2 * X2, p3 = L3 * X3;
+                sLg += L0; sLg += L1; sLg += L2; sLg += L3;
+                sWlg += p0; sWlg += p1; sWlg += p2; sWlg += p3;
+                sW += X0; sW += X1; sW += X2; sW += X3;
+            }
+            for (; i < pos; i++) {
+                double x = (double)v[i], l = (double)lg[i];
+                sLg += l; sWlg += l * x; sW += x;
+            }
+            const int b = code & 0x7F;
+            if (!(code & 0x80)) { sm.lo[unit][b][0] = sLg; sm.lo[unit][b][1] = sWlg; sm.lo[unit][b][2] = sW; }
+            else {
+                double dLg = sLg - sm.lo[unit][b][0], dWlg = sWlg - sm.lo[unit][b][1], dW = sW - sm.lo[unit][b][2];
                 if (dW > 0.0) {
+                    const int beg = __ldg(&ed[2 * b]), end = __ldg(&ed[2 * b + 1]);
                     if (kind == 0) {                                  // noise level (ulcEncoder_Psyopt.c:206-222)
                         double inv = 1.0 / (double)(end - beg);
                         dWlg = dWlg / dW;
@@ -641,22 +665,25 @@ struct Encoder {
                         level = (float)(dWlg - dLg - log(dW));
                     }
                 }
-                sm.band[unit][pe] = level;
-                pe++;
-            }
-            if (i < n) {
-                double x = (double)v[i], l = (double)lg[i];
-                sLg += l; sWlg += l * x; sW += x;
+                sm.band[unit][b] = level;
             }
         }
-        // bands whose edges were never reached cannot exist: every edge is clamped to [0, n]
     }
     __device__ void serial_sums(int k) {
         const float *lgN = blk(k - 2);
         const int U = NCH * sm.nsub;
-        if (tid == 0) {                                               // block complexity (ulcEncoder_BlockTransform.c:310-325)
+        constexpr int NW = NTHR / 32;
+        const int warp = tid >> 5, lane = tid & 31;
+        if (tid == NTHR - 1) {                                        // block complexity (ulcEncoder_BlockTransform.c:310-325)
             float sq = 0.0f, ab = 0.0f;
-            for (int i = 0; i < CN; i++) { float re = w.XA[i]; sq += re * re; ab += fabsf(re); }
+            const float4 *x4 = reinterpret_cast<const float4 *>(w.XA);
+#pragma unroll 2
+            for (int i = 0; i < (CN >> 2); i++) {
+                float4 r = x4[i];
+                float a0 = r.x * r.x, a1 = r.y * r.y, a2 = r.z * r.z, a3 = r.w * r.w;
+                sq += a0; sq += a1; sq += a2; sq += a3;
+                ab += fabsf(r.x); ab += fabsf(r.y); ab += fabsf(r.z); ab += fabsf(r.w);
+            }
             float cx = sq;
             if (cx != 0.0f) {
                 float scale = kLn2f * (float)tb.log2N;
@@ -665,8 +692,10 @@ struct Encoder {
                 if (cx > 1.0f) cx = 1.0f;
             }
             sm.cx = cx;
-        } else if (tid >= 32 && tid < 32 + U + sm.nsub) {
-            int u = tid - 32;
+        }
+        // one Bark analysis unit per (warp, lane) slot, spread over the warps so that units run concurrently
+        const int u = lane * NW + warp;
+        if (lane < 2 && u < U + sm.nsub) {
             if (u < U) {
                 int c = u / sm.nsub, j = u - c * sm.nsub;
                 const SubInfo &s = sm.sub[j];
@@ -709,7 +738,7 @@ struct Encoder {
         uint32_t *uk = reinterpret_cast<uint32_t *>(w.TA);
         uint16_t *idxA = reinterpret_cast<uint16_t *>(w.XB);
         for (int i = tid; i < CN; i += NTHR) {
-            const int c = i / N, n = i - c * N;
+            const int c = i >> tb.log2N, n = i & (N - 1);
             float key = w.TA[i];
             key = 2.0f * key + w.mask[n >> 1] + -0x1.62E430p0f * (float)(c & 1);     // ulcEncoder_BlockTransform.c:337-345
             if (dbgKeys) dbgKeys[i] = key;
@@ -778,7 +807,7 @@ struct Encoder {
             int b = base;
             for (int e = 0; e < E; e++) {
                 const int i = i0 + e;
-                const int c = i / N, n = i - c * N;
+                const int c = i >> tb.log2N, n = i & (N - 1);
                 for (int j = 0; j < sm.nsub; j++) if (n == sm.sub[j].off) sm.unitSel[c * sm.nsub + j] = b;
                 if ((int)rank[i] < nOut) selList[b++] = (uint16_t)i;
             }
@@ -846,7 +875,7 @@ struct Encoder {
         const int prevKeptP1 = block_excl_max<NTHR>(lastKeptP1, sm.scan);
 
         // unit of this thread's slots (a thread's slots never straddle a sub-block: E divides every sub-block size)
-        const int c = i0 / N, nloc = i0 - c * N, j = find_sub(sm, nloc), u = c * sm.nsub + j;
+        const int c = i0 >> tb.log2N, nloc = i0 & (N - 1), j = find_sub(sm, nloc), u = c * sm.nsub + j;
         const int uOff = c * N + sm.sub[j].off, uEnd = uOff + sm.sub[j].S;
         const bool ownsTail = (i0 + E == uEnd);
 

@@ -21,6 +21,9 @@ struct UlcbEncTables {
     //   edges[((sh*2 + kind)*NBARK + b)*2 + {0,1}] = {beg, end};  kind 0 = noise spectrum [b, b+2),
     //   kind 1 = masking [b-0.75, b+0.25)
     const int16_t *edges;
+    // the same edges as a walk list: events[((sh*2 + kind)*2*NBARK + e)*2 + {0,1}] = {line position, band | 0x80 if end},
+    // sorted by position (begins before ends at equal positions, then by band)
+    const int16_t *events;
     // per-line Bark interpolation for shift sh, line i: index lineOff[sh] + i -> band index (int)bark, frac
     const uint8_t *lineBand;
     const float   *lineFrac;
