@@ -53,6 +53,7 @@ struct EncSmall {
     SubInfo sub[4];
     int     nsub;
     int     wcPrev, wcCur, wcNext;
+    int     wcRing[2];               // decisions published by the detector warp
     int     nNz;
     float   cx;
     int     unitSel[MAXU + 1];
@@ -134,7 +135,12 @@ __device__ __forceinline__ bool node_is_dct4(int d, int node) {   // root = DCT-
     return ones & 1;
 }
 
-// CTA-wide exclusive scans of one int per thread.  `scr` = smem int[NTHR/32 + 2].
+// The CTA is NTHR worker threads + one extra warp that runs the transient detector one block ahead.
+// Workers synchronise among themselves on named barrier 1; barrier 0 joins everybody once per block.
+template <int NTHR> __device__ __forceinline__ void wsync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory"); }
+template <int NTHR> __device__ __forceinline__ void fsync() { asm volatile("bar.sync 0, %0;" ::"n"(NTHR + 32) : "memory"); }
+
+// Worker-wide exclusive scans of one int per thread.  `scr` = smem int[NTHR/32 + 2].
 template <int NTHR>
 __device__ __forceinline__ int block_excl_sum(int v, int *scr, int &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,9 +148,9 @@ __device__ __forceinline__ int block_excl_sum(int v, int *scr, int &total) {
     int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    __syncthreads();
+    wsync<NTHR>();
     if (lane == 31) scr[warp] = inc;
-    __syncthreads();
+    wsync<NTHR>();
     if (warp == 0) {
         int t = lane < NW ? scr[lane] : 0, ti = t;
 #pragma unroll
@@ -152,7 +158,7 @@ __device__ __forceinline__ int block_excl_sum(int v, int *scr, int &total) {
         if (lane < NW) scr[lane] = ti - t;
         if (lane == 31) scr[NW] = ti;
     }
-    __syncthreads();
+    wsync<NTHR>();
     total = scr[NW];
     return inc - v + scr[warp];
 }
@@ -165,9 +171,9 @@ __device__ __forceinline__ int block_excl_max(int v, int *scr) {     // v >= 0; 
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, t); }
     int exl = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) exl = 0;
-    __syncthreads();
+    wsync<NTHR>();
     if (lane == 31) scr[warp] = inc;
-    __syncthreads();
+    wsync<NTHR>();
     if (warp == 0) {
         int t = lane < NW ? scr[lane] : 0, ti = t;
 #pragma unroll
@@ -176,7 +182,7 @@ __device__ __forceinline__ int block_excl_max(int v, int *scr) {     // v >= 0; 
         if (lane == 0) te = 0;
         if (lane < NW) scr[lane] = te;
     }
-    __syncthreads();
+    wsync<NTHR>();
     return max(exl, scr[warp]);
 }
 
@@ -392,61 +398,12 @@ struct Encoder {
         }
     }
 
-    // ---------------- transient detector ----------------
-    __device__ void window_control(int k) {
-        const float *R0 = blk(k), *R1 = blk(k - 1);
-        float2 *E = reinterpret_cast<float2 *>(w.TA);
-        for (int n = tid; n < N; n += NTHR) {
-            float ehp = 0.0f, ebp = 0.0f;
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                auto z = [&](int i) -> float { return (i < H) ? R1[c * N + H + i] : R0[c * N + i - H]; };
-                float t0 = z(n - 1), t1 = z(n), t2 = z(n + 1);
-                float hp = (-t0 + 2.0f * t1) - t2, bp = -t0 + t2;
-                ehp += hp * hp; ebp += bp * bp;
-            }
-            E[n] = make_float2(sqrtf(ehp), sqrtf(ebp));
-        }
-        __syncthreads();
+    // ---------------- per-block setup (worker thread 0): window controls and the sub-block table ----------------
+    __device__ void begin_block(int decision) {
         if (tid == 0) {
-            float php = sm.env[0], pbp = sm.env[1];
-            const float a1 = tb.c1PostHp, a2 = tb.c1PostBp;
-#pragma unroll 4
-            for (int n = 0; n < N; n++) {                            // post-masking envelopes (:73-88)
-                float2 e = E[n];
-                float dh = e.x - php, db = e.y - pbp;
-                php += dh * a1; pbp += db * a2;
-                E[n] = make_float2(php, pbp);
-            }
-            sm.env[0] = php; sm.env[1] = pbp;
-            float qhp = php, qbp = pbp;
-            const float b1 = tb.c1PreHp, b2 = tb.c1PreBp;
-#pragma unroll 4
-            for (int n = N - 1; n >= 0; n--) {                       // pre-masking, backwards (:92-104)
-                float2 e = E[n];
-                float dh = e.x - qhp, db = e.y - qbp;
-                qhp += dh * b1; qbp += db * b2;
-                float a = dh * qbp, b = db * qhp;
-                E[n].x = a * a + b * b;
-            }
-            const int bin = N >> 3;
-            const float cb = tb.c1Blk;
-            float m = sm.env[2];
-            for (int s = 0; s < 8; s++) {                            // block-mask envelope into 8 segment sums (:107-134)
-                sm.seg[2 * s] = sm.seg[16 + 2 * s]; sm.seg[2 * s + 1] = sm.seg[16 + 2 * s + 1];
-                float acc = 0.0f, cnt = 0.0f;
-#pragma unroll 4
-                for (int n = 0; n < bin; n++) {
-                    float d = E[s * bin + n].x - m;
-                    m += d * cb;
-                    acc += m; cnt += 1.0f;
-                }
-                sm.seg[16 + 2 * s] = acc; sm.seg[16 + 2 * s + 1] = cnt;
-            }
-            sm.env[2] = m;
             sm.wcPrev = sm.wcCur;
             sm.wcCur  = sm.wcNext;
-            sm.wcNext = window_decide(sm.seg, tb.log2N);
+            sm.wcNext = decision;
             // sub-block table of the block being coded now (ulcEncoder_BlockTransform.c:156-172)
             const int wc = sm.wcCur;
             unsigned pat = kLayoutE[(wc >> 4) & 15];
@@ -470,7 +427,7 @@ struct Encoder {
             }
             sm.nNz = 0;
         }
-        __syncthreads();
+        wsync<NTHR>();
     }
 
     // ---------------- fold + window (closed form of the lapping FIFO and Fourier_MDCT_Template.h:45-187) ----------------
@@ -583,10 +540,10 @@ struct Encoder {
     }
     __device__ void transform() {
         const int lgN = tb.log2N;
-        for (int lgm = lgN; lgm >= 4; lgm--) { dct_down(1 << lgm, lgm); __syncthreads(); }
+        for (int lgm = lgN; lgm >= 4; lgm--) { dct_down(1 << lgm, lgm); wsync<NTHR>(); }
         dct_leaves();
-        __syncthreads();
-        for (int lgm = 4; lgm <= lgN; lgm++) { dct_up(1 << lgm, lgm); __syncthreads(); }
+        wsync<NTHR>();
+        for (int lgm = 4; lgm <= lgN; lgm++) { dct_up(1 << lgm, lgm); wsync<NTHR>(); }
     }
 
     // ---------------- normalise, keys, line sums (ulcEncoder_BlockTransform.c:243-281) ----------------
@@ -760,31 +717,31 @@ struct Encoder {
                 int dg = (uk[src[tid * E + e]] >> shift) & 15;
                 w.cnt[dg * NTHR + tid]++;
             }
-            __syncthreads();
+            wsync<NTHR>();
             int loc = 0;
 #pragma unroll
             for (int q = 0; q < 16; q++) loc += w.cnt[tid * 16 + q];
             int tot, base = block_excl_sum<NTHR>(loc, sm.scan, tot);
 #pragma unroll
             for (int q = 0; q < 16; q++) { int t = w.cnt[tid * 16 + q]; w.cnt[tid * 16 + q] = (uint16_t)base; base += t; }
-            __syncthreads();
+            wsync<NTHR>();
             for (int e = 0; e < E; e++) {
                 uint16_t ix = src[tid * E + e];
                 int dg = (uk[ix] >> shift) & 15;
                 int pos = w.cnt[dg * NTHR + tid]++;
                 dst[pos] = ix;
             }
-            __syncthreads();
+            wsync<NTHR>();
             uint16_t *t = src; src = dst; dst = t;
         }
         // 8 passes: the sorted order is back in the first array.  Turn order into ranks (uint16 at TA).
-        __syncthreads();
+        wsync<NTHR>();
         uint16_t *rank = reinterpret_cast<uint16_t *>(w.TA);
         // keys are dead now; but rank[] aliases them, so stage through registers
         const uint16_t *ord = reinterpret_cast<const uint16_t *>(w.XB);
-        __syncthreads();
+        wsync<NTHR>();
         for (int r = tid; r < CN; r += NTHR) rank[ord[r]] = (uint16_t)r;
-        __syncthreads();
+        wsync<NTHR>();
     }
 
     // ---------------- one coder pass (ulcEncoder_Encode.c:319-360); returns the size in bits ----------------
@@ -814,7 +771,7 @@ struct Encoder {
             if (tid == 0) sm.unitSel[U] = nSel;
         }
         if (write) for (int i = tid; i < (CN >> 1) + 4; i += NTHR) outW[i] = 0u;
-        __syncthreads();
+        wsync<NTHR>();
 
         // G2: greedy quantiser zones, one thread per (channel, sub-block) (ulcEncoder_Encode.c:200-269)
         if (tid < U) {
@@ -844,7 +801,7 @@ struct Encoder {
             sm.unitZones[tid] = z;
             sm.unitLastQ[tid] = prevQ;
         }
-        __syncthreads();
+        wsync<NTHR>();
 
         // G2b: per selected coefficient, its zone's quantiser and header flags
         for (int m = tid; m < nSel; m += NTHR) {
@@ -861,7 +818,7 @@ struct Encoder {
             }
             info[selList[m]] = (uint8_t)inf;
         }
-        __syncthreads();
+        wsync<NTHR>();
 
         // G3: kept coefficients and the last kept index before each thread's slots
         uint32_t keptMask = 0; int lastKeptP1 = 0;
@@ -914,23 +871,126 @@ struct Encoder {
             walk(ws, false);
             if (tid == 0) { WriteSink h{outW, 0, capNyb}; h.put(sm.wcCur); if (sm.wcCur & 8) h.put(sm.wcCur >> 4); }
         }
-        __syncthreads();
+        wsync<NTHR>();
         return ((hdr + total) * 4 + 7) & ~7;
     }
 };
 
+
+// ---- transient detector warp (ulcEncoder_WindowControl.c:31-239) -----------------------------------------
+// Runs on its own warp, one block ahead of the workers.  It reads its analysis window (second half of block
+// b-1, first half of block b, one sample either side) straight from the PCM input, so it shares nothing with
+// the workers but the published decision.  The tap energies are computed by the 32 lanes; the three one-pole
+// envelope recurrences are serial by definition and run on lane 0 in the reference's operation order.
+template <int NCH>
+struct Detector {
+    const UlcbEncodeArgs &args;
+    float2 *E;                    // [N] private scratch
+    float *seg;                   // [32] {sum,cnt} x 16 (shared memory)
+    float env[3];
+    const unsigned char *pcm; long long nSamples; const float *prevBlk;   // prevBlk: block before this call (M/S planar) or nullptr
+
+    __device__ __forceinline__ float sample(int c, long long s) const {   // M/S sample c at call-relative index s
+        const int N = args.tb.N;
+        if (s < 0) return prevBlk ? prevBlk[c * N + (int)(s + N)] : 0.0f;
+        if (s >= nSamples) return 0.0f;
+        float v[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; q++)
+            v[q] = args.pcmFloat ? reinterpret_cast<const float *>(pcm)[(size_t)s * NCH + q]
+                                 : (float)reinterpret_cast<const int16_t *>(pcm)[(size_t)s * NCH + q] * 0x1.0p-15f;
+        const int p = c | 1;
+        if (p < NCH) { float a = v[p - 1], b = v[p]; return (c & 1) ? (a - b) * 0.5f : (a + b) * 0.5f; }
+        return v[c];
+    }
+    __device__ int decide(int b) {
+        const int N = args.tb.N, H = N >> 1, lane = threadIdx.x & 31;
+        const UlcbEncTables &tb = args.tb;
+        const long long s0 = (long long)(b - 1) * N + H;                  // sample index of z[0]
+        for (int n = lane; n < N; n += 32) {
+            float ehp = 0.0f, ebp = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                float t0 = sample(c, s0 + n - 1), t1 = sample(c, s0 + n), t2 = sample(c, s0 + n + 1);
+                float hp = (-t0 + 2.0f * t1) - t2, bp = -t0 + t2;
+                ehp += hp * hp; ebp += bp * bp;
+            }
+            E[n] = make_float2(sqrtf(ehp), sqrtf(ebp));
+        }
+        __syncwarp();
+        int decision = 0;
+        if (lane == 0) {
+            float4 *E4 = reinterpret_cast<float4 *>(E);
+            float php = env[0], pbp = env[1];
+            const float a1 = tb.c1PostHp, a2 = tb.c1PostBp;
+#pragma unroll 2
+            for (int n = 0; n < (N >> 1); n++) {                     // post-masking envelopes (:73-88), two samples per step
+                float4 e = E4[n];
+                float dh = e.x - php, db = e.y - pbp;
+                php += dh * a1; pbp += db * a2;
+                e.x = php; e.y = pbp;
+                dh = e.z - php; db = e.w - pbp;
+                php += dh * a1; pbp += db * a2;
+                e.z = php; e.w = pbp;
+                E4[n] = e;
+            }
+            env[0] = php; env[1] = pbp;
+            float qhp = php, qbp = pbp;
+            const float b1 = tb.c1PreHp, b2 = tb.c1PreBp;
+#pragma unroll 2
+            for (int n = (N >> 1) - 1; n >= 0; n--) {                // pre-masking, backwards (:92-104)
+                float4 e = E4[n];
+                float dh = e.z - qhp, db = e.w - qbp;
+                qhp += dh * b1; qbp += db * b2;
+                float a = dh * qbp, bb = db * qhp;
+                e.z = a * a + bb * bb;
+                dh = e.x - qhp; db = e.y - qbp;
+                qhp += dh * b1; qbp += db * b2;
+                a = dh * qbp; bb = db * qhp;
+                e.x = a * a + bb * bb;
+                E4[n] = e;
+            }
+            const int bin = N >> 3;
+            const float cb = tb.c1Blk;
+            float m = env[2];
+            for (int s = 0; s < 8; s++) {                            // block-mask envelope into 8 segment sums (:107-134)
+                seg[2 * s] = seg[16 + 2 * s]; seg[2 * s + 1] = seg[16 + 2 * s + 1];
+                float acc = 0.0f, cnt = 0.0f;
+                const float4 *S4 = E4 + ((s * bin) >> 1);
+#pragma unroll 2
+                for (int n = 0; n < (bin >> 1); n++) {
+                    float4 e = S4[n];
+                    float d = e.x - m;
+                    m += d * cb;
+                    acc += m; cnt += 1.0f;
+                    d = e.z - m;
+                    m += d * cb;
+                    acc += m; cnt += 1.0f;
+                }
+                seg[16 + 2 * s] = acc; seg[16 + 2 * s + 1] = cnt;
+            }
+            env[2] = m;
+            decision = window_decide(seg, tb.log2N);
+        }
+        return __shfl_sync(0xffffffffu, decision, 0);
+    }
+};
+
 template <int NCH, int NTHR, bool GWS>
-__global__ void __launch_bounds__(NTHR, 1) ulcb_encode_kernel(UlcbEncodeArgs args) {
+__global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArgs args) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = args.tb.N, CN = NCH * N, H = N >> 1;
     const int tid = threadIdx.x;
+    const bool isDetector = tid >= NTHR;                              // the extra warp
     EncSmall &sm = *reinterpret_cast<EncSmall *>(smraw);
     Work wk;
+    float2 *detE;
     {
         unsigned char *p = smraw + ((sizeof(EncSmall) + 15) & ~(size_t)15);
         wk.cnt = reinterpret_cast<uint16_t *>(p); p += 32 * NTHR;
         wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
         wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H;
+        detE = reinterpret_cast<float2 *>(p); p += sizeof(float2) * N;
         float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
         wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
     }
@@ -942,54 +1002,69 @@ __global__ void __launch_bounds__(NTHR, 1) ulcb_encode_kernel(UlcbEncodeArgs arg
         const size_t elem = args.pcmFloat ? 4 : 2;
         const unsigned char *pcm = reinterpret_cast<const unsigned char *>(args.pcm) + (size_t)stream * args.inStride * elem;
         UlcbEncStreamState *st = args.state ? args.state + stream : nullptr;
+        const bool resume = st && st->valid;
+        fsync<NTHR>();                                                // the previous stream is finished everywhere
+
+        if (isDetector) {
+            // ================= transient detector warp: decisions for blocks 0..nBlocks-1, one block ahead =================
+            const int lane = tid & 31;
+            Detector<NCH> det{args, detE, sm.seg, {0.0f, 0.0f, 0.0f}, pcm, nSamples,
+                              resume ? args.stateSamples + (size_t)stream * 2 * CN + CN : nullptr};
+            if (lane == 0) {
+                for (int i = 0; i < 16; i++) { sm.seg[i] = 0.0f; sm.seg[16 + i] = resume ? st->seg[i] : 0.0f; }
+                if (resume) for (int i = 0; i < 3; i++) det.env[i] = st->env[i];
+            }
+            __syncwarp();
+            for (int b = 0; b < nBlocks; b++) {
+                const int d = det.decide(b);
+                if (lane == 0) sm.wcRing[b & 1] = d;
+                fsync<NTHR>();                                        // publish decision b; workers start block b
+            }
+            if (st && lane == 0) {
+                for (int i = 0; i < 3; i++) st->env[i] = det.env[i];
+                for (int i = 0; i < 16; i++) st->seg[i] = sm.seg[16 + i];
+            }
+            continue;
+        }
+
+        // ================= workers =================
         uint8_t *out = args.out + (size_t)stream * args.outStride;
         uint64_t outPos = 0;
         int overflow = 0;
         uint32_t k0 = 0;
-
-        // ---- stream state ----
-        __syncthreads();
-        if (st && st->valid) {
+        if (resume) {
             k0 = st->calls;
             const float *ss = args.stateSamples + (size_t)stream * 2 * CN;
             for (int i = tid; i < CN; i += NTHR) { enc.blk((int)(k0 % 3) - 2)[i] = ss[i]; enc.blk((int)(k0 % 3) - 1)[i] = ss[CN + i]; }
-            if (tid == 0) {
-                for (int i = 0; i < 3; i++) sm.env[i] = st->env[i];
-                for (int i = 0; i < 16; i++) { sm.seg[i] = 0.0f; sm.seg[16 + i] = st->seg[i]; }
-                sm.wcNext = st->nextWindowCtrl; sm.wcCur = st->windowCtrl; sm.wcPrev = st->prevWindowCtrl;
-            }
+            if (tid == 0) { sm.wcNext = st->nextWindowCtrl; sm.wcCur = st->windowCtrl; sm.wcPrev = st->prevWindowCtrl; }
         } else {
             for (int i = tid; i < 3 * CN; i += NTHR) wk.R[i] = 0.0f;
-            if (tid == 0) {
-                for (int i = 0; i < 3; i++) sm.env[i] = 0.0f;
-                for (int i = 0; i < 32; i++) sm.seg[i] = 0.0f;
-                sm.wcNext = 0x10; sm.wcCur = 0x10; sm.wcPrev = 0x10;          // libulc/ulcEncoder.c:70
-            }
+            if (tid == 0) { sm.wcNext = 0x10; sm.wcCur = 0x10; sm.wcPrev = 0x10; }    // libulc/ulcEncoder.c:70
         }
         const int kb = (int)(k0 % 3);                                         // only k mod 3 matters for the rotating buffers
-        __syncthreads();
+        wsync<NTHR>();
 
         for (int b = 0; b < nBlocks; b++) {
             const int k = kb + b;
             long long valid = nSamples - (long long)b * N;
             enc.ingest(k, pcm + (size_t)b * N * NCH * elem, valid < 0 ? 0 : valid);
-            __syncthreads();
-            enc.window_control(k);
+            fsync<NTHR>();                                            // decision b is published (and the ingest is visible)
+            enc.begin_block(sm.wcRing[b & 1]);
             enc.fold(k);
-            __syncthreads();
+            wsync<NTHR>();
             enc.transform();
             enc.analyse(k);
-            __syncthreads();
+            wsync<NTHR>();
             const size_t dbgBlk = ((size_t)stream * args.nBlocksAll + b);
             if (args.dbgCoefs) for (int i = tid; i < CN; i += NTHR) args.dbgCoefs[dbgBlk * CN + i] = wk.XA[i];
             enc.serial_sums(k);
-            __syncthreads();
+            wsync<NTHR>();
             enc.spread();
-            __syncthreads();
+            wsync<NTHR>();
             if (args.dbgNoise) for (int i = tid; i < CN; i += NTHR) args.dbgNoise[dbgBlk * CN + i] = wk.TB[i];
             if (args.dbgMask) for (int i = tid; i < H; i += NTHR) args.dbgMask[dbgBlk * H + i] = wk.mask[i];
             enc.make_keys(args.dbgKeys ? args.dbgKeys + dbgBlk * CN : nullptr);
-            __syncthreads();
+            wsync<NTHR>();
             enc.rank_sort();
             if (args.dbgRanks) for (int i = tid; i < CN; i += NTHR) args.dbgRanks[dbgBlk * CN + i] = reinterpret_cast<const uint16_t *>(wk.TA)[i];
 
@@ -1036,7 +1111,7 @@ __global__ void __launch_bounds__(NTHR, 1) ulcb_encode_kernel(UlcbEncodeArgs arg
                 if (args.windowCtrl) args.windowCtrl[mi] = sm.wcCur;
             }
             if (!overflow) outPos += (uint64_t)nBytes;
-            __syncthreads();
+            wsync<NTHR>();
         }
 
         // ---- save state ----
@@ -1046,8 +1121,6 @@ __global__ void __launch_bounds__(NTHR, 1) ulcb_encode_kernel(UlcbEncodeArgs arg
             for (int i = tid; i < CN; i += NTHR) { ss[i] = enc.blk(k - 2)[i]; ss[CN + i] = enc.blk(k - 1)[i]; }
             if (tid == 0) {
                 st->valid = 1; st->calls = k0 + (uint32_t)nBlocks;
-                for (int i = 0; i < 3; i++) st->env[i] = sm.env[i];
-                for (int i = 0; i < 16; i++) st->seg[i] = sm.seg[16 + i];
                 st->nextWindowCtrl = sm.wcNext; st->windowCtrl = sm.wcCur; st->prevWindowCtrl = sm.wcPrev;
                 st->complexity = sm.cx;
             }
@@ -1056,7 +1129,6 @@ __global__ void __launch_bounds__(NTHR, 1) ulcb_encode_kernel(UlcbEncodeArgs arg
             if (args.totalBytes) args.totalBytes[stream] = outPos;
             if (args.status) args.status[stream] = overflow;
         }
-        __syncthreads();
     }
 }
 
@@ -1066,7 +1138,7 @@ bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4
 int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }
 size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)7 * nChan * N + 64; }
 size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs) {
-    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N;
+    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + sizeof(float2) * N;
     if (!globalWs) s += sizeof(float) * ulcb_encode_ws_floats(N, nChan);
     return s + 16;
 }
@@ -1078,7 +1150,7 @@ static cudaError_t launch_e(const UlcbEncodeArgs &args, int gridBlocks, cudaStre
     size_t smem = ulcb_encode_smem_bytes(args.tb.N, NCH, NTHR, gws);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<gridBlocks, NTHR, smem, stream>>>(args);
+    k<<<gridBlocks, NTHR + 32, smem, stream>>>(args);
     return cudaGetLastError();
 }
 
