@@ -45,3 +45,12 @@ with capi.Context(44100, C, N) as ctx:
     byts = int(bb.sum().item())
     print(f"encode {a.mode} {a.rate} N={N} streams={a.streams} blocks/stream={nb}: {ms:.1f} ms/launch, {audio / (ms / 1e3):.0f} x realtime, "
           f"{ms * 1e3 / (nb * a.streams) * min(a.streams, 148):.1f} us per block per SM-slot, avg {byts / (a.streams * nb):.1f} B/block, status bad {int((st != 0).sum())}")
+
+    import ctypes as C
+    if hasattr(ctx.L, "ULCB_DebugPhaseTimes"):
+        buf = (C.c_ulonglong * 24)()
+        ctx.L.ULCB_DebugPhaseTimes(buf)
+        nblk = max(1, buf[12])
+        names = ["ingest", "wait-detector", "begin+fold", "dct", "analyse", "serial-sums", "spread", "keys+sort", "rate+encode", "emit"]
+        tot = sum(buf[i] for i in range(10))
+        print("phase cycles per block (thread 0): " + ", ".join(f"{n} {buf[i] / nblk:.0f}" for i, n in enumerate(names)) + f" | total {tot / nblk:.0f} | begin_block {buf[10] / nblk:.0f} detector busy {buf[13] / nblk:.0f} wait {buf[14] / nblk:.0f} [stage {buf[16] / nblk:.0f} energy {buf[17] / nblk:.0f} post {buf[18] / nblk:.0f} pre {buf[19] / nblk:.0f} blk {buf[20] / nblk:.0f} decide {buf[21] / nblk:.0f}]")

@@ -513,6 +513,9 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
     a.metaStride = metaStride; a.totalBytes = dTotalBytes; a.status = dStatus;
     a.state = state; a.stateSamples = stateSamples;
     if (taps) { a.dbgCoefs = taps->coefs; a.dbgKeys = taps->keys; a.dbgNoise = taps->noise; a.dbgMask = taps->mask; a.dbgRanks = taps->ranks; a.dbgCounts = taps->counts; }
+#ifdef ULCB_PHASE_TIMING
+    if (getenv("ULCB_DBG_FLAGS")) a.dbgFlags = atoi(getenv("ULCB_DBG_FLAGS"));
+#endif
     int grid = nStreams;
     if (ulcb_encode_uses_global_ws(ctx->N, ctx->nChan)) {
         const int cap = ctx->smCount * 2;

@@ -32,6 +32,13 @@
 #include <stdint.h>
 #include "ulcb_encode.h"
 
+#ifdef ULCB_PHASE_TIMING
+__device__ unsigned long long g_ulcbPhase[32];
+#define TICK(i) do { if (tid == 0) { long long t_ = clock64(); phaseAcc[i] += t_ - tPrev; tPrev = t_; } } while (0)
+#else
+#define TICK(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr float kLn2f = 0x1.62E430p-1f;
@@ -65,6 +72,7 @@ struct EncSmall {
     int     scan[40];
     float   band[MAXBU][ULCB_NBARK];
     double  lo[MAXBU][ULCB_NBARK][3];
+    double  stage[MAXBU][3][32];
 };
 
 // ---- small exact helpers -------------------------------------------------------------------------
@@ -137,8 +145,10 @@ __device__ __forceinline__ bool node_is_dct4(int d, int node) {   // root = DCT-
 
 // The CTA is NTHR worker threads + one extra warp that runs the transient detector one block ahead.
 // Workers synchronise among themselves on named barrier 1; barrier 0 joins everybody once per block.
-template <int NTHR> __device__ __forceinline__ void wsync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory"); }
-template <int NTHR> __device__ __forceinline__ void fsync() { asm volatile("bar.sync 0, %0;" ::"n"(NTHR + 32) : "memory"); }
+// (bar.sync is warp-aligned: a warp counts as arrived as soon as any of its lanes executes it, so each warp is
+// reconverged explicitly first - single-lane serial sections precede several of these barriers.)
+template <int NTHR> __device__ __forceinline__ void wsync() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory"); }
+template <int NTHR> __device__ __forceinline__ void fsync() { __syncwarp(); asm volatile("bar.sync 0, %0;" ::"n"(NTHR + 32) : "memory"); }
 
 // Worker-wide exclusive scans of one int per thread.  `scr` = smem int[NTHR/32 + 2].
 template <int NTHR>
@@ -193,6 +203,7 @@ struct Work {
     float *TA, *TB;      // DCT "T" buffers; afterwards TA = keys -> ranks/selection list, TB = noise pairs
     float *amp2, *mask;  // [N/2]
     uint16_t *cnt;       // radix counters [16][NTHR]
+    uint8_t *encScratch; // 3*CN bytes for the coder (aliases cnt, which is dead after the sort; global for large blocks)
 };
 
 // ---- transient detector (ulcEncoder_WindowControl.c:140-239) decision on the 16 segment sums ----------
@@ -482,6 +493,7 @@ struct Encoder {
     }
     __device__ void dct_down(int m, int lgm) {
         const int hm = m >> 1;
+#pragma unroll 4
         for (int P = tid; P < CN; P += NTHR) {
             int hb, cbase, j, lp; locate(P, hb, cbase, j, lp);
             const int lgS = sm.sub[j].lgS;
@@ -517,6 +529,7 @@ struct Encoder {
     }
     __device__ void dct_up(int m, int lgm) {
         const int hm = m >> 1;
+#pragma unroll 4
         for (int P = tid; P < CN; P += NTHR) {
             int hb, cbase, j, lp; locate(P, hb, cbase, j, lp);
             const int lgS = sm.sub[j].lgS;
@@ -581,86 +594,103 @@ struct Encoder {
     }
 
     // ---------------- serial sums: complexity + Bark band analysis ----------------
+    // Bark analysis of one unit by one warp.  The three running f64 sums (struct LineSum_t, ulcEncoder_Psyopt.c:16-51)
+    // must be accumulated in index order; lanes 0,1,2 each own one sum, so one DADD per line serves all three, and the
+    // per-line conversions / products are done 32 lines at a time by the whole warp.  The 50 band edges are walked
+    // from a host-sorted list; the 25 band levels are evaluated in parallel afterwards (one lane per band).
     __device__ void band_unit(int unit, const float *v, const float *lg, int n, int sh, int kind) {
-        // running f64 sums in index order (struct LineSum_t, ulcEncoder_Psyopt.c:16-51), sampled at the band edges.
-        // The 50 edges are walked in position order from a host-sorted list, so the inner loop is a bare accumulation.
+        const int lane = tid & 31;
         const int16_t *ev = tb.events + ((sh * 2 + kind) * 2 * ULCB_NBARK) * 2;
         const int16_t *ed = tb.edges + ((sh * 2 + kind) * ULCB_NBARK) * 2;
-        double sLg = 0.0, sWlg = 0.0, sW = 0.0;
-        float level = kind ? 0.0f : -100.0f;
-        int i = 0;
-        for (int e = 0; e < 2 * ULCB_NBARK; e++) {
-            const int pos = __ldg(&ev[2 * e]), code = __ldg(&ev[2 * e + 1]);
-            for (; i + 4 <= pos; i += 4) {
-                float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
-                float l0 = lg[i], l1 = lg[i + 1], l2 = lg[i + 2], l3 = lg[i + 3];
-                double X0 = (double)x0, X1 = (double)x1, X2 = (double)x2, X3 = (double)x3;
-                double L0 = (double)l0, L1 = (double)l1, L2 = (double)l2, L3 = (double)l3;
-                double p0 = L0 * X0, p1 = L1 * X1, p2 = L2 * X2, p3 = L3 * X3;
-                sLg += L0; sLg += L1; sLg += L2; sLg += L3;
-                sWlg += p0; sWlg += p1; sWlg += p2; sWlg += p3;
-                sW += X0; sW += X1; sW += X2; sW += X3;
+        double (*stage)[32] = sm.stage[unit];
+        double (*lo)[3] = sm.lo[unit];
+        const int src = lane < 3 ? lane : 0;
+        double acc = 0.0;
+        int e = 0, nextPos = __ldg(&ev[0]);
+        auto events_at = [&](int pos) {
+            while (nextPos == pos) {
+                const int code = __ldg(&ev[2 * e + 1]), b = code & 0x7F;
+                if (lane < 3) { if (code & 0x80) lo[b][lane] = acc - lo[b][lane]; else lo[b][lane] = acc; }
+                e++;
+                nextPos = (e < 2 * ULCB_NBARK) ? (int)__ldg(&ev[2 * e]) : 0x7fffffff;
             }
-            for (; i < pos; i++) {
-                double x = (double)v[i], l = (double)lg[i];
-                sLg += l; sWlg += l * x; sW += x;
-            }
-            const int b = code & 0x7F;
-            if (!(code & 0x80)) { sm.lo[unit][b][0] = sLg; sm.lo[unit][b][1] = sWlg; sm.lo[unit][b][2] = sW; }
-            else {
-                double dLg = sLg - sm.lo[unit][b][0], dWlg = sWlg - sm.lo[unit][b][1], dW = sW - sm.lo[unit][b][2];
-                if (dW > 0.0) {
-                    const int beg = __ldg(&ed[2 * b]), end = __ldg(&ed[2 * b + 1]);
-                    if (kind == 0) {                                  // noise level (ulcEncoder_Psyopt.c:206-222)
-                        double inv = 1.0 / (double)(end - beg);
-                        dWlg = dWlg / dW;
-                        dLg = dLg * inv;
-                        level = 0.5f * (float)(log(dW * inv) + dLg - dWlg);
-                    } else {                                          // masking (ulcEncoder_Psyopt.c:117-131)
-                        dWlg = dWlg / dW;
-                        dLg = dLg / (double)(end - beg);
-                        level = (float)(dWlg - dLg - log(dW));
-                    }
-                }
-                sm.band[unit][b] = level;
+        };
+        float xN = v[lane], lN = lg[lane];
+        for (int base = 0; base < n; base += 32) {
+            const double X = (double)xN, L = (double)lN;
+            if (base + 32 < n) { xN = v[base + 32 + lane]; lN = lg[base + 32 + lane]; }
+            __syncwarp();
+            stage[0][lane] = L; stage[1][lane] = L * X; stage[2][lane] = X;
+            __syncwarp();
+            if (nextPos >= base + 32) {
+#pragma unroll 8
+                for (int t = 0; t < 32; t++) acc += stage[src][t];
+            } else {
+                for (int t = 0; t < 32; t++) { events_at(base + t); acc += stage[src][t]; }
             }
         }
+        events_at(n);
+        __syncwarp();
+        // band levels: lanes 0..24; a band without energy inherits the previous band's level
+        float level = 0.0f; bool ok = false;
+        if (lane < ULCB_NBARK) {
+            const double dLg0 = lo[lane][0], dWlg0 = lo[lane][1], dW = lo[lane][2];
+            if (dW > 0.0) {
+                ok = true;
+                const int beg = __ldg(&ed[2 * lane]), end = __ldg(&ed[2 * lane + 1]);
+                if (kind == 0) {                                      // noise level (ulcEncoder_Psyopt.c:206-222)
+                    double inv = 1.0 / (double)(end - beg);
+                    double dWlg = dWlg0 / dW;
+                    double dLg = dLg0 * inv;
+                    level = 0.5f * (float)(log(dW * inv) + dLg - dWlg);
+                } else {                                              // masking (ulcEncoder_Psyopt.c:117-131)
+                    double dWlg = dWlg0 / dW;
+                    double dLg = dLg0 / (double)(end - beg);
+                    level = (float)(dWlg - dLg - log(dW));
+                }
+            }
+        }
+        const unsigned okMask = __ballot_sync(0xffffffffu, ok);
+        const unsigned below = okMask & ((2u << lane) - 1u);          // valid bands at or below this one
+        const int from = below ? 31 - __clz(below) : 0;
+        const float got = __shfl_sync(0xffffffffu, level, from);
+        if (lane < ULCB_NBARK) sm.band[unit][lane] = below ? got : (kind ? 0.0f : -100.0f);
     }
     __device__ void serial_sums(int k) {
         const float *lgN = blk(k - 2);
-        const int U = NCH * sm.nsub;
+        const int U = NCH * sm.nsub, nTasks = U + sm.nsub + 1;
         constexpr int NW = NTHR / 32;
         const int warp = tid >> 5, lane = tid & 31;
-        if (tid == NTHR - 1) {                                        // block complexity (ulcEncoder_BlockTransform.c:310-325)
-            float sq = 0.0f, ab = 0.0f;
-            const float4 *x4 = reinterpret_cast<const float4 *>(w.XA);
+        for (int task = warp; task < nTasks; task += NW) {
+            if (task == nTasks - 1) {                                 // block complexity (ulcEncoder_BlockTransform.c:310-325)
+                if (lane == 0 && !(args.dbgFlags & 1)) {
+                    float sq = 0.0f, ab = 0.0f;
+                    const float4 *x4 = reinterpret_cast<const float4 *>(w.XA);
 #pragma unroll 2
-            for (int i = 0; i < (CN >> 2); i++) {
-                float4 r = x4[i];
-                float a0 = r.x * r.x, a1 = r.y * r.y, a2 = r.z * r.z, a3 = r.w * r.w;
-                sq += a0; sq += a1; sq += a2; sq += a3;
-                ab += fabsf(r.x); ab += fabsf(r.y); ab += fabsf(r.z); ab += fabsf(r.w);
-            }
-            float cx = sq;
-            if (cx != 0.0f) {
-                float scale = kLn2f * (float)tb.log2N;
-                cx = logf_ref(ab * ab / sq) / scale;
-                if (cx < 0.0f) cx = 0.0f;
-                if (cx > 1.0f) cx = 1.0f;
-            }
-            sm.cx = cx;
-        }
-        // one Bark analysis unit per (warp, lane) slot, spread over the warps so that units run concurrently
-        const int u = lane * NW + warp;
-        if (lane < 2 && u < U + sm.nsub) {
-            if (u < U) {
-                int c = u / sm.nsub, j = u - c * sm.nsub;
+                    for (int i = 0; i < (CN >> 2); i++) {
+                        float4 r = x4[i];
+                        float a0 = r.x * r.x, a1 = r.y * r.y, a2 = r.z * r.z, a3 = r.w * r.w;
+                        sq += a0; sq += a1; sq += a2; sq += a3;
+                        ab += fabsf(r.x); ab += fabsf(r.y); ab += fabsf(r.z); ab += fabsf(r.w);
+                    }
+                    float cx = sq;
+                    if (cx != 0.0f) {
+                        float scale = kLn2f * (float)tb.log2N;
+                        cx = logf_ref(ab * ab / sq) / scale;
+                        if (cx < 0.0f) cx = 0.0f;
+                        if (cx > 1.0f) cx = 1.0f;
+                    }
+                    sm.cx = cx;
+                }
+            } else if ((args.dbgFlags & 2) || ((args.dbgFlags & 4) && task != U)) {
+            } else if (task < U) {
+                int c = task / sm.nsub, j = task - c * sm.nsub;
                 const SubInfo &s = sm.sub[j];
-                band_unit(u, w.TB + c * N + s.off, lgN + c * H + (s.off >> 1), s.S >> 1, s.sh, 0);
+                band_unit(task, w.TB + c * N + s.off, lgN + c * H + (s.off >> 1), s.S >> 1, s.sh, 0);
             } else {
-                int j = u - U;
+                int j = task - U;
                 const SubInfo &s = sm.sub[j];
-                band_unit(u, w.amp2 + (s.off >> 1), w.mask + (s.off >> 1), s.S >> 1, s.sh, 1);
+                band_unit(task, w.amp2 + (s.off >> 1), w.mask + (s.off >> 1), s.S >> 1, s.sh, 1);
             }
         }
     }
@@ -752,6 +782,8 @@ struct Encoder {
         uint16_t *zoneStart = reinterpret_cast<uint16_t *>(info + CN);           // [CN]
         uint8_t  *zoneQi = info + 3 * CN;                                         // [CN]
         uint32_t *outW = reinterpret_cast<uint32_t *>(blk(k - 2));               // packed nybbles
+        uint16_t *jump = reinterpret_cast<uint16_t *>(w.encScratch);             // [CN] next zone start if a zone starts here
+        uint8_t  *qcand = w.encScratch + 2 * CN;                                  // [CN] quantiser of that zone
         const float *coef = w.XA, *pairs = w.TB;
         const int E = CN / NTHR, U = NCH * sm.nsub, i0 = tid * E;
         const int capNyb = 8 * ((CN >> 1) + 4);                                   // 2*CN + 16 bytes
@@ -773,30 +805,37 @@ struct Encoder {
         if (write) for (int i = tid; i < (CN >> 1) + 4; i += NTHR) outW[i] = 0u;
         wsync<NTHR>();
 
-        // G2: greedy quantiser zones, one thread per (channel, sub-block) (ulcEncoder_Encode.c:200-269)
+        // G2: greedy quantiser zones (ulcEncoder_Encode.c:200-269).  A zone that starts at selected coefficient m runs
+        // until the first later one that would push max/min of the levels above 4; that end only depends on m, so
+        // every selected coefficient computes "the zone that would start here" in parallel (jump pointer + quantiser),
+        // and one thread per (channel, sub-block) then just follows the pointers from the first selected coefficient.
+        for (int m = tid; m < nSel; m += NTHR) {
+            int u = 0;
+            while (m >= sm.unitSel[u + 1]) u++;
+            const int m1 = sm.unitSel[u + 1];
+            float lo = fabsf(coef[selList[m]]), hi = lo;
+            int mm = m + 1;
+            for (; mm < m1; mm++) {
+                const float level = fabsf(coef[selList[mm]]);
+                const float newLo = level < lo ? level : lo, newHi = level > hi ? level : hi;
+                if (newHi > newLo * 4.0f) break;
+                lo = newLo; hi = newHi;
+            }
+            int q = (int)(0x1.657006p2f + -0x1.715476p0f * logf_ref(hi));     // :83-88
+            if (q < 5) q = 5;
+            if (q > 31) q = 31;
+            jump[m] = (uint16_t)mm;
+            qcand[m] = (uint8_t)q;
+        }
+        wsync<NTHR>();
         if (tid < U) {
             const int m0 = sm.unitSel[tid], m1 = sm.unitSel[tid + 1];
-            float lo = 1000.0f, hi = -1000.0f;
-            int z = 0, zs = -1, prevQ = -1;
-            for (int m = m0; m <= m1; m++) {
-                float newLo = 0.0f, newHi = hi, level = 0.0f;
-                if (m < m1) {
-                    level = fabsf(coef[selList[m]]);
-                    newLo = level < lo ? level : lo;
-                    newHi = level > hi ? level : hi;
-                    if (zs == -1) zs = m;
-                }
-                if (newHi > newLo * 4.0f) {
-                    int q = (int)(0x1.657006p2f + -0x1.715476p0f * logf_ref(hi));     // :83-88
-                    if (q < 5) q = 5;
-                    if (q > 31) q = 31;
-                    zoneStart[m0 + z] = (uint16_t)zs;
-                    zoneQi[m0 + z] = (uint8_t)q;
-                    z++;
-                    prevQ = q;
-                    zs = m;
-                    lo = hi = level;
-                } else { lo = newLo; hi = newHi; }
+            int z = 0, prevQ = -1;
+            for (int m = m0; m < m1; m = jump[m]) {
+                prevQ = qcand[m];
+                zoneStart[m0 + z] = (uint16_t)m;
+                zoneQi[m0 + z] = (uint8_t)prevQ;
+                z++;
             }
             sm.unitZones[tid] = z;
             sm.unitLastQ[tid] = prevQ;
@@ -886,70 +925,102 @@ template <int NCH>
 struct Detector {
     const UlcbEncodeArgs &args;
     float2 *E;                    // [N] private scratch
+    float *stg;                   // [NCH][N+2] analysis window, M/S
     float *seg;                   // [32] {sum,cnt} x 16 (shared memory)
     float env[3];
     const unsigned char *pcm; long long nSamples; const float *prevBlk;   // prevBlk: block before this call (M/S planar) or nullptr
 
-    __device__ __forceinline__ float sample(int c, long long s) const {   // M/S sample c at call-relative index s
-        const int N = args.tb.N;
-        if (s < 0) return prevBlk ? prevBlk[c * N + (int)(s + N)] : 0.0f;
-        if (s >= nSamples) return 0.0f;
-        float v[NCH];
-#pragma unroll
-        for (int q = 0; q < NCH; q++)
-            v[q] = args.pcmFloat ? reinterpret_cast<const float *>(pcm)[(size_t)s * NCH + q]
-                                 : (float)reinterpret_cast<const int16_t *>(pcm)[(size_t)s * NCH + q] * 0x1.0p-15f;
-        const int p = c | 1;
-        if (p < NCH) { float a = v[p - 1], b = v[p]; return (c & 1) ? (a - b) * 0.5f : (a + b) * 0.5f; }
-        return v[c];
-    }
     __device__ int decide(int b) {
-        const int N = args.tb.N, H = N >> 1, lane = threadIdx.x & 31;
+        const int N = args.tb.N, H = N >> 1, lane = threadIdx.x & 31, W = N + 2;
         const UlcbEncTables &tb = args.tb;
-        const long long s0 = (long long)(b - 1) * N + H;                  // sample index of z[0]
+        // stage the window: samples (b-1)*N + H - 1 .. b*N + H of the call's timeline
+        const long long sBeg = (long long)(b - 1) * N + H - 1;
+#ifdef ULCB_PHASE_TIMING
+        long long dt0 = clock64();
+#define DTICK(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_ulcbPhase[i], (unsigned long long)(t_ - dt0)); dt0 = t_; } } while (0)
+#else
+#define DTICK(i) do { } while (0)
+#endif
+        int i0 = 0;
+        if (sBeg < 0) {                                               // reaches back into the block before this call
+            i0 = (-sBeg < (long long)W) ? (int)(-sBeg) : W;
+            for (int i = lane; i < i0; i += 32)
+#pragma unroll
+                for (int c = 0; c < NCH; c++) stg[c * W + i] = prevBlk ? prevBlk[c * N + (int)(N + sBeg + i)] : 0.0f;
+        }
+        if (nSamples > 0) {
+#pragma unroll 4
+            for (int i = i0 + lane; i < W; i += 32) {
+                const long long sv = sBeg + i;
+                const bool ok = sv < nSamples;
+                const size_t sc = ok ? (size_t)sv : 0;
+                float v[NCH];
+#pragma unroll
+                for (int q = 0; q < NCH; q++)
+                    v[q] = args.pcmFloat ? reinterpret_cast<const float *>(pcm)[sc * NCH + q]
+                                         : (float)reinterpret_cast<const int16_t *>(pcm)[sc * NCH + q] * 0x1.0p-15f;
+#pragma unroll
+                for (int c = 1; c < NCH; c += 2) { float a = v[c - 1], bb = v[c]; v[c - 1] = (a + bb) * 0.5f; v[c] = (a - bb) * 0.5f; }
+#pragma unroll
+                for (int c = 0; c < NCH; c++) stg[c * W + i] = ok ? v[c] : 0.0f;
+            }
+        } else {
+            for (int i = i0 + lane; i < W; i += 32)
+#pragma unroll
+                for (int c = 0; c < NCH; c++) stg[c * W + i] = 0.0f;
+        }
+        __syncwarp();
+        DTICK(16);
+#pragma unroll 2
         for (int n = lane; n < N; n += 32) {
             float ehp = 0.0f, ebp = 0.0f;
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
-                float t0 = sample(c, s0 + n - 1), t1 = sample(c, s0 + n), t2 = sample(c, s0 + n + 1);
+                float t0 = stg[c * W + n], t1 = stg[c * W + n + 1], t2 = stg[c * W + n + 2];
                 float hp = (-t0 + 2.0f * t1) - t2, bp = -t0 + t2;
                 ehp += hp * hp; ebp += bp * bp;
             }
             E[n] = make_float2(sqrtf(ehp), sqrtf(ebp));
         }
         __syncwarp();
+        DTICK(17);
         int decision = 0;
         if (lane == 0) {
             float4 *E4 = reinterpret_cast<float4 *>(E);
+            // The loads of the next 8 samples are issued before the current 8 are processed, so the only latency
+            // left in these loops is the recurrence itself (sub, mul, add per sample).
+            const int nq = N >> 3;                                   // groups of 4 float4 = 8 samples
             float php = env[0], pbp = env[1];
             const float a1 = tb.c1PostHp, a2 = tb.c1PostBp;
-#pragma unroll 2
-            for (int n = 0; n < (N >> 1); n++) {                     // post-masking envelopes (:73-88), two samples per step
-                float4 e = E4[n];
-                float dh = e.x - php, db = e.y - pbp;
-                php += dh * a1; pbp += db * a2;
-                e.x = php; e.y = pbp;
-                dh = e.z - php; db = e.w - pbp;
-                php += dh * a1; pbp += db * a2;
-                e.z = php; e.w = pbp;
-                E4[n] = e;
+            {
+                float4 nx0 = E4[0], nx1 = E4[1], nx2 = E4[2], nx3 = E4[3];
+                for (int g = 0; g < nq; g++) {                        // post-masking envelopes (:73-88)
+                    float4 c0 = nx0, c1 = nx1, c2 = nx2, c3 = nx3;
+                    if (g + 1 < nq) { nx0 = E4[4 * g + 4]; nx1 = E4[4 * g + 5]; nx2 = E4[4 * g + 6]; nx3 = E4[4 * g + 7]; }
+#define POST2(e) { float dh = e.x - php, db = e.y - pbp; php += dh * a1; pbp += db * a2; e.x = php; e.y = pbp; \
+                   dh = e.z - php; db = e.w - pbp; php += dh * a1; pbp += db * a2; e.z = php; e.w = pbp; }
+                    POST2(c0) POST2(c1) POST2(c2) POST2(c3)
+#undef POST2
+                    E4[4 * g] = c0; E4[4 * g + 1] = c1; E4[4 * g + 2] = c2; E4[4 * g + 3] = c3;
+                }
             }
             env[0] = php; env[1] = pbp;
+            DTICK(18);
             float qhp = php, qbp = pbp;
             const float b1 = tb.c1PreHp, b2 = tb.c1PreBp;
-#pragma unroll 2
-            for (int n = (N >> 1) - 1; n >= 0; n--) {                // pre-masking, backwards (:92-104)
-                float4 e = E4[n];
-                float dh = e.z - qhp, db = e.w - qbp;
-                qhp += dh * b1; qbp += db * b2;
-                float a = dh * qbp, bb = db * qhp;
-                e.z = a * a + bb * bb;
-                dh = e.x - qhp; db = e.y - qbp;
-                qhp += dh * b1; qbp += db * b2;
-                a = dh * qbp; bb = db * qhp;
-                e.x = a * a + bb * bb;
-                E4[n] = e;
+            {
+                float4 nx0 = E4[4 * nq - 4], nx1 = E4[4 * nq - 3], nx2 = E4[4 * nq - 2], nx3 = E4[4 * nq - 1];
+                for (int g = nq - 1; g >= 0; g--) {                   // pre-masking, backwards (:92-104)
+                    float4 c0 = nx0, c1 = nx1, c2 = nx2, c3 = nx3;
+                    if (g > 0) { nx0 = E4[4 * g - 4]; nx1 = E4[4 * g - 3]; nx2 = E4[4 * g - 2]; nx3 = E4[4 * g - 1]; }
+#define PRE2(e) { float dh = e.z - qhp, db = e.w - qbp; qhp += dh * b1; qbp += db * b2; float a = dh * qbp, bb = db * qhp; e.z = a * a + bb * bb; \
+                  dh = e.x - qhp; db = e.y - qbp; qhp += dh * b1; qbp += db * b2; a = dh * qbp; bb = db * qhp; e.x = a * a + bb * bb; }
+                    PRE2(c3) PRE2(c2) PRE2(c1) PRE2(c0)
+#undef PRE2
+                    E4[4 * g] = c0; E4[4 * g + 1] = c1; E4[4 * g + 2] = c2; E4[4 * g + 3] = c3;
+                }
             }
+            DTICK(19);
             const int bin = N >> 3;
             const float cb = tb.c1Blk;
             float m = env[2];
@@ -957,20 +1028,21 @@ struct Detector {
                 seg[2 * s] = seg[16 + 2 * s]; seg[2 * s + 1] = seg[16 + 2 * s + 1];
                 float acc = 0.0f, cnt = 0.0f;
                 const float4 *S4 = E4 + ((s * bin) >> 1);
-#pragma unroll 2
-                for (int n = 0; n < (bin >> 1); n++) {
-                    float4 e = S4[n];
-                    float d = e.x - m;
-                    m += d * cb;
-                    acc += m; cnt += 1.0f;
-                    d = e.z - m;
-                    m += d * cb;
-                    acc += m; cnt += 1.0f;
+                const int ng = bin >> 3;                              // bin >= 32
+                float4 nx0 = S4[0], nx1 = S4[1], nx2 = S4[2], nx3 = S4[3];
+                for (int g = 0; g < ng; g++) {
+                    float4 c0 = nx0, c1 = nx1, c2 = nx2, c3 = nx3;
+                    if (g + 1 < ng) { nx0 = S4[4 * g + 4]; nx1 = S4[4 * g + 5]; nx2 = S4[4 * g + 6]; nx3 = S4[4 * g + 7]; }
+#define BLK2(e) { float d = e.x - m; m += d * cb; acc += m; cnt += 1.0f; d = e.z - m; m += d * cb; acc += m; cnt += 1.0f; }
+                    BLK2(c0) BLK2(c1) BLK2(c2) BLK2(c3)
+#undef BLK2
                 }
                 seg[16 + 2 * s] = acc; seg[16 + 2 * s + 1] = cnt;
             }
             env[2] = m;
+            DTICK(20);
             decision = window_decide(seg, tb.log2N);
+            DTICK(21);
         }
         return __shfl_sync(0xffffffffu, decision, 0);
     }
@@ -984,15 +1056,17 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
     const bool isDetector = tid >= NTHR;                              // the extra warp
     EncSmall &sm = *reinterpret_cast<EncSmall *>(smraw);
     Work wk;
-    float2 *detE;
+    float2 *detE; float *detStage;
     {
         unsigned char *p = smraw + ((sizeof(EncSmall) + 15) & ~(size_t)15);
         wk.cnt = reinterpret_cast<uint16_t *>(p); p += 32 * NTHR;
         wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
         wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H;
         detE = reinterpret_cast<float2 *>(p); p += sizeof(float2) * N;
+        detStage = reinterpret_cast<float *>(p); p += sizeof(float) * NCH * (N + 4);
         float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
         wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
+        wk.encScratch = GWS ? reinterpret_cast<uint8_t *>(big + 7 * CN) : reinterpret_cast<uint8_t *>(wk.cnt);
     }
     Encoder<NCH, NTHR> enc(args, sm, wk);
 
@@ -1008,18 +1082,33 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
         if (isDetector) {
             // ================= transient detector warp: decisions for blocks 0..nBlocks-1, one block ahead =================
             const int lane = tid & 31;
-            Detector<NCH> det{args, detE, sm.seg, {0.0f, 0.0f, 0.0f}, pcm, nSamples,
+            Detector<NCH> det{args, detE, detStage, sm.seg, {0.0f, 0.0f, 0.0f}, pcm, nSamples,
                               resume ? args.stateSamples + (size_t)stream * 2 * CN + CN : nullptr};
             if (lane == 0) {
                 for (int i = 0; i < 16; i++) { sm.seg[i] = 0.0f; sm.seg[16 + i] = resume ? st->seg[i] : 0.0f; }
                 if (resume) for (int i = 0; i < 3; i++) det.env[i] = st->env[i];
             }
             __syncwarp();
+#ifdef ULCB_PHASE_TIMING
+            long long detAcc = 0, detWait = 0;
+#endif
             for (int b = 0; b < nBlocks; b++) {
+#ifdef ULCB_PHASE_TIMING
+                long long t0 = clock64();
+#endif
                 const int d = det.decide(b);
                 if (lane == 0) sm.wcRing[b & 1] = d;
+#ifdef ULCB_PHASE_TIMING
+                long long t1 = clock64(); detAcc += t1 - t0;
+#endif
                 fsync<NTHR>();                                        // publish decision b; workers start block b
+#ifdef ULCB_PHASE_TIMING
+                detWait += clock64() - t1;
+#endif
             }
+#ifdef ULCB_PHASE_TIMING
+            if (lane == 0) { atomicAdd(&g_ulcbPhase[13], (unsigned long long)detAcc); atomicAdd(&g_ulcbPhase[14], (unsigned long long)detWait); }
+#endif
             if (st && lane == 0) {
                 for (int i = 0; i < 3; i++) st->env[i] = det.env[i];
                 for (int i = 0; i < 16; i++) st->seg[i] = sm.seg[16 + i];
@@ -1044,28 +1133,40 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
         const int kb = (int)(k0 % 3);                                         // only k mod 3 matters for the rotating buffers
         wsync<NTHR>();
 
+#ifdef ULCB_PHASE_TIMING
+        long long phaseAcc[12] = {0}; long long tPrev = clock64();
+#endif
         for (int b = 0; b < nBlocks; b++) {
             const int k = kb + b;
             long long valid = nSamples - (long long)b * N;
             enc.ingest(k, pcm + (size_t)b * N * NCH * elem, valid < 0 ? 0 : valid);
+            TICK(0);
             fsync<NTHR>();                                            // decision b is published (and the ingest is visible)
+            TICK(1);
             enc.begin_block(sm.wcRing[b & 1]);
+            TICK(10);
             enc.fold(k);
             wsync<NTHR>();
+            TICK(2);
             enc.transform();
+            TICK(3);
             enc.analyse(k);
             wsync<NTHR>();
+            TICK(4);
             const size_t dbgBlk = ((size_t)stream * args.nBlocksAll + b);
             if (args.dbgCoefs) for (int i = tid; i < CN; i += NTHR) args.dbgCoefs[dbgBlk * CN + i] = wk.XA[i];
             enc.serial_sums(k);
             wsync<NTHR>();
+            TICK(5);
             enc.spread();
             wsync<NTHR>();
+            TICK(6);
             if (args.dbgNoise) for (int i = tid; i < CN; i += NTHR) args.dbgNoise[dbgBlk * CN + i] = wk.TB[i];
             if (args.dbgMask) for (int i = tid; i < H; i += NTHR) args.dbgMask[dbgBlk * H + i] = wk.mask[i];
             enc.make_keys(args.dbgKeys ? args.dbgKeys + dbgBlk * CN : nullptr);
             wsync<NTHR>();
             enc.rank_sort();
+            TICK(7);
             if (args.dbgRanks) for (int i = tid; i < CN; i += NTHR) args.dbgRanks[dbgBlk * CN + i] = reinterpret_cast<const uint16_t *>(wk.TA)[i];
 
             // ---- rate control (libulc/ulcEncoder.c:93-158) ----
@@ -1096,6 +1197,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
                 size = enc.encode_pass(k, lo, true);
             }
             if (args.dbgCounts && tid == 0) { args.dbgCounts[dbgBlk * 2] = maxCoef; args.dbgCounts[dbgBlk * 2 + 1] = nOutUsed; }
+            TICK(8);
 
             // ---- emit ----
             const int nBytes = size >> 3;
@@ -1112,7 +1214,11 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
             }
             if (!overflow) outPos += (uint64_t)nBytes;
             wsync<NTHR>();
+            TICK(9);
         }
+#ifdef ULCB_PHASE_TIMING
+        if (tid == 0) { for (int i = 0; i < 12; i++) atomicAdd(&g_ulcbPhase[i], (unsigned long long)phaseAcc[i]); atomicAdd(&g_ulcbPhase[12], (unsigned long long)nBlocks); }
+#endif
 
         // ---- save state ----
         if (st) {
@@ -1134,12 +1240,22 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
 
 }  // namespace
 
+#ifdef ULCB_PHASE_TIMING
+extern "C" int ULCB_DebugPhaseTimes(unsigned long long *out13) {
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out13, g_ulcbPhase, sizeof(unsigned long long) * 24);
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_ulcbPhase, z, sizeof z);
+    return (int)e;
+}
+#endif
+
 bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4096; }
 int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }
-size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)7 * nChan * N + 64; }
+size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)8 * nChan * N + 64; }
 size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs) {
-    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + sizeof(float2) * N;
-    if (!globalWs) s += sizeof(float) * ulcb_encode_ws_floats(N, nChan);
+    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + sizeof(float2) * N + sizeof(float) * nChan * (N + 4);
+    if (!globalWs) s += sizeof(float) * ((size_t)7 * nChan * N + 64);
     return s + 16;
 }
 

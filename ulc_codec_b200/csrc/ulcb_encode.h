@@ -76,6 +76,7 @@ struct UlcbEncodeArgs {
     float          *dbgMask;
     int32_t        *dbgRanks;
     int32_t        *dbgCounts;         // [stream][nBlocksAll][2] = {nNz, nOut}
+    int             dbgFlags;          // ULCB_PHASE_TIMING builds only: skip phases (timing experiments)
 };
 
 size_t      ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs);
