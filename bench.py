@@ -142,6 +142,95 @@ def cpu_reference_decode(blocks, target_seconds: float = 12.0):
             "sample": f"{nb} blocks of one stream, oracle/ulc_oracle.c via ctypes (float out, no PCM16 conversion)"}
 
 
+def wav_bytes(pcm16: np.ndarray) -> bytes:
+    """Minimal 16-bit PCM RIFF/WAVE file (what tools/WavIO_Reader.c parses)."""
+    data = np.ascontiguousarray(pcm16, np.int16).tobytes()
+    nch = pcm16.shape[1]
+    return (b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, nch, RATE, RATE * nch * 2, nch * 2, 16)
+            + b"data" + struct.pack("<I", len(data)) + data)
+
+
+def cpu_reference_encode(quality: float = 50.0, seconds: float = 30.0):
+    """Times the reference's own VBR encoder (oracle/_ref/ulcencodetool_avx) on all host cores, one process per core,
+    each on its own synthetic stream.  Returns dict(value=xrealtime, cores, kind, sample) or None when the tool is absent."""
+    from ulc_codec_b200 import corpus
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    tool = os.path.join(ROOT, "oracle", "_ref", "ulcencodetool_avx")
+    if not os.access(tool, os.X_OK):
+        return None
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    ns = int(seconds * RATE)
+    with tempfile.TemporaryDirectory(dir=shm) as td:
+        base = [corpus.generate(200000 + i, ns, "music") for i in range(min(cores, 4))]
+        files = []
+        for c in range(cores):
+            path = os.path.join(td, f"s{c}.wav")
+            with open(path, "wb") as f:
+                f.write(wav_bytes(base[c % len(base)]))
+            files.append(path)
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([tool, p, p + ".ulc", f"-{quality:g}", f"-blocksize:{N}"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for p in files]
+        rcs = [p.wait() for p in procs]
+        wall = time.perf_counter() - t0
+    if any(rcs):
+        return None
+    return {"value": cores * seconds / wall, "unit": "xrealtime", "cores": cores, "kind": "reference",
+            "sample": f"{cores} procs x one {seconds:g} s stream, oracle/_ref/ulcencodetool_avx -{quality:g} (unmodified reference, AVX/FMA build), WAV in /dev/shm"}
+
+
+def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, warmup, peaks, with_cpu):
+    """configs[2]: batched VBR Quality 50 encode, 60 s stereo streams, BlockSize 2048, PCM16 in, corpus generated on the device."""
+    ns = STREAM_SECONDS * RATE
+    nb = ctx.blocks_for(ns)
+    stride = ns * NCH
+    pcm = torch.empty(n_streams * stride, dtype=torch.int16, device=dev)
+    ctx.generate_corpus_device("music", rank * n_streams, n_streams, ns, pcm.data_ptr(), stride)
+    ostride = nb * 640                                               # VBR Q50 averages ~460 B/block on this corpus
+    out = torch.empty(n_streams * ostride, dtype=torch.uint8, device=dev)
+    bb = torch.zeros(n_streams * nb, dtype=torch.int32, device=dev)
+    st = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+
+    def step():
+        ctx.encode_streams_device(n_streams, pcm.data_ptr(), "pcm16", stride, nb, "vbr", 50.0, out.data_ptr(), ostride,
+                                  d_block_bytes=bb.data_ptr(), meta_stride=nb, d_status=st.data_ptr())
+    for _ in range(warmup):
+        step()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(steps):
+        step()
+    e1.record(ext)
+    ctx.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert int((st != 0).sum().item()) == 0, "encode arena overflow"
+    out_bytes = int(bb.sum().item())
+    algo = n_streams * nb * N * NCH * 2 + out_bytes                  # PCM16 in + bytes out (SURVEY.md 8d)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = algo / (ms / 1e3) / 1e9
+    r = {"metric": "audio-seconds/sec (xrealtime) encode, batched VBR Quality=50, 60 s stereo 44.1 kHz streams, BlockSize 2048, PCM16 in",
+         "value": world * n_streams * nb * N / RATE / (ms / 1e3), "unit": "xrealtime", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+         "config": {"workload": "configs[2]: batched VBR encode Quality=50, window switching on", "streams_per_gpu": n_streams,
+                    "blocks_per_stream": nb, "input": "integer-only synthetic music corpus generated on the device (csrc/ulcb_corpus.cu), every stream distinct",
+                    "avg_bytes_per_block": out_bytes / (n_streams * nb)},
+         "roofline": {"bound": "hbm", "kernel": "ulcb_encode_kernel<2,512,false>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                      "algorithmic_bytes_per_launch": algo, "launch_ms": ms, "traffic": None},
+         "gpu_launches": steps}
+    if with_cpu:
+        c = cpu_reference_encode()
+        r["cpu_baseline"] = c
+    del pcm, out
+    return r
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -152,6 +241,7 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (default = BASELINE configs[1])")
     ap.add_argument("--e2e-streams", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--enc-streams", type=int, default=2048, help="streams per GPU of the secondary encode measurement (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -295,6 +385,14 @@ def main():
                "d2h_bytes_per_step": int(ne * stride * 2), "streams_per_gpu": ne, "ms_per_step": dt * 1e3,
                "api": "ULCB_DecodeStreams (host pointers, pinned), bounded to e2e_streams streams per GPU"}
 
+    # ---- secondary measurement: batched VBR encode (configs[2]); the headline stays the decode line above ----
+    enc = None
+    if args.enc_streams > 0:
+        del d_bytes, d_out
+        torch.cuda.empty_cache()
+        enc = bench_encode(ctx, capi, torch, dist, dev, rank, world, args.enc_streams, max(1, args.steps // 2), 1, peaks,
+                           with_cpu=(rank == 0 and world == 1 and not args.no_cpu))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,7 +404,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "xrealtime", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "cpu_baseline": cpu, "encode": enc}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -194,6 +194,13 @@ int ULCB_EncodeStreams(ULCB_Context *ctx, int nStreams, const void *pcm, int for
                        uint8_t *out, uint64_t outStrideBytes, uint32_t *blockBytes, float *complexity, int32_t *windowCtrl,
                        uint64_t *totalBytes, int32_t *status);
 
+/* Measurement input: the integer-only synthetic PCM16 corpus of SURVEY.md 8d, generated on the device.  Stream
+ * firstStreamId+i, samples t0 .. t0+nSamples-1, stereo interleaved, written at dOut + i*strideElems.  kind 0 =
+ * music-like, 1 = transient-heavy.  The two look-up tables (host pointers) are the ones ulc_codec_b200/corpus.py
+ * builds; the output is bit-identical to corpus.generate().  Asynchronous on the context's stream. */
+int ULCB_GenerateCorpusDevice(ULCB_Context *ctx, int kind, uint32_t firstStreamId, int nStreams, uint64_t nSamples, uint64_t t0,
+                              const int16_t *sineLut1024, const int16_t *burstLut882, int16_t *dOut, uint64_t strideElems);
+
 /* The CUDA stream (cudaStream_t, as an opaque pointer) the context launches on, so callers that
  * own device memory (e.g. through torch) can order their work against it. */
 void *ULCB_Stream(ULCB_Context *ctx);

@@ -164,3 +164,18 @@ def test_roundtrip_gpu_encode_gpu_decode(capi):
     n = min(len(x), len(y)) - N
     snr = 10 * np.log10((x[:n] ** 2).sum() / ((x[:n] - y[:n]) ** 2).sum())
     assert snr > 12.0, snr
+
+
+def test_device_corpus_is_bit_identical(capi):
+    """The device generator (csrc/ulcb_corpus.cu) and the numpy generator feed GPU and CPU the same samples."""
+    import torch
+    from ulc_codec_b200 import corpus
+    n, ns = 50000, 5
+    for kind in ("music", "transient"):
+        out = torch.zeros(ns * n * 2, dtype=torch.int16, device="cuda")
+        with capi.Context(44100, 2, 2048) as ctx:
+            ctx.generate_corpus_device(kind, 7, ns, n, out.data_ptr(), n * 2, t0=12345)
+            ctx.sync()
+        got = out.cpu().numpy().reshape(ns, n, 2)
+        for i in range(ns):
+            assert np.array_equal(got[i], corpus.generate(7 + i, n, kind, t0=12345)), (kind, i)

@@ -25,6 +25,7 @@ EXPORTS = (
     "ULCB_LaunchCount", "ULCB_TestDCT4", "ULCB_TestParse",
     "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
     "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
+    "ULCB_GenerateCorpusDevice",
 )
 
 MODE_VBR, MODE_CBR, MODE_ABR = 0, 1, 2
@@ -94,6 +95,7 @@ def load():
     L.ULCB_EncodeStreamsDevice.argtypes = [vp, i32, vp, i32, vp, u64, vp, u32, pp, vp, u64, vp, vp, vp, u64, vp, vp]
     L.ULCB_EncodeStreams.argtypes = [vp, i32, vp, i32, vp, u64, u32, pp, vp, u64, vp, vp, vp, vp, vp]
     L.ULCB_TestEncode.argtypes = [vp, i32, vp, i32, vp, u64, u32, pp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ULCB_GenerateCorpusDevice.argtypes = [vp, i32, u32, i32, u64, u64, vp, vp, vp, u64]
     es = C.POINTER(ULC_EncoderState_t)
     L.ULC_EncoderState_Init.argtypes = [es]
     L.ULC_EncoderState_Destroy.argtypes = [es]
@@ -245,6 +247,14 @@ class Context:
                                              n_blocks_all, C.byref(prm), d_out, out_stride, d_block_bytes or None, d_complexity or None,
                                              d_window_ctrl or None, meta_stride, d_total or None, d_status or None)
         _check(self.L, self.h, rc, "ULCB_EncodeStreamsDevice")
+
+    def generate_corpus_device(self, kind: str, first_id: int, n_streams: int, n_samples: int, d_out: int, stride_elems: int, t0: int = 0):
+        """Fill device memory with the synthetic corpus (bit-identical to corpus.generate)."""
+        from . import corpus
+        sine, burst = corpus.sine_lut(), corpus.burst_lut()
+        rc = self.L.ULCB_GenerateCorpusDevice(self.h, corpus._KINDS[kind], first_id, n_streams, n_samples, t0,
+                                              sine.ctypes.data, burst.ctypes.data, d_out, stride_elems)
+        _check(self.L, self.h, rc, "ULCB_GenerateCorpusDevice")
 
     def test_parse(self, data: np.ndarray, n_blocks: int):
         """(coefs float32[nBlocks, nChan*N], bits uint32[nBlocks]) of one stream: parse + dequantise + noise only."""

@@ -15,6 +15,9 @@
 #include "ulcb_decode.h"
 #include "ulcb_encode.h"
 
+cudaError_t ulcb_corpus_launch(int16_t *dOut, uint64_t strideElems, int kind, uint32_t firstId, int nStreams, uint64_t nSamples,
+                               uint64_t t0, const int16_t *dSine, const int16_t *dBurst, cudaStream_t stream);
+
 struct ULCB_Context {
     int device = 0, rateHz = 0, nChan = 0, N = 0;
     uint32_t maxBlocks = 0;
@@ -24,6 +27,7 @@ struct ULCB_Context {
     UlcbTables tb{};
     UlcbEncTables etb{};
     int smCount = 148;
+    int16_t *corpusLut = nullptr;       // sine[1024] + burst[882]
     float *encWs = nullptr; size_t encWsFloats = 0; int encGrid = 0;   // global workspace for large block sizes
     std::vector<void *> owned;          // device allocations freed with the context
     // staging for the host-pointer entry points (grown on demand)
@@ -284,6 +288,7 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->dOut) cudaFree(ctx->dOut);
     if (ctx->dAux) cudaFree(ctx->dAux);
     if (ctx->encWs) cudaFree(ctx->encWs);
+    if (ctx->corpusLut) cudaFree(ctx->corpusLut);
     delete ctx;
 }
 
@@ -475,6 +480,23 @@ int ULC_DecodeBlock(struct ULC_DecoderState_t *State, float *DstData, const void
     UlcbStreamState st;
     if (cudaMemcpy(&st, d->dState, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess) State->LastSubBlockSize = st.lastSubBlockSize;
     return (int)*d->hBits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic corpus (measurement input) - device twin of ulc_codec_b200/corpus.py
+// ------------------------------------------------------------------------------------------------
+int ULCB_GenerateCorpusDevice(ULCB_Context *ctx, int kind, uint32_t firstStreamId, int nStreams, uint64_t nSamples, uint64_t t0,
+                              const int16_t *sineLut1024, const int16_t *burstLut882, int16_t *dOut, uint64_t strideElems) {
+    if (!ctx || !dOut || !sineLut1024 || !burstLut882 || nStreams < 0 || (kind != 0 && kind != 1) || ctx->nChan != 2) return ULCB_E_PARAM;
+    if (strideElems < 2 * nSamples || (strideElems & 1)) return ULCB_E_PARAM;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->corpusLut) CK(ctx, cudaMalloc(&ctx->corpusLut, sizeof(int16_t) * (1024 + 896)));
+    CK(ctx, cudaMemcpyAsync(ctx->corpusLut, sineLut1024, sizeof(int16_t) * 1024, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(ctx->corpusLut + 1024, burstLut882, sizeof(int16_t) * 882, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));                 // the LUT arguments may be pageable host memory
+    CK(ctx, ulcb_corpus_launch(dOut, strideElems, kind, firstStreamId, nStreams, nSamples, t0, ctx->corpusLut, ctx->corpusLut + 1024, ctx->stream));
+    ctx->launches++;
+    return ULCB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -27,6 +27,20 @@
 #include "ulcb_dct.cuh"
 #include "ulcb_decode.h"
 
+#ifdef ULCB_PHASE_TIMING
+__device__ unsigned long long g_ulcbDecPhase[16];
+#define DTK(i) do { if (tid == 0) { long long t_ = clock64(); phaseAcc[i] += t_ - tPrev; tPrev = t_; } } while (0)
+extern "C" int ULCB_DebugDecodePhaseTimes(unsigned long long *out16) {
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_ulcbDecPhase, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_ulcbDecPhase, z, sizeof z);
+    return (int)e;
+}
+#else
+#define DTK(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int PAGE_WORDS = 256;                // one parse page = 256 32-bit words = 2048 nybbles
@@ -86,6 +100,7 @@ struct Smem {
     uint32_t *emitB;     // [PAGE_WORDS] drawStart (relative to block draw base)
     NoiseRun *runs;      // [maxRuns]
     int      *ctl;       // control scalars
+    int      *scan;      // [SCAN_INTS] scratch of the chain resolver
 };
 enum { C_NRUNS = 0, C_SEND, C_ENDPOS, C_ENDKIND, C_ENDCOEFS, C_ENDDRAWS, C_ENDQ, C_ENDZYX, C_OK,
        C_EXITPH, C_SUMCOEFS, C_SUMDRAWS, C_LASTQ, C_COUNT };
@@ -148,113 +163,99 @@ __device__ __forceinline__ uint32_t page_window(const Smem<NCH> &sm, int i) {  /
 }
 
 // ------------------------------------------------------------------------------------------------
-// Resolve (warp 0) the token chain that starts at page-relative nybble tp with `remain` coefficients
-// still to come, quantiser qcur.  Writes emit records for the segments on the chain and the control
-// block (end segment/position/kind or carry-out to the next page).
+// Resolve the token chain that starts at page-relative nybble tp with `remain` coefficients still to come,
+// quantiser qcur.  Every thread owns one 8-nybble segment of the page.  Which phase (token-start offset 0..4)
+// each segment is entered at is a prefix composition of the segments' 5-state transition maps - an associative
+// operator, so it is a CTA-wide scan; coefficient / noise-draw counts and "last quantiser set" are then ordinary
+// scans of the per-segment values looked up at that phase.  Writes emit records for the segments on the chain
+// and the control block (end segment/position/kind, or the carry-out to the next page).
 // ------------------------------------------------------------------------------------------------
+enum { MAP_IDENT = 0 | (1 << 3) | (2 << 6) | (3 << 9) | (4 << 12) | (5 << 15), SCAN_INTS = 136 };
+
+__device__ __forceinline__ uint32_t map_compose(uint32_t f, uint32_t g) {      // apply f, then g; state 5 = stopped
+    uint32_t h = 0;
+#pragma unroll
+    for (int e = 0; e < 6; e++) h |= ((g >> (3 * ((f >> (3 * e)) & 7))) & 7) << (3 * e);
+    return h;
+}
+
 template <int NCH>
 __device__ void resolve_chain(const Smem<NCH> &sm, int tp, int remain, int qcur, int coefBase, int drawBase) {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int s0 = tp >> 3, e0 = tp & 7;
-    const int lane0 = s0 >> 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = tid, s0 = tp >> 3, e0 = tp & 7;
+    const bool has = s < PAGE_WORDS;
+    const int col = info_col(has ? s : 0);
+    int *scr = sm.scan;
+    constexpr int SEGW = PAGE_WORDS / 32;                          // warps that own segments
 
-    // pass 1: compose this lane's 8 segment maps (entries 0..4 -> exit 0..4 or 7 = stopped)
-    uint32_t F = 0;                                  // 5 x 3 bits
-    {
-        int cur[5] = {0, 1, 2, 3, 4};
-        for (int k = 0; k < 8; k++) {
-            int s = lane * 8 + k;
-            if (s < s0) continue;
-            uint32_t m = sm.pmap[info_col(s)];
+    // ---- entry phases: scan of transition maps ----
+    uint32_t m = MAP_IDENT;
+    if (has && s >= s0) {
+        if (s == s0) {
+            uint32_t w = sm.info[e0 * INFO_ROW + col];
+            uint32_t x = (w & 8) ? 5u : (w & 7u);
+            m = x * 0x9249u;                                       // the same exit whatever the (irrelevant) input
+        } else {
+            uint32_t pm = sm.pmap[col];
+            m = 5u << 15;
 #pragma unroll
-            for (int e = 0; e < 5; e++) cur[e] = (cur[e] == 7) ? 7 : (int)((m >> (3 * cur[e])) & 7u);
+            for (int e = 0; e < 5; e++) { uint32_t v = (pm >> (3 * e)) & 7u; m |= (v == 7u ? 5u : v) << (3 * e); }
         }
+    }
 #pragma unroll
-        for (int e = 0; e < 5; e++) F |= (uint32_t)cur[e] << (3 * e);
-    }
-    // the start lane's true result: walk from e0 (may be 5..7, not covered by the 5-entry map)
-    int startOut = 0;
-    if (lane == lane0) {
-        int ph = e0;
-        for (int k = s0 - lane * 8; k < 8; k++) {
-            int s = lane * 8 + k;
-            uint32_t w = sm.info[ph * INFO_ROW + info_col(s)];
-            if (w & 8) { ph = 7; break; }
-            ph = w & 7;
-        }
-        startOut = ph;
-    }
-    // serial hand-over of the phase from lane to lane
-    int phIn = 0, carry = __shfl_sync(FULL, startOut, lane0);
-    for (int l = lane0 + 1; l < 32; l++) {
-        int out = (carry == 7) ? 7 : (int)((F >> (3 * carry)) & 7u);
-        if (lane == l) phIn = carry;
-        carry = __shfl_sync(FULL, out, l);
-    }
-    if (lane == lane0) phIn = e0;
-    const int pageExit = carry;                      // phase entering the next page (7 = stopped)
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, m, d); if (lane >= d) m = map_compose(t, m); }
+    if (lane == 31 && warp < SEGW) scr[warp] = (int)m;
+    if (tid == 0) scr[132] = 1 << 30;
+    __syncthreads();
+    uint32_t pre = MAP_IDENT;
+    for (int wv = 0; wv < warp && wv < SEGW; wv++) pre = map_compose(pre, (uint32_t)scr[wv]);
+    const uint32_t minc = map_compose(pre, m);
+    uint32_t mexc = __shfl_up_sync(FULL, minc, 1);
+    if (lane == 0) mexc = pre;
+    const int ph = (s == s0) ? e0 : (int)(mexc & 7u);
+    const bool on = has && s >= s0 && (s == s0 || ph != 5);
 
-    // pass 2: walk own segments with the true phase; local sums
-    int locCoefs = 0, locDraws = 0, locQ = 0, stopSeg = 1 << 30;
-    int segPh[8], segC[8], segD[8], segQ[8];
-    {
-        int ph = phIn;
-        bool on = (lane == lane0) || (lane > lane0 && phIn != 7);   // NB: 7 is also a legal START offset for lane0
-        for (int k = 0; k < 8; k++) {
-            int s = lane * 8 + k;
-            segPh[k] = -1; segC[k] = locCoefs; segD[k] = locDraws; segQ[k] = locQ;
-            if (!on || s < s0) continue;
-            int col = info_col(s);
-            uint32_t w = sm.info[ph * INFO_ROW + col];
-            int l = sm.lq[ph * INFO_ROW + col];
-            segPh[k] = ph;
-            locCoefs += (w >> 4) & 0x3fff;
-            locDraws += (w >> 18) & 0x3fff;
-            if (l) locQ = l;
-            if (w & 8) { stopSeg = s; on = false; }
-            ph = w & 7;
-        }
+    // ---- counts at the true phase: coefficients, noise draws, last quantiser ----
+    int c = 0, d = 0, l = 0, stop = 0;
+    if (on) {
+        uint32_t w = sm.info[ph * INFO_ROW + col];
+        c = (w >> 4) & 0x3fff; d = (int)(w >> 18); l = sm.lq[ph * INFO_ROW + col]; stop = (w >> 3) & 1;
     }
-    // exclusive scans across lanes
-    int preC = locCoefs, preD = locDraws, preQ = locQ;
-    for (int d = 1; d < 32; d <<= 1) {
-        int c = __shfl_up_sync(FULL, preC, d), dd = __shfl_up_sync(FULL, preD, d), q = __shfl_up_sync(FULL, preQ, d);
-        if (lane >= d) { preC += c; preD += dd; if (!preQ) preQ = q; }
+    int ic = c, id = d, il = l;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        int tc = __shfl_up_sync(FULL, ic, k), td = __shfl_up_sync(FULL, id, k), tl = __shfl_up_sync(FULL, il, k);
+        if (lane >= k) { ic += tc; id += td; if (!il) il = tl; }
     }
-    int totC = __shfl_sync(FULL, preC, 31), totD = __shfl_sync(FULL, preD, 31), totQ = __shfl_sync(FULL, preQ, 31);
-    preC -= locCoefs; preD -= locDraws;
-    {   // exclusive "last quantiser" = inclusive of the previous lane
-        int q = __shfl_up_sync(FULL, preQ, 1);
-        preQ = (lane == 0) ? 0 : q;
-    }
-    // end segment: first on-chain segment with a stop or whose inclusive coefficient count reaches `remain`
-    int endSeg = stopSeg;
-    for (int k = 0; k < 8; k++) {
-        if (segPh[k] < 0) continue;
-        int incl = preC + ((k == 7) ? locCoefs : segC[k + 1]);
-        if (incl >= remain) { int s = lane * 8 + k; if (s < endSeg) endSeg = s; break; }
-    }
-    for (int d = 16; d; d >>= 1) endSeg = min(endSeg, __shfl_xor_sync(FULL, endSeg, d));
+    if (lane == 31 && warp < SEGW) { scr[32 + warp] = ic; scr[64 + warp] = id; scr[96 + warp] = il; }
+    __syncthreads();
+    int pc = 0, pd = 0, pl = 0;
+    for (int wv = 0; wv < warp && wv < SEGW; wv++) { pc += scr[32 + wv]; pd += scr[64 + wv]; if (scr[96 + wv]) pl = scr[96 + wv]; }
+    ic += pc; id += pd; if (!il) il = pl;
+    const int ec = ic - c, ed = id - d;                            // exclusive sums
+    int el = __shfl_up_sync(FULL, il, 1);                          // last quantiser set before this segment
+    if (lane == 0) el = pl;
 
-    // pass 3: emit records
-    for (int k = 0; k < 8; k++) {
-        int s = lane * 8 + k;
+    // ---- end segment: first on-chain segment with a stop code or that completes the sub-block ----
+    if (on && (stop || ic >= remain)) atomicMin(&scr[132], s);
+    __syncthreads();
+    const int endSeg = scr[132];
+
+    if (has) {
         uint32_t a = 0, b = 0;
-        if (segPh[k] >= 0 && s <= endSeg) {
-            int q = segQ[k] ? (segQ[k] & 31) : (preQ ? (preQ & 31) : qcur);
-            a = (uint32_t)(coefBase + preC + segC[k]) | ((uint32_t)segPh[k] << 16) | ((uint32_t)q << 20) | 0x80000000u;
-            b = (uint32_t)(drawBase + preD + segD[k]);
+        if (on && s <= endSeg) {
+            int q = el ? (el & 31) : qcur;
+            a = (uint32_t)(coefBase + ec) | ((uint32_t)ph << 16) | ((uint32_t)q << 20) | 0x80000000u;
+            b = (uint32_t)(drawBase + ed);
         }
         sm.emitA[s] = a; sm.emitB[s] = b;
     }
     if (endSeg < (1 << 30)) {
-        // the owner lane walks the end segment token by token
-        if (lane == (endSeg >> 3)) {
-            int k = endSeg & 7;
-            int q = segQ[k] ? (segQ[k] & 31) : (preQ ? (preQ & 31) : qcur);
-            int c = preC + segC[k], d = preD + segD[k];
-            int p = endSeg * 8 + ((endSeg == s0) ? e0 : segPh[k]);
+        if (s == endSeg) {                                         // the owner walks the end segment token by token
+            int q = el ? (el & 31) : qcur;
+            int cc = ec, dd = ed;
+            int p = endSeg * 8 + ph;
             int kind = -1, zyx = 0, ok = 1;
             for (;;) {
                 uint32_t x = page_window(sm, p);
@@ -265,18 +266,18 @@ __device__ void resolve_chain(const Smem<NCH> &sm, int tp, int remain, int qcur,
                     p += t.len; break;
                 }
                 if (t.q >= 0) q = t.q;
-                if (c + t.coefs > remain) { ok = 0; break; }       // run overshoot: corrupt (ulcDecoder.c:127,139,154)
-                c += t.coefs; d += t.draws; p += t.len;
-                if (c == remain) { kind = 0; break; }
+                if (cc + t.coefs > remain) { ok = 0; break; }     // run overshoot: corrupt (ulcDecoder.c:127,139,154)
+                cc += t.coefs; dd += t.draws; p += t.len;
+                if (cc == remain) { kind = 0; break; }
             }
             sm.ctl[C_SEND] = endSeg; sm.ctl[C_ENDPOS] = p; sm.ctl[C_ENDKIND] = kind;
-            sm.ctl[C_ENDCOEFS] = c; sm.ctl[C_ENDDRAWS] = d; sm.ctl[C_ENDQ] = q; sm.ctl[C_ENDZYX] = zyx;
+            sm.ctl[C_ENDCOEFS] = cc; sm.ctl[C_ENDDRAWS] = dd; sm.ctl[C_ENDQ] = q; sm.ctl[C_ENDZYX] = zyx;
             sm.ctl[C_OK] = ok;
         }
-    } else if (lane == 0) {
-        sm.ctl[C_SEND] = -1;                         // chain runs off this page
-        sm.ctl[C_EXITPH] = pageExit; sm.ctl[C_SUMCOEFS] = totC; sm.ctl[C_SUMDRAWS] = totD;
-        sm.ctl[C_LASTQ] = totQ ? (totQ & 31) : qcur;
+    } else if (s == PAGE_WORDS - 1) {
+        sm.ctl[C_SEND] = -1;                                       // chain runs off this page
+        sm.ctl[C_EXITPH] = (int)(minc & 7u); sm.ctl[C_SUMCOEFS] = ic; sm.ctl[C_SUMDRAWS] = id;
+        sm.ctl[C_LASTQ] = il ? (il & 31) : qcur;
         sm.ctl[C_OK] = 1;
     }
 }
@@ -343,6 +344,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
         sm.emitB = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * PAGE_WORDS;
         sm.runs = reinterpret_cast<NoiseRun *>(p);  p += sizeof(NoiseRun) * maxRuns;
         sm.ctl  = reinterpret_cast<int *>(p);       p += sizeof(int) * 16;
+        sm.scan = reinterpret_cast<int *>(p);       p += sizeof(int) * 136;
         sm.pmap = reinterpret_cast<uint16_t *>(p);  p += sizeof(uint16_t) * INFO_ROW;
         sm.lq   = reinterpret_cast<uint8_t *>(p);
     }
@@ -370,6 +372,9 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
         }
         long long curPage = -1;
         __syncthreads();
+#ifdef ULCB_PHASE_TIMING
+        long long phaseAcc[8] = {0}; long long tPrev = clock64();
+#endif
 
         for (int blk = 0; blk < nBlocks; blk++) {
             void *outBlk = PCM16
@@ -408,11 +413,14 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                         if (!silent) {
                             int remain = S, sub0 = coefBase;
                             for (;;) {
+                                DTK(0);
                                 ensure(pos);
                                 int tp = (int)(pos - curPage * PAGE_NYB);
                                 __syncthreads();
-                                if (tid < 32) resolve_chain<NCH>(sm, tp, remain, q, sub0 + (S - remain), (int)blkDraws);
+                                DTK(5);
+                                resolve_chain<NCH>(sm, tp, remain, q, sub0 + (S - remain), (int)blkDraws);
                                 __syncthreads();
+                                DTK(6);
                                 int sEnd = sm.ctl[C_SEND];
 #ifdef ULCB_DEBUG_PARSE
                                 if (tid == 0 && args.dbgCoefs && blk <= 2)
@@ -422,6 +430,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
 #endif
                                 if (!sm.ctl[C_OK]) { ok = false; break; }
                                 emit_chain<NCH>(sm, tp, sEnd < 0 ? PAGE_WORDS : sEnd, sm.ctl[C_ENDPOS], maxRuns, drawBase);
+                                DTK(7);
                                 if (sEnd >= 0) {
                                     const int kind = sm.ctl[C_ENDKIND];
                                     const int cdone = sm.ctl[C_ENDCOEFS];      // coefficients consumed by this page's part of the chain
@@ -480,6 +489,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
 
             // ---------------- noise fill ----------------
             __syncthreads();
+            DTK(0);
             {
                 const int nRuns = min(sm.ctl[C_NRUNS], maxRuns);
                 const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
@@ -500,6 +510,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                 }
             }
             __syncthreads();
+            DTK(1);
             if (args.dbgCoefs) {
                 float *dc = args.dbgCoefs + ((size_t)stream * args.nBlocksAll + blk) * NCH * N;
                 for (int i = tid; i < NCH * N; i += nthr) dc[i] = sm.buf[i];
@@ -511,6 +522,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                 for (unsigned pat = kLayout[wc >> 4];; j++) {
                     const int sh = pat & 7, S = N >> sh, hS = S >> 1, lgHS = tb.log2N - sh - 1;
                     dct4_inplace<MAXPAIRS>(sm.buf + off, N, NCH, S, sh, tb);
+                    DTK(2);
 
                     int ov = S;
                     if (pat & 8) ov >>= (wc & 7);
@@ -573,6 +585,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                 }
             }
 
+            DTK(3);
             // ---------------- M/S undo + interleave + store ----------------
             if (NCH == 2) {
                 for (int i = tid; i < N / 4; i += nthr) {
@@ -605,7 +618,11 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                 }
             }
             __syncthreads();
+            DTK(4);
         }
+#ifdef ULCB_PHASE_TIMING
+        if (tid == 0) { for (int i = 0; i < 8; i++) atomicAdd(&g_ulcbDecPhase[i], (unsigned long long)phaseAcc[i]); atomicAdd(&g_ulcbDecPhase[8], (unsigned long long)nBlocks); }
+#endif
 
         // ---- save stream state / status ----
         if (st) {
@@ -626,7 +643,7 @@ size_t ulcb_decode_smem_bytes(int N, int nChan) {
     size_t maxRuns = (size_t)nChan * N / 16 + 8 * nChan;
     return sizeof(float) * nChan * N + sizeof(float) * nChan * (N / 2) + sizeof(uint32_t) * (PAGE_WORDS + 4) +
            sizeof(uint32_t) * 8 * INFO_ROW + 2 * sizeof(uint32_t) * PAGE_WORDS + sizeof(NoiseRun) * maxRuns +
-           sizeof(int) * 16 + sizeof(uint16_t) * INFO_ROW + 8 * INFO_ROW + 16;
+           sizeof(int) * (16 + 136) + sizeof(uint16_t) * INFO_ROW + 8 * INFO_ROW + 16;
 }
 
 template <int NCH, int NTHR>
