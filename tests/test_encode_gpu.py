@@ -179,3 +179,22 @@ def test_device_corpus_is_bit_identical(capi):
         got = out.cpu().numpy().reshape(ns, n, 2)
         for i in range(ns):
             assert np.array_equal(got[i], corpus.generate(7 + i, n, kind, t0=12345)), (kind, i)
+
+
+def test_shard_of_a_batch_equals_the_batch(capi):
+    """rank r of G owns streams [a, b); running that shard alone must give exactly what the full batch
+    gives for those streams (no cross-stream state), for the encoder and the decoder."""
+    from ulc_codec_b200 import corpus, shard
+    pcms = [corpus.generate(300 + i, 20000 + 1000 * i, "music") for i in range(7)]
+    with capi.Context(44100, 2, 2048) as ctx:
+        nb = ctx.blocks_for(max(len(p) for p in pcms))
+        full = ctx.encode_streams(pcms, "vbr", 45.0, n_blocks=nb)
+        dfull, sfull, _ = ctx.decode_streams(full["streams"], nb, fmt="pcm16")
+        for world in (2, 3):
+            for r in range(world):
+                a, b = shard.stream_range(r, world, len(pcms))
+                part = ctx.encode_streams(pcms[a:b], "vbr", 45.0, n_blocks=nb)
+                for i in range(a, b):
+                    assert np.array_equal(part["streams"][i - a], full["streams"][i])
+                dpart, spart, _ = ctx.decode_streams(full["streams"][a:b], nb, fmt="pcm16")
+                assert np.array_equal(dpart, dfull[a:b]) and np.array_equal(spart, sfull[a:b])
