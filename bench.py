@@ -349,7 +349,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (kern_ms / 1e3) / 1e9
-    roof = {"bound": "hbm", "kernel": "ulcb_decode_kernel<2,true,256>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roof = {"bound": "hbm", "kernel": "ulcb_decode_ws_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)",
             "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kern_ms, "traffic": None}
 

@@ -31,3 +31,10 @@ with capi.Context(44100, 2, 2048, max_blocks=a.blocks) as ctx:
         buf = (C.c_ulonglong * 16)(); ctx.L.ULCB_DebugDecodePhaseTimes(buf)
         n = max(1, buf[8]); names = ["parse", "noise", "dct", "unfold+delay", "store"]
         print("phase cycles per block (thread 0): " + ", ".join(f"{nm} {buf[i] / n:.0f}" for i, nm in enumerate(names)) + f" | total {sum(buf[i] for i in range(8)) / n:.0f} | ensure/load_page {buf[5] / n:.0f} resolve {buf[6] / n:.0f} emit {buf[7] / n:.0f}")
+    if hasattr(ctx.L, "ULCB_DebugDecodeWsPhaseTimes"):
+        buf = (C.c_ulonglong * 32)(); ctx.L.ULCB_DebugDecodeWsPhaseTimes(buf)
+        n = max(1, buf[8])
+        print("ws parse cycles/block: " + ", ".join(f"{nm} {buf[i] / n:.0f}" for i, nm in enumerate(["other", "wait-empty", "win-load", "chain"])) + f" | chains/block {buf[4] / n:.2f}")
+        names = ["other", "wait-full", "noise", "load+pre", "fft1+tw", "transpose", "fft2", "post+unfold", "swap-write", "xchg-wait", "ms+store"]
+        print("ws transform(ch0) cycles/block: " + ", ".join(f"{nm} {buf[16 + i] / n:.0f}" for i, nm in enumerate(names)))
+        print("ws chain cycles/block: " + ", ".join(f"{nm} {buf[9 + i] / n:.0f}" for i, nm in enumerate(["digest", "mapscan", "entry+walk", "counts+lq", "scans", "end-walk", "emit"])))

@@ -19,9 +19,11 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 // In-place DCT-IV of nT transforms of size S.  Transform t occupies base[t*stride .. t*stride+S).
 // sh = log2(N/S) selects the twiddle tables.  All threads of the CTA must call this.
 // MAXPAIRS bounds the register staging of the post pass: nT*S/4 <= MAXPAIRS*blockDim.x.
-template <int MAXPAIRS>
+// WARP = true: the calling warp alone owns the transform(s) (32 "threads", __syncwarp between passes).
+template <int MAXPAIRS, bool WARP = false>
 __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, const UlcbTables &tb) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nthr = WARP ? 32 : blockDim.x;
+    auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     const int M = S >> 1;                       // complex FFT size
     const float2 *__restrict__ E = tb.dctE[sh];
 
@@ -36,7 +38,7 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
         z[n] = zn;
         z[m] = zm;
     }
-    __syncthreads();
+    sync();
 
     // ---- radix-4 DIF stages ----
     const int Mmax = tb.N >> 1;
@@ -66,7 +68,7 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
             }
             x[0] = y0; x[q] = y1; x[2 * q] = y2; x[3 * q] = y3;
         }
-        __syncthreads();
+        sync();
     }
     if (L == 2) {                               // odd log2(M): one radix-2 stage on adjacent pairs
         for (int idx = tid; idx < nT * (M >> 1); idx += nthr) {
@@ -76,7 +78,7 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
             x[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
             x[1] = make_float2(a0.x - a1.x, a0.y - a1.y);
         }
-        __syncthreads();
+        sync();
     }
 
     // ---- post-twiddle + un-permute: pairs (k, M-1-k); staged in registers across a barrier ----
@@ -94,7 +96,7 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
             o1[r] = make_float2(ym.x, -yk.y);   // X[2m], X[2m+1] = X[S-1-2k]
         }
     }
-    __syncthreads();
+    sync();
 #pragma unroll
     for (int r = 0; r < MAXPAIRS; r++) {
         int idx = tid + r * nthr;
@@ -105,5 +107,5 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
             z[m] = o1[r];
         }
     }
-    __syncthreads();
+    sync();
 }

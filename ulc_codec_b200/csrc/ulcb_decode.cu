@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "ulcb_dct.cuh"
 #include "ulcb_decode.h"
 
@@ -664,6 +665,14 @@ int ulcb_decode_threads(int N, int nChan) {
 
 cudaError_t ulcb_decode_launch(const UlcbDecodeArgs &args, int nChan, int pcm16, int gridBlocks, cudaStream_t stream) {
     const int N = args.tb.N;
+    static const bool forceGeneric = getenv("ULCB_DECODE_GENERIC") != nullptr;
+    if (!forceGeneric && ulcb_decode_ws_supported(args, nChan)) {
+        int dev = 0, sms = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        return ulcb_decode_ws_launch(args, pcm16, sms, stream);
+    }
     size_t smem = ulcb_decode_smem_bytes(N, nChan);
     int nthr = ulcb_decode_threads(N, nChan);
     if (nChan == 2) {

@@ -34,3 +34,8 @@ struct UlcbDecodeArgs {
 size_t      ulcb_decode_smem_bytes(int N, int nChan);
 int         ulcb_decode_threads(int N, int nChan);
 cudaError_t ulcb_decode_launch(const UlcbDecodeArgs &args, int nChan, int pcm16, int gridBlocks, cudaStream_t stream);
+
+// Warp-specialised fast path (ulcb_decode_ws.cu): BlockSize 2048, stereo, fresh streams.  ulcb_decode_launch
+// routes to it when it applies; ULCB_DECODE_GENERIC=1 in the environment forces the generic kernel (A/B timing).
+bool        ulcb_decode_ws_supported(const UlcbDecodeArgs &args, int nChan);
+cudaError_t ulcb_decode_ws_launch(const UlcbDecodeArgs &args, int pcm16, int smCount, cudaStream_t stream);
