@@ -606,13 +606,26 @@ struct Encoder {
         double (*lo)[3] = sm.lo[unit];
         const int src = lane < 3 ? lane : 0;
         double acc = 0.0;
-        int e = 0, nextPos = __ldg(&ev[0]);
-        auto events_at = [&](int pos) {
-            while (nextPos == pos) {
-                const int code = __ldg(&ev[2 * e + 1]), b = code & 0x7F;
-                if (lane < 3) { if (code & 0x80) lo[b][lane] = acc - lo[b][lane]; else lo[b][lane] = acc; }
-                e++;
-                nextPos = (e < 2 * ULCB_NBARK) ? (int)__ldg(&ev[2 * e]) : 0x7fffffff;
+        // The 2*NBARK band-edge events (position-sorted) live two per lane.  Lanes 0..2 run the three dependent DADD
+        // chains over a group of 32 lines and leave the running sum BEFORE each line in `stage`; the lanes whose
+        // events fall inside the group then pick their snapshots up in parallel (band starts first, then band ends,
+        // which is the list order for a band that starts and ends on the same line).
+        int p0 = 0x7fffffff, c0 = 0, p1 = 0x7fffffff, c1 = 0;
+        if (lane < 2 * ULCB_NBARK) { p0 = __ldg(&ev[2 * lane]); c0 = __ldg(&ev[2 * lane + 1]); }
+        if (lane + 32 < 2 * ULCB_NBARK) { p1 = __ldg(&ev[2 * (lane + 32)]); c1 = __ldg(&ev[2 * (lane + 32) + 1]); }
+        auto apply = [&](int pos, int code, int base, bool ends) {
+            if (pos >= base && pos < base + 32 && ((code & 0x80) != 0) == ends) {
+                const int t = pos - base, b = code & 0x7F;
+#pragma unroll
+                for (int q = 0; q < 3; q++) { const double val = stage[q][t]; lo[b][q] = ends ? val - lo[b][q] : val; }
+            }
+        };
+        auto events_in = [&](int base) {
+            const bool mine = (p0 >= base && p0 < base + 32) || (p1 >= base && p1 < base + 32);
+            if (__any_sync(0xffffffffu, mine)) {
+                apply(p0, c0, base, false); apply(p1, c1, base, false);
+                __syncwarp();
+                apply(p0, c0, base, true); apply(p1, c1, base, true);
             }
         };
         float xN = v[lane], lN = lg[lane];
@@ -622,14 +635,21 @@ struct Encoder {
             __syncwarp();
             stage[0][lane] = L; stage[1][lane] = L * X; stage[2][lane] = X;
             __syncwarp();
-            if (nextPos >= base + 32) {
-#pragma unroll 8
-                for (int t = 0; t < 32; t++) acc += stage[src][t];
-            } else {
-                for (int t = 0; t < 32; t++) { events_at(base + t); acc += stage[src][t]; }
+#pragma unroll
+            for (int t0 = 0; t0 < 32; t0 += 8) {
+                double a[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) a[t] = stage[src][t0 + t];
+#pragma unroll
+                for (int t = 0; t < 8; t++) { if (lane < 3) stage[src][t0 + t] = acc; acc += a[t]; }
             }
+            __syncwarp();
+            events_in(base);
         }
-        events_at(n);
+        __syncwarp();
+        if (lane < 3) stage[src][0] = acc;                                // events on the line past the end see the totals
+        __syncwarp();
+        events_in(n);
         __syncwarp();
         // band levels: lanes 0..24; a band without energy inherits the previous band's level
         float level = 0.0f; bool ok = false;
