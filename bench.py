@@ -222,7 +222,7 @@ def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, war
                     "blocks_per_stream": nb, "input": "integer-only synthetic music corpus generated on the device (csrc/ulcb_corpus.cu), every stream distinct",
                     "avg_bytes_per_block": out_bytes / (n_streams * nb)},
          "roofline": {"bound": "hbm", "kernel": "ulcb_encode_kernel<2,512,false>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                      "algorithmic_bytes_per_launch": algo, "launch_ms": ms, "traffic": None},
+                      "algorithmic_bytes_per_launch": algo, "launch_ms": ms, "traffic": measured_traffic("encode", n_streams, nb)},
          "gpu_launches": steps}
     if with_cpu:
         c = cpu_reference_encode()
@@ -232,6 +232,19 @@ def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, war
 
 
 # ------------------------------------------------------------------------------------------------
+
+def measured_traffic(kernel: str, n_streams: int, n_blocks: int):
+    """DRAM bytes (read + write) of one launch of `kernel`, from the committed `ncu --set full` capture of the same
+    launch shape (profiles/traffic.json, written by scripts/ncu_traffic.py).  None when the shapes differ."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+    except Exception:
+        return None
+    if t.get("streams") != n_streams or t.get("blocks") != n_blocks:
+        return None
+    return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,7 +364,8 @@ def main():
     achieved = algo_bytes / (kern_ms / 1e3) / 1e9
     roof = {"bound": "hbm", "kernel": "ulcb_decode_ws_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)",
-            "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kern_ms, "traffic": None}
+            "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kern_ms,
+            "traffic": measured_traffic("decode", n_streams, BLOCKS_PER_STREAM)}
 
     # ---- e2e: through the host-pointer C-ABI call, pinned host buffers, copies inside the timed region ----
     e2e = None

@@ -116,7 +116,8 @@ enum {
 	ULCB_E_NODEVICE    = -5,   /* no sm_100 GPU / kernel image: there is no CPU fallback */
 };
 
-enum { ULCB_FMT_PCM16 = 0, ULCB_FMT_FLOAT32 = 1 };
+enum { ULCB_FMT_PCM16 = 0, ULCB_FMT_FLOAT32 = 1,
+       ULCB_FMT_PCM8U = 2, ULCB_FMT_PCM24 = 3 /* these two: ULCB_ConvertSamplesDevice only */ };
 
 /* Create a context bound to CUDA device `device` for streams of (rateHz, nChan, blockSize).
  * maxBlocksPerStream bounds the stream length the noise-sign table is prepared for. */
@@ -200,6 +201,14 @@ int ULCB_EncodeStreams(ULCB_Context *ctx, int nStreams, const void *pcm, int for
  * builds; the output is bit-identical to corpus.generate().  Asynchronous on the context's stream. */
 int ULCB_GenerateCorpusDevice(ULCB_Context *ctx, int kind, uint32_t firstStreamId, int nStreams, uint64_t nSamples, uint64_t t0,
                               const int16_t *sineLut1024, const int16_t *burstLut882, int16_t *dOut, uint64_t strideElems);
+
+/* Device-side sample I/O.  replaces: WAV_ConvertToFloat_{PCM8u,PCM16,PCM24} / WAV_ConvertFromFloat_{...},
+ * /root/reference/tools/WavIO_Helper.c:31-87 (what tools/ulcEncodeTool.c:153 and tools/ulcDecodeTool.c:166-171 call
+ * around every block).  Converts nSamples interleaved samples between `format` (ULCB_FMT_PCM8U: unsigned 8-bit,
+ * ULCB_FMT_PCM16, ULCB_FMT_PCM24: packed little-endian 3-byte, ULCB_FMT_FLOAT32) and float32 in +-1.0 with the
+ * reference's scale / clamp / round-half-even rules.  toFloat != 0: dSrc holds `format`, dDst float32; toFloat == 0:
+ * dSrc holds float32, dDst `format`.  Device pointers; asynchronous on the context's stream. */
+int ULCB_ConvertSamplesDevice(ULCB_Context *ctx, int format, int toFloat, const void *dSrc, void *dDst, uint64_t nSamples);
 
 /* The CUDA stream (cudaStream_t, as an opaque pointer) the context launches on, so callers that
  * own device memory (e.g. through torch) can order their work against it. */

@@ -242,3 +242,41 @@ class Encoder:
             for k_, v_ in extra.items():
                 r[k_] = np.stack(v_) if np.ndim(v_[0]) else np.array(v_)
         return r
+
+
+# ---- sample formats (tools/WavIO_Helper.c:31-87), numpy restatement; pinned against the reference tools in
+# ---- tests/test_sample_formats.py (ulcdecodetool -format:..., ulcencodetool reading 8/16/24-bit and float WAVs)
+def samples_to_float(raw: np.ndarray, fmt: str) -> np.ndarray:
+    """raw: uint8 (pcm8u), int16 (pcm16), uint8[3n] little-endian packed (pcm24) or float32 (f32) -> float32."""
+    if fmt == "pcm8u":
+        # :31-37 as written: the byte is read as int8, PROMOTED to int and only then xor-ed with 0x80, so the result is
+        # b+128 for b < 128 and b-384 above (outside +-1.0) - reproduced, not repaired, because that is what the
+        # reference encoder sees for an 8-bit WAV
+        return (raw.astype(np.uint8).view(np.int8).astype(np.int32) ^ 0x80).astype(np.float32) * np.float32(2.0 ** -7)
+    if fmt == "pcm16":
+        return raw.astype(np.int16).astype(np.float32) * np.float32(2.0 ** -15)                                # :49-55
+    if fmt == "pcm24":
+        b = raw.astype(np.uint8).reshape(-1, 3).astype(np.uint32)
+        x = ((b[:, 0] << 8) | (b[:, 1] << 16) | (b[:, 2] << 24)).astype(np.uint32).view(np.int32)
+        return x.astype(np.float32) * np.float32(2.0 ** -31)                                                    # :67-77
+    if fmt == "f32":
+        return raw.astype(np.float32)
+    raise ValueError(fmt)
+
+
+def samples_from_float(x: np.ndarray, fmt: str) -> np.ndarray:
+    """float32 -> the format's storage (uint8 / int16 / packed uint8[3n] / float32): clamp, lrintf (half-even)."""
+    x = x.astype(np.float32)
+    if fmt == "pcm8u":
+        q = np.rint(np.clip(x * np.float32(128.0), np.float32(-128.0), np.float32(127.0))).astype(np.int8)    # :39-45
+        return q.view(np.uint8) ^ np.uint8(0x80)
+    if fmt == "pcm16":
+        return float_to_pcm16(x)
+    if fmt == "pcm24":
+        q = np.rint(np.clip(x * np.float32(8388608.0), np.float32(-8388608.0), np.float32(8388607.0))).astype(np.int32).view(np.uint32)
+        out = np.empty((len(q), 3), np.uint8)
+        out[:, 0] = q & 0xFF; out[:, 1] = (q >> 8) & 0xFF; out[:, 2] = (q >> 16) & 0xFF                         # :79-87
+        return out.reshape(-1)
+    if fmt == "f32":
+        return x
+    raise ValueError(fmt)

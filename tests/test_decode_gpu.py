@@ -149,3 +149,39 @@ def test_decode_vs_reference_avx_build(capi):
             pcm, status, _ = ctx.decode_streams([g["data"]], nb, fmt="f32")
         assert status[0] == -1
         assert peak_rel_err(pcm[0], ref) < {2048: 1.5e-5, 4096: 3e-5, 8192: 8e-5}[g["block_size"]], name
+
+
+def test_fast_and_generic_kernels_agree(tmp_path):
+    """BlockSize 2048 stereo takes the warp-specialised kernel (csrc/ulcb_decode_ws.cu); every other shape, and
+    ULCB_DECODE_GENERIC=1, takes the generic one (csrc/ulcb_decode.cu).  Same bytes in -> same parse (bits per block
+    identical) and the same PCM up to the two FFT factorisations' rounding."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from ulc_codec_b200 import capi\n"
+        "from tests.fixtures import load_golden_stream\n"
+        "out = {}\n"
+        "for name in ('transient_vbr50_bs2048', 'music_vbr75_bs2048'):\n"
+        "    g = load_golden_stream(name); nb = len(g['block_bytes'])\n"
+        "    with capi.Context(44100, 2, 2048, max_blocks=nb) as ctx:\n"
+        "        f, st, bits = ctx.decode_streams([g['data']], nb, fmt='f32', want_bits=True)\n"
+        "        p, _, _ = ctx.decode_streams([g['data']], nb, fmt='pcm16')\n"
+        "    assert st[0] == -1\n"
+        "    out[name + '_f'] = f[0]; out[name + '_p'] = p[0]; out[name + '_b'] = bits[0]\n"
+        "np.savez(sys.argv[1], **out)\n" % root)
+    res = {}
+    for tag, env in (("fast", {}), ("generic", {"ULCB_DECODE_GENERIC": "1"})):
+        path = str(tmp_path / (tag + ".npz"))
+        subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, **env}, cwd=root)
+        res[tag] = np.load(path)
+    for k in res["fast"].files:
+        a, b = res["fast"][k], res["generic"][k]
+        if k.endswith("_b"):
+            assert np.array_equal(a, b), k
+        elif k.endswith("_p"):
+            assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= 1, k
+        else:
+            assert peak_rel_err(a, b) < 2e-6, (k, peak_rel_err(a, b))

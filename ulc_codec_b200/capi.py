@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libulcb200.so")
 
 FMT_PCM16, FMT_FLOAT32 = 0, 1
-_FMT = {"pcm16": FMT_PCM16, "s16": FMT_PCM16, "f32": FMT_FLOAT32, "float32": FMT_FLOAT32}
+FMT_PCM8U, FMT_PCM24 = 2, 3
+_FMT = {"pcm16": FMT_PCM16, "s16": FMT_PCM16, "f32": FMT_FLOAT32, "float32": FMT_FLOAT32, "pcm8u": FMT_PCM8U, "pcm24": FMT_PCM24}
 
 # every symbol include/ulcb200.h declares (tests/test_capi_symbols.py checks the header against this)
 EXPORTS = (
@@ -25,7 +26,7 @@ EXPORTS = (
     "ULCB_LaunchCount", "ULCB_TestDCT4", "ULCB_TestParse",
     "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
     "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
-    "ULCB_GenerateCorpusDevice",
+    "ULCB_GenerateCorpusDevice", "ULCB_ConvertSamplesDevice",
 )
 
 MODE_VBR, MODE_CBR, MODE_ABR = 0, 1, 2
@@ -96,6 +97,7 @@ def load():
     L.ULCB_EncodeStreams.argtypes = [vp, i32, vp, i32, vp, u64, u32, pp, vp, u64, vp, vp, vp, vp, vp]
     L.ULCB_TestEncode.argtypes = [vp, i32, vp, i32, vp, u64, u32, pp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ULCB_GenerateCorpusDevice.argtypes = [vp, i32, u32, i32, u64, u64, vp, vp, vp, u64]
+    L.ULCB_ConvertSamplesDevice.argtypes = [vp, i32, i32, vp, vp, u64]
     es = C.POINTER(ULC_EncoderState_t)
     L.ULC_EncoderState_Init.argtypes = [es]
     L.ULC_EncoderState_Destroy.argtypes = [es]
@@ -255,6 +257,12 @@ class Context:
         rc = self.L.ULCB_GenerateCorpusDevice(self.h, corpus._KINDS[kind], first_id, n_streams, n_samples, t0,
                                               sine.ctypes.data, burst.ctypes.data, d_out, stride_elems)
         _check(self.L, self.h, rc, "ULCB_GenerateCorpusDevice")
+
+    def convert_samples_device(self, fmt: str, to_float: bool, d_src: int, d_dst: int, n_samples: int):
+        """Device-side sample-format conversion with the reference's rules (tools/WavIO_Helper.c:31-87).
+        fmt in {"pcm8u", "pcm16", "pcm24", "f32"}; the other side is float32."""
+        rc = self.L.ULCB_ConvertSamplesDevice(self.h, _FMT[fmt], 1 if to_float else 0, d_src, d_dst, n_samples)
+        _check(self.L, self.h, rc, "ULCB_ConvertSamplesDevice")
 
     def test_parse(self, data: np.ndarray, n_blocks: int):
         """(coefs float32[nBlocks, nChan*N], bits uint32[nBlocks]) of one stream: parse + dequantise + noise only."""

@@ -14,6 +14,7 @@
 #include "ulcb_dct.cuh"
 #include "ulcb_decode.h"
 #include "ulcb_encode.h"
+#include "ulcb_pcm.h"
 
 cudaError_t ulcb_corpus_launch(int16_t *dOut, uint64_t strideElems, int kind, uint32_t firstId, int nStreams, uint64_t nSamples,
                                uint64_t t0, const int16_t *dSine, const int16_t *dBurst, cudaStream_t stream);
@@ -485,6 +486,16 @@ int ULC_DecodeBlock(struct ULC_DecoderState_t *State, float *DstData, const void
 // ------------------------------------------------------------------------------------------------
 // Synthetic corpus (measurement input) - device twin of ulc_codec_b200/corpus.py
 // ------------------------------------------------------------------------------------------------
+int ULCB_ConvertSamplesDevice(ULCB_Context *ctx, int format, int toFloat, const void *dSrc, void *dDst, uint64_t nSamples) {
+    if (!ctx || !dSrc || !dDst || format < 0 || format > ULCB_FMT_PCM24) return ULCB_E_PARAM;
+    if (nSamples == 0) return ULCB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (toFloat) CK(ctx, ulcb_pcm_to_float(static_cast<float *>(dDst), dSrc, (size_t)nSamples, format, ctx->smCount, ctx->stream));
+    else         CK(ctx, ulcb_pcm_from_float(dDst, static_cast<const float *>(dSrc), (size_t)nSamples, format, ctx->smCount, ctx->stream));
+    ctx->launches++;
+    return ULCB_OK;
+}
+
 int ULCB_GenerateCorpusDevice(ULCB_Context *ctx, int kind, uint32_t firstStreamId, int nStreams, uint64_t nSamples, uint64_t t0,
                               const int16_t *sineLut1024, const int16_t *burstLut882, int16_t *dOut, uint64_t strideElems) {
     if (!ctx || !dOut || !sineLut1024 || !burstLut882 || nStreams < 0 || (kind != 0 && kind != 1) || ctx->nChan != 2) return ULCB_E_PARAM;

@@ -290,37 +290,39 @@ struct Parser {
         int slot = nRuns + __popc(b1 & lt) + __popc(b2 & lt);
         nRuns += __popc(b1) + __popc(b2);
         if (emit) {
+            // Straight-line, predicated: one pass over the 8 nybble positions.  Values are assembled as bf16 bit patterns
+            // with integer arithmetic (exact small integer via the 2^23 trick, then the quantiser subtracted from the
+            // exponent field): coefficient = sign * v^2 * 2^-(5+q), noise amplitude = lv^2 * 2^-(7+q), zero when q > 26
+            // (ulcDecoder.c:96-98).
             int idx = idx0 + ec, draw = blkDraws + ed;
-            float scale = quant_scale(qIn);
+            int eb = qIn > 26 ? -1 : (5 + qIn) << 7;                               // bf16 exponent bias of the quantiser
             uint16_t *cf = sm.coef[c];
-            const uint32_t mine = starts & below, special = W.is0 | W.is1 | W.is8 | W.isF;
+            const uint32_t mine = starts & below, special = W.is0 | W.is1 | W.is8 | W.isF, qtok = W.isF & ~W.stop;
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 const uint32_t bit = 8u << (4 * o);
                 const bool tok = (mine & bit) != 0;
                 const uint32_t x = __funnelshift_r(W.w, W.nx, 4 * o);
                 const int v0 = x & 15, v1 = (x >> 4) & 15, v2 = (x >> 8) & 15, b12 = (v1 << 4) | v2;
-                if (tok && !(special & bit)) {                                     // coefficient: sign * v^2 * quantiser
-                    int v = (v0 ^ 8) - 8;
-                    v = v * abs(v);
-                    if (idx < N) cf[idx] = (uint16_t)(__float_as_uint((float)v * scale) >> 16);
-                }
+                const bool s8 = (W.is8 & bit) != 0;
+                const int sv = (v0 ^ 8) - 8;
+                const int m2 = s8 ? (int)(((x >> 13) & 7) + 1) * (int)(((x >> 13) & 7) + 1) : sv * sv;   // lv^2 or v^2, 1..64
+                const uint32_t fb = __float_as_uint(__uint_as_float(0x4B000000u | (uint32_t)m2) - 8388608.0f) >> 16;
+                const uint32_t val = eb < 0 ? 0u : (fb - (uint32_t)eb - (s8 ? 0x100u : 0u)) | ((uint32_t)(v0 & 8 & (s8 ? 0 : 8)) << 12);
                 int n = (special & bit) ? 0 : 1;
-                if (W.is0 & bit) n = v1 + 1;
-                if (W.is1 & bit) n = b12 + 33;
-                if (W.is8 & bit) n = ((b12 << 1) | ((x >> 12) & 1)) + 16;
-                if (tok && (W.is8 & bit)) {                                        // noise run: one record, filled by the transform warp
-                    const int lv = (int)((x >> 13) & 7) + 1;                       // (X>>1)+1, X = 4th nybble
-                    const float amp = (float)(lv * lv) * scale * 0.25f;
-                    if (slot < MAXRUNS && idx + n <= N) {
-                        Run r; r.a = (uint32_t)idx | ((uint32_t)n << 12);
-                        r.b = (uint32_t)draw | (__float_as_uint(amp) & 0xffff0000u);
-                        sm.runs[c][slot] = r;
-                    }
-                    slot++; draw += n;
+                n = (W.is0 & bit) ? v1 + 1 : n;
+                n = (W.is1 & bit) ? b12 + 33 : n;
+                n = s8 ? ((b12 << 1) | (int)((x >> 12) & 1)) + 16 : n;
+                if (tok && !(special & bit) && idx < N) cf[idx] = (uint16_t)val;   // coefficient
+                if (tok && s8 && slot < MAXRUNS && idx + n <= N) {                 // noise run: one record, filled by the transform warp
+                    Run r; r.a = (uint32_t)idx | ((uint32_t)n << 12); r.b = (uint32_t)draw | (val << 16);
+                    sm.runs[c][slot] = r;
                 }
-                if (tok && (W.isF & ~W.stop & bit)) scale = quant_scale(v1 < 14 ? v1 : 14 + v2);
-                if (tok) idx += n;
+                const bool nz = tok && s8;
+                slot += nz ? 1 : 0; draw += nz ? n : 0;
+                const int nq = v1 < 14 ? v1 : 14 + v2;
+                eb = (tok && (qtok & bit)) ? (nq > 26 ? -1 : (5 + nq) << 7) : eb;
+                idx += tok ? n : 0;
             }
         }
         CTK(6);
