@@ -69,6 +69,7 @@ struct EncSmall {
     int     tailLen[MAXU];
     uint32_t tailTok[MAXU];
     int     passTotal;
+    int     selBin, selBelow;        // radix-select hand-off
     int     scan[40];
     float   band[MAXBU][ULCB_NBARK];
     double  lo[MAXBU][ULCB_NBARK][3];
@@ -686,7 +687,7 @@ struct Encoder {
                 if (lane == 0 && !(args.dbgFlags & 1)) {
                     float sq = 0.0f, ab = 0.0f;
                     const float4 *x4 = reinterpret_cast<const float4 *>(w.XA);
-#pragma unroll 2
+#pragma unroll 8
                     for (int i = 0; i < (CN >> 2); i++) {
                         float4 r = x4[i];
                         float a0 = r.x * r.x, a1 = r.y * r.y, a2 = r.z * r.z, a3 = r.w * r.w;
@@ -791,6 +792,70 @@ struct Encoder {
         const uint16_t *ord = reinterpret_cast<const uint16_t *>(w.XB);
         wsync<NTHR>();
         for (int r = tid; r < CN; r += NTHR) rank[ord[r]] = (uint16_t)r;
+        wsync<NTHR>();
+    }
+
+    // VBR needs only the predicate "rank < nOut" (encode_pass, :236-268 of ulcEncoder_Encode.c scan coefficients whose
+    // TransformIndex is below the cut), and nOut is known before the ranks are: an MSB-first radix SELECT of the nOut-th
+    // key (4 histogram passes of 8 bits, no scatter) replaces the 8-pass sort.  Keys equal to the threshold are taken in
+    // index order, which is the order the stable sort gives them.  Writes rank = 0 (kept) / 0xFFFF (dropped).
+    static constexpr int MAXE = 16;
+    __device__ bool can_select() const { return CN / NTHR <= MAXE; }
+    __device__ void rank_select(int nOut) {
+        const uint32_t *uk = reinterpret_cast<const uint32_t *>(w.TA);
+        const int E = CN / NTHR, i0 = tid * E;
+        uint32_t key[MAXE];
+#pragma unroll
+        for (int e = 0; e < MAXE; e++) key[e] = e < E ? uk[i0 + e] : 0xffffffffu;
+        int *hist = reinterpret_cast<int *>(w.cnt);                     // 256 bins
+        uint32_t prefix = 0, pmask = 0;
+        int need = nOut;                                                 // keys still to take among those matching the prefix
+        if (nOut > 0) {
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                if (tid < 256) hist[tid] = 0;
+                wsync<NTHR>();
+#pragma unroll
+                for (int e = 0; e < MAXE; e++)
+                    if (e < E && (key[e] & pmask) == prefix) atomicAdd(&hist[(key[e] >> shift) & 255], 1);
+                wsync<NTHR>();
+                if (tid < 32) {
+                    int c[8], s = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { c[q] = hist[tid * 8 + q]; s += c[q]; }
+                    int inc = s;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (tid >= d) inc += t; }
+                    const int exc = inc - s;
+                    if (exc < need && need <= inc) {                     // exactly one lane: the bin that holds the need-th key
+                        int run = exc, bin = tid * 8 + 7;
+                        for (int q = 0; q < 8; q++) { if (need <= run + c[q]) { bin = tid * 8 + q; break; } run += c[q]; }
+                        sm.selBin = bin; sm.selBelow = run;
+                    }
+                }
+                wsync<NTHR>();
+                need -= sm.selBelow;
+                prefix |= (uint32_t)sm.selBin << shift;
+                pmask |= 0xffu << shift;
+            }
+        }
+        // prefix = the nOut-th smallest key; `need` of the keys equal to it are kept, first in index order
+        int eq = 0;
+#pragma unroll
+        for (int e = 0; e < MAXE; e++) eq += (e < E && key[e] == prefix) ? 1 : 0;
+        int tot, base = block_excl_sum<NTHR>(eq, sm.scan, tot);
+        wsync<NTHR>();                                                   // every key is in registers: TA may be overwritten
+        uint16_t *rank = reinterpret_cast<uint16_t *>(w.TA);
+#pragma unroll
+        for (int e = 0; e < MAXE; e++) {
+            if (e < E) {
+                bool keep = false;
+                if (nOut > 0) {
+                    if (key[e] < prefix) keep = true;
+                    else if (key[e] == prefix) { keep = base < need; base++; }
+                }
+                rank[i0 + e] = keep ? (uint16_t)0 : (uint16_t)0xFFFF;
+            }
+        }
         wsync<NTHR>();
     }
 
@@ -1185,20 +1250,21 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
             if (args.dbgMask) for (int i = tid; i < H; i += NTHR) args.dbgMask[dbgBlk * H + i] = wk.mask[i];
             enc.make_keys(args.dbgKeys ? args.dbgKeys + dbgBlk * CN : nullptr);
             wsync<NTHR>();
-            enc.rank_sort();
-            TICK(7);
-            if (args.dbgRanks) for (int i = tid; i < CN; i += NTHR) args.dbgRanks[dbgBlk * CN + i] = reinterpret_cast<const uint16_t *>(wk.TA)[i];
-
             // ---- rate control (libulc/ulcEncoder.c:93-158) ----
             const int maxCoef = sm.nNz;
             const float cx = sm.cx;
-            int size, nOutUsed;
+            int size, nOutUsed, nOutVbr = maxCoef;
+            if (args.mode == ULCB_ENC_VBR && args.param > 0.0f) {
+                float f = (float)(NCH * N) * cx / args.param;
+                if (f < (float)maxCoef) nOutVbr = (int)f;
+            }
+            if (args.mode == ULCB_ENC_VBR && !args.dbgRanks && enc.can_select()) enc.rank_select(nOutVbr);
+            else enc.rank_sort();
+            TICK(7);
+            if (args.dbgRanks) for (int i = tid; i < CN; i += NTHR) args.dbgRanks[dbgBlk * CN + i] = reinterpret_cast<const uint16_t *>(wk.TA)[i];
+
             if (args.mode == ULCB_ENC_VBR) {
-                int nOut = maxCoef;
-                if (args.param > 0.0f) {
-                    float f = (float)(NCH * N) * cx / args.param;
-                    if (f < (float)maxCoef) nOut = (int)f;
-                }
+                const int nOut = nOutVbr;
                 nOutUsed = nOut;
                 size = enc.encode_pass(k, nOut, true);
             } else {
