@@ -1009,124 +1009,132 @@ struct Encoder {
 template <int NCH>
 struct Detector {
     const UlcbEncodeArgs &args;
-    float2 *E;                    // [N] private scratch
+    float2 *E;                    // [3][N] private scratch: the block buffers of the three pipelined passes
     float *stg;                   // [NCH][N+2] analysis window, M/S
     float *seg;                   // [32] {sum,cnt} x 16 (shared memory)
     float env[3];
     const unsigned char *pcm; long long nSamples; const float *prevBlk;   // prevBlk: block before this call (M/S planar) or nullptr
 
-    __device__ int decide(int b) {
+    // One iteration of the software-pipelined detector.  The three envelope passes of a block depend on each other
+    // (post-mask forwards -> pre-mask backwards from the post-mask end value -> block-mask forwards), but the passes of
+    // DIFFERENT blocks do not: iteration `it` runs post(it), pre(it-1) and blk(it-2) as three independent dependency
+    // chains in ONE loop on lane 0, so the recurrences' add/mul latencies overlap instead of adding up.  Each pass keeps
+    // the reference's operation order, so the decisions are unchanged.  E holds three block buffers that rotate through
+    // the roles post (in place) -> pre (in place) -> blk (read).  Returns the decision for block it-2 (it >= 2).
+    float preHp = 0.0f, preBp = 0.0f;          // post-mask end values of the block whose pre-mask pass comes next
+    __device__ int iterate(int it, int nBlocks) {
         const int N = args.tb.N, H = N >> 1, lane = threadIdx.x & 31, W = N + 2;
         const UlcbEncTables &tb = args.tb;
-        // stage the window: samples (b-1)*N + H - 1 .. b*N + H of the call's timeline
-        const long long sBeg = (long long)(b - 1) * N + H - 1;
+        const bool doPost = it < nBlocks, doPre = it >= 1 && it - 1 < nBlocks, doBlk = it >= 2;
+        float2 *P = E + (size_t)(it % 3) * N, *Q = E + (size_t)((it + 2) % 3) * N, *R = E + (size_t)((it + 1) % 3) * N;
+        const int b = it;
 #ifdef ULCB_PHASE_TIMING
         long long dt0 = clock64();
 #define DTICK(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_ulcbPhase[i], (unsigned long long)(t_ - dt0)); dt0 = t_; } } while (0)
 #else
 #define DTICK(i) do { } while (0)
 #endif
-        int i0 = 0;
-        if (sBeg < 0) {                                               // reaches back into the block before this call
-            i0 = (-sBeg < (long long)W) ? (int)(-sBeg) : W;
-            for (int i = lane; i < i0; i += 32)
+        if (doPost) {
+            // stage the window: samples (b-1)*N + H - 1 .. b*N + H of the call's timeline
+            const long long sBeg = (long long)(b - 1) * N + H - 1;
+            int i0 = 0;
+            if (sBeg < 0) {                                               // reaches back into the block before this call
+                i0 = (-sBeg < (long long)W) ? (int)(-sBeg) : W;
+                for (int i = lane; i < i0; i += 32)
 #pragma unroll
-                for (int c = 0; c < NCH; c++) stg[c * W + i] = prevBlk ? prevBlk[c * N + (int)(N + sBeg + i)] : 0.0f;
-        }
-        if (nSamples > 0) {
+                    for (int c = 0; c < NCH; c++) stg[c * W + i] = prevBlk ? prevBlk[c * N + (int)(N + sBeg + i)] : 0.0f;
+            }
+            if (nSamples > 0) {
+                for (int ib = i0 + lane; ib < W; ib += 256) {             // 8 independent loads in flight per lane
+                    float v[8][NCH]; bool ok[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = ib + 32 * u;
+                        const long long sv = sBeg + i;
+                        ok[u] = i < W && sv < nSamples;
+                        const size_t sc = ok[u] ? (size_t)sv : 0;
+#pragma unroll
+                        for (int q = 0; q < NCH; q++)
+                            v[u][q] = args.pcmFloat ? reinterpret_cast<const float *>(pcm)[sc * NCH + q]
+                                                    : (float)reinterpret_cast<const int16_t *>(pcm)[sc * NCH + q] * 0x1.0p-15f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = ib + 32 * u;
+#pragma unroll
+                        for (int c = 1; c < NCH; c += 2) { float a = v[u][c - 1], bb = v[u][c]; v[u][c - 1] = (a + bb) * 0.5f; v[u][c] = (a - bb) * 0.5f; }
+                        if (i < W)
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) stg[c * W + i] = ok[u] ? v[u][c] : 0.0f;
+                    }
+                }
+            } else {
+                for (int i = i0 + lane; i < W; i += 32)
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) stg[c * W + i] = 0.0f;
+            }
+            __syncwarp();
+            DTICK(16);
 #pragma unroll 4
-            for (int i = i0 + lane; i < W; i += 32) {
-                const long long sv = sBeg + i;
-                const bool ok = sv < nSamples;
-                const size_t sc = ok ? (size_t)sv : 0;
-                float v[NCH];
+            for (int n = lane; n < N; n += 32) {
+                float ehp = 0.0f, ebp = 0.0f;
 #pragma unroll
-                for (int q = 0; q < NCH; q++)
-                    v[q] = args.pcmFloat ? reinterpret_cast<const float *>(pcm)[sc * NCH + q]
-                                         : (float)reinterpret_cast<const int16_t *>(pcm)[sc * NCH + q] * 0x1.0p-15f;
-#pragma unroll
-                for (int c = 1; c < NCH; c += 2) { float a = v[c - 1], bb = v[c]; v[c - 1] = (a + bb) * 0.5f; v[c] = (a - bb) * 0.5f; }
-#pragma unroll
-                for (int c = 0; c < NCH; c++) stg[c * W + i] = ok ? v[c] : 0.0f;
+                for (int c = 0; c < NCH; c++) {
+                    float t0 = stg[c * W + n], t1 = stg[c * W + n + 1], t2 = stg[c * W + n + 2];
+                    float hp = (-t0 + 2.0f * t1) - t2, bp = -t0 + t2;
+                    ehp += hp * hp; ebp += bp * bp;
+                }
+                P[n] = make_float2(sqrtf(ehp), sqrtf(ebp));
             }
-        } else {
-            for (int i = i0 + lane; i < W; i += 32)
-#pragma unroll
-                for (int c = 0; c < NCH; c++) stg[c * W + i] = 0.0f;
-        }
-        __syncwarp();
-        DTICK(16);
-#pragma unroll 2
-        for (int n = lane; n < N; n += 32) {
-            float ehp = 0.0f, ebp = 0.0f;
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                float t0 = stg[c * W + n], t1 = stg[c * W + n + 1], t2 = stg[c * W + n + 2];
-                float hp = (-t0 + 2.0f * t1) - t2, bp = -t0 + t2;
-                ehp += hp * hp; ebp += bp * bp;
-            }
-            E[n] = make_float2(sqrtf(ehp), sqrtf(ebp));
         }
         __syncwarp();
         DTICK(17);
+        // The five one-pole chains are the same three instructions (d = x - s; s += d * c) on different data, so they
+        // run SIMD across lanes: lane 0/1 = post-mask HP/BP of block it (forwards, envelope written back in place),
+        // lane 2/3 = pre-mask HP/BP of block it-1 (backwards; their cross products give the error energy, which lane 2
+        // writes over the HP slot), lane 4 = block-mask of block it-2 (forwards) and its running segment sum.
         int decision = 0;
-        if (lane == 0) {
-            float4 *E4 = reinterpret_cast<float4 *>(E);
-            // The loads of the next 8 samples are issued before the current 8 are processed, so the only latency
-            // left in these loops is the recurrence itself (sub, mul, add per sample).
-            const int nq = N >> 3;                                   // groups of 4 float4 = 8 samples
-            float php = env[0], pbp = env[1];
-            const float a1 = tb.c1PostHp, a2 = tb.c1PostBp;
-            {
-                float4 nx0 = E4[0], nx1 = E4[1], nx2 = E4[2], nx3 = E4[3];
-                for (int g = 0; g < nq; g++) {                        // post-masking envelopes (:73-88)
-                    float4 c0 = nx0, c1 = nx1, c2 = nx2, c3 = nx3;
-                    if (g + 1 < nq) { nx0 = E4[4 * g + 4]; nx1 = E4[4 * g + 5]; nx2 = E4[4 * g + 6]; nx3 = E4[4 * g + 7]; }
-#define POST2(e) { float dh = e.x - php, db = e.y - pbp; php += dh * a1; pbp += db * a2; e.x = php; e.y = pbp; \
-                   dh = e.z - php; db = e.w - pbp; php += dh * a1; pbp += db * a2; e.z = php; e.w = pbp; }
-                    POST2(c0) POST2(c1) POST2(c2) POST2(c3)
-#undef POST2
-                    E4[4 * g] = c0; E4[4 * g + 1] = c1; E4[4 * g + 2] = c2; E4[4 * g + 3] = c3;
-                }
-            }
-            env[0] = php; env[1] = pbp;
-            DTICK(18);
-            float qhp = php, qbp = pbp;
-            const float b1 = tb.c1PreHp, b2 = tb.c1PreBp;
-            {
-                float4 nx0 = E4[4 * nq - 4], nx1 = E4[4 * nq - 3], nx2 = E4[4 * nq - 2], nx3 = E4[4 * nq - 1];
-                for (int g = nq - 1; g >= 0; g--) {                   // pre-masking, backwards (:92-104)
-                    float4 c0 = nx0, c1 = nx1, c2 = nx2, c3 = nx3;
-                    if (g > 0) { nx0 = E4[4 * g - 4]; nx1 = E4[4 * g - 3]; nx2 = E4[4 * g - 2]; nx3 = E4[4 * g - 1]; }
-#define PRE2(e) { float dh = e.z - qhp, db = e.w - qbp; qhp += dh * b1; qbp += db * b2; float a = dh * qbp, bb = db * qhp; e.z = a * a + bb * bb; \
-                  dh = e.x - qhp; db = e.y - qbp; qhp += dh * b1; qbp += db * b2; a = dh * qbp; bb = db * qhp; e.x = a * a + bb * bb; }
-                    PRE2(c3) PRE2(c2) PRE2(c1) PRE2(c0)
-#undef PRE2
-                    E4[4 * g] = c0; E4[4 * g + 1] = c1; E4[4 * g + 2] = c2; E4[4 * g + 3] = c3;
-                }
-            }
-            DTICK(19);
+        {
+            const bool isPost = lane < 2, isPre = lane == 2 || lane == 3, isBlk = lane == 4;
+            float *base = reinterpret_cast<float *>(isPost ? P : isPre ? Q : R);
+            const int comp = isBlk ? 0 : (lane & 1);                       // .x (HP / energy) or .y (BP)
+            const int dir = isPre ? -1 : 1;
+            float *ptr = base + comp + (isPre ? 2 * (N - 1) : 0);
+            const float c = lane == 0 ? tb.c1PostHp : lane == 1 ? tb.c1PostBp : lane == 2 ? tb.c1PreHp : lane == 3 ? tb.c1PreBp : tb.c1Blk;
+            float st = lane == 0 ? env[0] : lane == 1 ? env[1] : lane == 2 ? preHp : lane == 3 ? preBp : env[2];
+            const bool store = (isPost && doPost) || (lane == 2 && doPre);
             const int bin = N >> 3;
-            const float cb = tb.c1Blk;
-            float m = env[2];
-            for (int s = 0; s < 8; s++) {                            // block-mask envelope into 8 segment sums (:107-134)
-                seg[2 * s] = seg[16 + 2 * s]; seg[2 * s + 1] = seg[16 + 2 * s + 1];
-                float acc = 0.0f, cnt = 0.0f;
-                const float4 *S4 = E4 + ((s * bin) >> 1);
-                const int ng = bin >> 3;                              // bin >= 32
-                float4 nx0 = S4[0], nx1 = S4[1], nx2 = S4[2], nx3 = S4[3];
-                for (int g = 0; g < ng; g++) {
-                    float4 c0 = nx0, c1 = nx1, c2 = nx2, c3 = nx3;
-                    if (g + 1 < ng) { nx0 = S4[4 * g + 4]; nx1 = S4[4 * g + 5]; nx2 = S4[4 * g + 6]; nx3 = S4[4 * g + 7]; }
-#define BLK2(e) { float d = e.x - m; m += d * cb; acc += m; cnt += 1.0f; d = e.z - m; m += d * cb; acc += m; cnt += 1.0f; }
-                    BLK2(c0) BLK2(c1) BLK2(c2) BLK2(c3)
-#undef BLK2
+            for (int sg = 0; sg < 8; sg++) {
+                float acc = 0.0f;
+                for (int n0 = 0; n0 < bin; n0 += 8) {                    // bin >= 32
+                    float xs[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) xs[q] = ptr[2 * dir * q];   // every slot is read before it is overwritten
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float d = xs[q] - st;
+                        st += d * c;
+                        const float ps = __shfl_xor_sync(0xffffffffu, st, 1);   // the other band's updated envelope
+                        const float pr = d * ps;
+                        const float sq = pr * pr;
+                        const float e = sq + __shfl_xor_sync(0xffffffffu, sq, 1);   // (dh*qbp)^2 + (db*qhp)^2 on lane 2
+                        if (store) ptr[2 * dir * q] = isPost ? st : e;
+                        acc += st;
+                    }
+                    ptr += 16 * dir;
                 }
-                seg[16 + 2 * s] = acc; seg[16 + 2 * s + 1] = cnt;
+                if (isBlk && doBlk) {
+                    seg[2 * sg] = seg[16 + 2 * sg]; seg[2 * sg + 1] = seg[16 + 2 * sg + 1];
+                    seg[16 + 2 * sg] = acc; seg[16 + 2 * sg + 1] = (float)bin;   // the count is one 1.0f per sample (:126)
+                }
             }
-            env[2] = m;
-            DTICK(20);
-            decision = window_decide(seg, tb.log2N);
+            // carry the envelope states
+            const float s0 = __shfl_sync(0xffffffffu, st, 0), s1 = __shfl_sync(0xffffffffu, st, 1), s4 = __shfl_sync(0xffffffffu, st, 4);
+            if (doPost) { env[0] = s0; env[1] = s1; preHp = s0; preBp = s1; }
+            if (doBlk) env[2] = s4;
+            __syncwarp();
+            DTICK(18);
+            if (doBlk && lane == 0) decision = window_decide(seg, tb.log2N);
             DTICK(21);
         }
         return __shfl_sync(0xffffffffu, decision, 0);
@@ -1147,9 +1155,10 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
         wk.cnt = reinterpret_cast<uint16_t *>(p); p += 32 * NTHR;
         wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
         wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H;
-        detE = reinterpret_cast<float2 *>(p); p += sizeof(float2) * N;
+        if (!GWS) { detE = reinterpret_cast<float2 *>(p); p += sizeof(float2) * N * 3; }
         detStage = reinterpret_cast<float *>(p); p += sizeof(float) * NCH * (N + 4);
         float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
+        if (GWS) detE = reinterpret_cast<float2 *>(big + 8 * CN + 64);
         wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
         wk.encScratch = GWS ? reinterpret_cast<uint8_t *>(big + 7 * CN) : reinterpret_cast<uint8_t *>(wk.cnt);
     }
@@ -1169,24 +1178,24 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
             const int lane = tid & 31;
             Detector<NCH> det{args, detE, detStage, sm.seg, {0.0f, 0.0f, 0.0f}, pcm, nSamples,
                               resume ? args.stateSamples + (size_t)stream * 2 * CN + CN : nullptr};
-            if (lane == 0) {
+            if (lane == 0)
                 for (int i = 0; i < 16; i++) { sm.seg[i] = 0.0f; sm.seg[16 + i] = resume ? st->seg[i] : 0.0f; }
-                if (resume) for (int i = 0; i < 3; i++) det.env[i] = st->env[i];
-            }
+            if (resume) for (int i = 0; i < 3; i++) det.env[i] = st->env[i];      // every lane: the chains run SIMD across lanes
             __syncwarp();
 #ifdef ULCB_PHASE_TIMING
             long long detAcc = 0, detWait = 0;
 #endif
-            for (int b = 0; b < nBlocks; b++) {
+            for (int it = 0; it < nBlocks + 2; it++) {
 #ifdef ULCB_PHASE_TIMING
                 long long t0 = clock64();
 #endif
-                const int d = det.decide(b);
-                if (lane == 0) sm.wcRing[b & 1] = d;
+                const int d = det.iterate(it, nBlocks);               // decision of block it-2
+                if (it < 2) continue;
+                if (lane == 0) sm.wcRing[(it - 2) & 1] = d;
 #ifdef ULCB_PHASE_TIMING
                 long long t1 = clock64(); detAcc += t1 - t0;
 #endif
-                fsync<NTHR>();                                        // publish decision b; workers start block b
+                fsync<NTHR>();                                        // publish decision it-2; workers start that block
 #ifdef ULCB_PHASE_TIMING
                 detWait += clock64() - t1;
 #endif
@@ -1338,9 +1347,9 @@ extern "C" int ULCB_DebugPhaseTimes(unsigned long long *out13) {
 
 bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4096; }
 int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }
-size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)8 * nChan * N + 64; }
+size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)8 * nChan * N + 64 + (size_t)6 * N; }   // + the detector's 3 block buffers
 size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs) {
-    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + sizeof(float2) * N + sizeof(float) * nChan * (N + 4);
+    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * nChan * (N + 4);
     if (!globalWs) s += sizeof(float) * ((size_t)7 * nChan * N + 64);
     return s + 16;
 }
