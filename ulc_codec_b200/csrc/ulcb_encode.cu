@@ -1034,6 +1034,14 @@ struct Detector {
 #else
 #define DTICK(i) do { } while (0)
 #endif
+        if (it + 1 < nBlocks && nSamples > 0) {
+            // the next iteration's window comes straight from HBM: ask for its lines now, a whole iteration early
+            const size_t elem = args.pcmFloat ? 4 : 2;
+            const long long s0 = (long long)b * N + H - 1;
+            const long long lo = s0 < 0 ? 0 : s0, hi = (s0 + W < nSamples ? s0 + W : nSamples);
+            for (long long o = lo * NCH * (long long)elem + 128ll * lane; o < hi * NCH * (long long)elem; o += 128 * 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pcm + o));
+        }
         if (doPost) {
             // stage the window: samples (b-1)*N + H - 1 .. b*N + H of the call's timeline
             const long long sBeg = (long long)(b - 1) * N + H - 1;
