@@ -74,6 +74,7 @@ struct Smem {
     float2   zbuf[2][32 * ZROW];  // per transform warp: FFT work buffer / short-block work buffer / output swap
     Run      runs[2][MAXRUNS];
     Meta     meta[2];
+    uint32_t wring[4][36];        // parse warp: 33-word stream windows in flight (cp.async), ring of 4
 };
 
 __device__ __forceinline__ float quant_scale(int q) {      // ulcDecoder.c:96-98
@@ -139,7 +140,7 @@ struct Parser {
     const int lane;
     Win W;
     long long curW = -1;           // word index of the window start (multiple of 32)
-    uint32_t pw = 0, pnx = 0;      // prefetched words of the next window
+    long long reqUpTo = -100;      // last window index requested
     bool digested = false;
 #ifdef ULCB_PHASE_TIMING
     long long cacc[10] = {0}, ct = 0;
@@ -148,20 +149,41 @@ struct Parser {
 #define CTK(i) do { } while (0)
 #endif
 
-    __device__ Parser(Smem &s, const StreamSrc &r, int l) : sm(s), src(r), lane(l) {}
+    __device__ Parser(Smem &s, const StreamSrc &r, int l) : sm(s), src(r), lane(l) {
+        asm volatile("cp.async.wait_all;" ::: "memory");               // the previous stream's look-ahead windows
+        __syncwarp();
+    }
 
-    // Make the 256-nybble window that holds `pos` current.  The words of the following window are requested at the
-    // same time (a stream is read front to back), so its latency is hidden behind this window's parse.
+    // Make the 256-nybble window that holds `pos` current.  Windows are copied global -> shared memory with cp.async,
+    // three ahead of the parse (a stream is read front to back), so the HBM/L2 latency of a window is hidden behind
+    // the parse of the two before it and costs no registers.
+    __device__ __forceinline__ void request(long long wi) {              // 33 words of window wi -> ring slot wi & 3
+        const long long g = wi * 32 + lane;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.wring[wi & 3][lane]);
+        const bool ok = g < src.nWordsValid;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src.abase + (ok ? g : 0)), "r"(ok ? 4 : 0) : "memory");
+        if (lane == 0) {
+            const bool ok2 = g + 32 < src.nWordsValid;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128u), "l"(src.abase + (ok2 ? g + 32 : 0)), "r"(ok2 ? 4 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     __device__ __forceinline__ void ensure(long long pos) {
         const long long wb = (pos >> 3) & ~31ll;
         if (wb != curW) {
-            if (wb == curW + 32 && curW >= 0) { W.w = pw; W.nx = pnx; }
-            else { W.w = fetch(wb + lane); W.nx = fetch(wb + lane + 1); }
+            const long long wi = wb >> 5;
+            if (wi > reqUpTo + 1 || wi + 3 <= reqUpTo) reqUpTo = wi - 1;   // not a step forward: start over from this window
+            while (reqUpTo < wi + 2) request(++reqUpTo);
+            const int ahead = (int)(reqUpTo - wi);                         // groups issued after this window's
+            if (ahead >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else if (ahead == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            W.w = sm.wring[wi & 3][lane]; W.nx = sm.wring[wi & 3][lane + 1];
+            __syncwarp();
             curW = wb; digested = false;
-            pw = fetch(wb + 32 + lane); pnx = fetch(wb + 33 + lane);
         }
     }
-    __device__ __forceinline__ uint32_t fetch(long long g) const { return g < src.nWordsValid ? __ldcs(src.abase + g) : 0u; }
     __device__ __forceinline__ int read_nyb(long long pos) {
         ensure(pos);
         const int rel = (int)(pos - curW * 8);
