@@ -142,6 +142,7 @@ struct Parser {
     long long curW = -1;           // word index of the window start (multiple of 32)
     long long reqUpTo = -100;      // last window index requested
     bool digested = false;
+    bool emptyPending = false;     // the EMPTY hand-off of the previous block has not been waited for yet
 #ifdef ULCB_PHASE_TIMING
     long long cacc[10] = {0}, ct = 0;
 #define CTK(i) do { long long t_ = clock64(); cacc[i] += t_ - ct; ct = t_; } while (0)
@@ -303,6 +304,7 @@ struct Parser {
 
         CTK(5);
         // ---- emit ----
+        if (emptyPending) { bar_sync(BAR_EMPTY, NTHR); emptyPending = false; }   // first write of this block: the transform warps must have loaded the last one
         const bool emit = on && lane <= endLane;
         const int lim = (lane == endLane) ? endP : 8;              // tokens starting before lim are mine
         const uint32_t below = lim >= 8 ? 0xffffffffu : ((1u << (4 * lim)) - 1u);
@@ -371,7 +373,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
 #endif
     for (int blk = 0; blk < nBlocks; blk++) {
         WTK(0);
-        if (blk > 0) bar_sync(BAR_EMPTY, NTHR);
+        P.emptyPending = blk > 0;                                        // waited for at the block's first write (Parser::chain) or its end
         WTK(1);
         Meta &mt = sm.meta[blk & 1];
         if (deadAt < 0 && pos >= src.endNyb) deadAt = blk;             // stream exhausted
@@ -379,7 +381,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
         int wc = 0x10;
         uint32_t rawBits = 0, blkDraws = 0;
         if (live) {
-            {   // clear both channels' coefficients
+            if (blk == 0) {   // clear both channels' coefficients once per stream; afterwards the transform warps clear what they load
                 uint4 *z = reinterpret_cast<uint4 *>(&sm.coef[0][0]);
 #pragma unroll
                 for (int i = 0; i < (int)(sizeof(sm.coef) / 16 / 32); i++) z[lane + 32 * i] = make_uint4(0, 0, 0, 0);
@@ -451,6 +453,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                 pos = (pos + 1) & ~1ll;                                   // blocks are byte aligned (ulcEncoder_Encode.c:357-358)
             }
         }
+        if (P.emptyPending) { bar_sync(BAR_EMPTY, NTHR); P.emptyPending = false; }   // block without a single token chain
         if (lane == 0) {
             mt.live = live; mt.wc = wc; mt.drawBase = drawBase;
             if (args.blockBits) args.blockBits[(size_t)stream * args.bitsStride + blk] = live ? rawBits : 0u;
@@ -625,12 +628,13 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
             {
                 // z[n] = (v[2n] + i v[N-1-2n]) E[n], n = lane + 32 j, stored at zb[j][lane]; v[N-1-2n] is the odd half of
                 // word 1023-n, which lane 31-lane holds at j' = 31-j
-                const uint32_t *cw = reinterpret_cast<const uint32_t *>(sm.coef[c]);
+                uint32_t *cw = reinterpret_cast<uint32_t *>(sm.coef[c]);
 #pragma unroll 2
                 for (int j = 0; j < 16; j++) {
                     const int ja = j, jb = 31 - j;
                     const int na = lane + 32 * ja, nb = lane + 32 * jb;
                     const uint32_t wa = cw[na], wb = cw[nb];
+                    cw[na] = 0u; cw[nb] = 0u;                             // leave the buffer clear for the parse warp's next block
                     float ea = __uint_as_float(wa << 16), oa = __uint_as_float(wa & 0xffff0000u);
                     float eb = __uint_as_float(wb << 16), ob = __uint_as_float(wb & 0xffff0000u);
                     if (nT) {
@@ -752,6 +756,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
                 const int sh = pat & 7, S = N >> sh, hS = S >> 1;
                 for (int i = lane; i < S; i += 32) {
                     float x = __uint_as_float((uint32_t)sm.coef[c][off + i] << 16);
+                    sm.coef[c][off + i] = 0;
                     if (nT) x *= tail_gain(mt, c, nT, off + i);
                     if (dbg) dbg[off + i] = x;
                     scr[i] = x;
