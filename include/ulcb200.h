@@ -160,12 +160,19 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams,
 int ULCB_Sync(ULCB_Context *ctx);
 
 /* ---- batched encode ---- */
-enum { ULCB_MODE_VBR = 0, ULCB_MODE_CBR = 1, ULCB_MODE_ABR = 2 };
+enum { ULCB_MODE_VBR = 0, ULCB_MODE_CBR = 1, ULCB_MODE_ABR = 2,
+       /* ABR whose AvgComplexity the library measures itself, per stream, in a first analysis pass on the device (window
+        * control + MDCT + BlockComplexity only) - what a user of tools/ulcEncodeTool.c does by hand: encode once, read
+        * "Avg complexity = %.5f" (:178-188), encode again with RateKbps,AvgComplexity (:41).  avgComplexity is ignored. */
+       ULCB_MODE_ABR_2PASS = 3 };
 typedef struct ULCB_EncodeParams {
 	int   mode;            /* ULCB_MODE_* */
 	float rate;            /* VBR: Quality (0,100]; CBR/ABR: RateKbps */
 	float avgComplexity;   /* ABR only (tools/ulcEncodeTool.c:42,158) */
 } ULCB_EncodeParams;
+
+/* The per-stream AvgComplexity values the last ULCB_MODE_ABR_2PASS call measured (synchronises the context's stream). */
+int ULCB_GetAvgComplexity(ULCB_Context *ctx, float *avgComplexity, int nStreams);
 
 /* Blocks the reference tool writes for a stream of nSamples sample points: ceil(n/BlockSize)+2
  * (coding delay + MDCT delay, tools/ulcEncodeTool.c:98). */

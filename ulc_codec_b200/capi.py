@@ -26,11 +26,12 @@ EXPORTS = (
     "ULCB_LaunchCount", "ULCB_TestDCT4", "ULCB_TestParse",
     "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
     "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
-    "ULCB_GenerateCorpusDevice", "ULCB_ConvertSamplesDevice",
+    "ULCB_GenerateCorpusDevice", "ULCB_ConvertSamplesDevice", "ULCB_GetAvgComplexity",
 )
 
 MODE_VBR, MODE_CBR, MODE_ABR = 0, 1, 2
-_MODE = {"vbr": MODE_VBR, "cbr": MODE_CBR, "abr": MODE_ABR}
+MODE_ABR_2PASS = 3
+_MODE = {"vbr": MODE_VBR, "cbr": MODE_CBR, "abr": MODE_ABR, "abr2": MODE_ABR_2PASS}
 
 
 class ULCB_EncodeParams(C.Structure):
@@ -98,6 +99,7 @@ def load():
     L.ULCB_TestEncode.argtypes = [vp, i32, vp, i32, vp, u64, u32, pp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ULCB_GenerateCorpusDevice.argtypes = [vp, i32, u32, i32, u64, u64, vp, vp, vp, u64]
     L.ULCB_ConvertSamplesDevice.argtypes = [vp, i32, i32, vp, vp, u64]
+    L.ULCB_GetAvgComplexity.argtypes = [vp, vp, i32]
     es = C.POINTER(ULC_EncoderState_t)
     L.ULC_EncoderState_Init.argtypes = [es]
     L.ULC_EncoderState_Destroy.argtypes = [es]
@@ -257,6 +259,12 @@ class Context:
         rc = self.L.ULCB_GenerateCorpusDevice(self.h, corpus._KINDS[kind], first_id, n_streams, n_samples, t0,
                                               sine.ctypes.data, burst.ctypes.data, d_out, stride_elems)
         _check(self.L, self.h, rc, "ULCB_GenerateCorpusDevice")
+
+    def avg_complexity(self, n_streams: int) -> np.ndarray:
+        """Per-stream AvgComplexity measured by the last mode="abr2" (two-pass ABR) call."""
+        out = np.zeros(n_streams, np.float32)
+        _check(self.L, self.h, self.L.ULCB_GetAvgComplexity(self.h, out.ctypes.data, n_streams), "ULCB_GetAvgComplexity")
+        return out
 
     def convert_samples_device(self, fmt: str, to_float: bool, d_src: int, d_dst: int, n_samples: int):
         """Device-side sample-format conversion with the reference's rules (tools/WavIO_Helper.c:31-87).

@@ -29,6 +29,8 @@ struct ULCB_Context {
     UlcbEncTables etb{};
     int smCount = 148;
     int16_t *corpusLut = nullptr;       // sine[1024] + burst[882]
+    float *dAvgCx = nullptr; int avgCap = 0, avgCount = 0;              // two-pass ABR: per-stream AvgComplexity
+    float *dCxScratch = nullptr; size_t cxScratchCap = 0;               // ... and the first pass's block complexities when the caller keeps none
     float *encWs = nullptr; size_t encWsFloats = 0; int encGrid = 0;   // global workspace for large block sizes
     std::vector<void *> owned;          // device allocations freed with the context
     // staging for the host-pointer entry points (grown on demand)
@@ -290,6 +292,8 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->dAux) cudaFree(ctx->dAux);
     if (ctx->encWs) cudaFree(ctx->encWs);
     if (ctx->corpusLut) cudaFree(ctx->corpusLut);
+    if (ctx->dAvgCx) cudaFree(ctx->dAvgCx);
+    if (ctx->dCxScratch) cudaFree(ctx->dCxScratch);
     delete ctx;
 }
 
@@ -526,7 +530,8 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
                          UlcbEncStreamState *state, float *stateSamples, const EncTaps *taps) {
     if (!ctx || nStreams < 0 || !dPcm || !dOut || !prm) return ULCB_E_PARAM;
     if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
-    if (prm->mode != ULCB_MODE_VBR && prm->mode != ULCB_MODE_CBR && prm->mode != ULCB_MODE_ABR) return ULCB_E_PARAM;
+    if (prm->mode != ULCB_MODE_VBR && prm->mode != ULCB_MODE_CBR && prm->mode != ULCB_MODE_ABR && prm->mode != ULCB_MODE_ABR_2PASS) return ULCB_E_PARAM;
+    if (prm->mode == ULCB_MODE_ABR_2PASS && (state || taps)) return ULCB_E_PARAM;     // whole streams only
     if (prm->mode == ULCB_MODE_VBR && !(prm->rate > 0.0f)) return ULCB_E_PARAM;
     if (prm->mode == ULCB_MODE_ABR && !(prm->avgComplexity > 0.0f)) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
@@ -561,8 +566,41 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
         }
         a.workspace = ctx->encWs; a.wsFloats = per;
     }
+    if (prm->mode == ULCB_MODE_ABR_2PASS) {
+        // pass 1: analysis only -> block complexities; mean per stream on the device; pass 2: ABR with the per-stream means
+        if (ctx->avgCap < nStreams) {
+            if (ctx->dAvgCx) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->dAvgCx); ctx->dAvgCx = nullptr; }
+            CK(ctx, cudaMalloc(&ctx->dAvgCx, sizeof(float) * (size_t)nStreams));
+            ctx->avgCap = nStreams;
+        }
+        float *cxBuf = dComplexity; uint64_t cxStride = metaStride;
+        if (!cxBuf) {
+            const size_t need = (size_t)nStreams * nBlocksAll;
+            if (ctx->cxScratchCap < need) {
+                if (ctx->dCxScratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->dCxScratch); ctx->dCxScratch = nullptr; }
+                CK(ctx, cudaMalloc(&ctx->dCxScratch, sizeof(float) * need));
+                ctx->cxScratchCap = need;
+            }
+            cxBuf = ctx->dCxScratch; cxStride = nBlocksAll;
+        }
+        UlcbEncodeArgs p1 = a;
+        p1.mode = ULCB_ENC_ANALYSE; p1.complexity = cxBuf; p1.metaStride = cxStride;
+        p1.blockBytes = nullptr; p1.windowCtrl = nullptr; p1.totalBytes = nullptr; p1.status = nullptr;
+        CK(ctx, ulcb_encode_launch(p1, ctx->nChan, grid, ctx->stream));
+        CK(ctx, ulcb_avg_complexity_launch(cxBuf, cxStride, dNBlocks, nBlocksAll, nStreams, ctx->dAvgCx, ctx->stream));
+        ctx->launches += 2; ctx->avgCount = nStreams;
+        a.mode = ULCB_ENC_ABR; a.avgPerStream = ctx->dAvgCx;
+    }
     CK(ctx, ulcb_encode_launch(a, ctx->nChan, grid, ctx->stream));
     ctx->launches++;
+    return ULCB_OK;
+}
+
+int ULCB_GetAvgComplexity(ULCB_Context *ctx, float *avgComplexity, int nStreams) {
+    if (!ctx || !avgComplexity || nStreams < 0 || nStreams > ctx->avgCount) return ULCB_E_PARAM;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(avgComplexity, ctx->dAvgCx, sizeof(float) * (size_t)nStreams, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return ULCB_OK;
 }
 

@@ -703,7 +703,7 @@ struct Encoder {
                     }
                     sm.cx = cx;
                 }
-            } else if ((args.dbgFlags & 2) || ((args.dbgFlags & 4) && task != U)) {
+            } else if (args.mode == ULCB_ENC_ANALYSE || (args.dbgFlags & 2) || ((args.dbgFlags & 4) && task != U)) {
             } else if (task < U) {
                 int c = task / sm.nsub, j = task - c * sm.nsub;
                 const SubInfo &s = sm.sub[j];
@@ -1260,6 +1260,16 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
             enc.serial_sums(k);
             wsync<NTHR>();
             TICK(5);
+            if (args.mode == ULCB_ENC_ANALYSE) {                      // first pass of two-pass ABR: complexity and window control only
+                if (tid == 0) {
+                    const size_t mi = (size_t)stream * args.metaStride + b;
+                    if (args.blockBytes) args.blockBytes[mi] = 0u;
+                    if (args.complexity) args.complexity[mi] = sm.cx;
+                    if (args.windowCtrl) args.windowCtrl[mi] = sm.wcCur;
+                }
+                wsync<NTHR>();
+                continue;
+            }
             enc.spread();
             wsync<NTHR>();
             TICK(6);
@@ -1286,7 +1296,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
                 size = enc.encode_pass(k, nOut, true);
             } else {
                 float kbps = args.param;
-                if (args.mode == ULCB_ENC_ABR) kbps = args.param * cx / args.avgComplexity;
+                if (args.mode == ULCB_ENC_ABR) kbps = args.param * cx / (args.avgPerStream ? args.avgPerStream[stream] : args.avgComplexity);
                 const int budget = (int)(((float)N * kbps) * 1000.0f / (float)args.tb.rateHz);
                 int lo = 0, hi = maxCoef, nOut = -1;
                 if (lo < hi) do {
@@ -1352,6 +1362,25 @@ extern "C" int ULCB_DebugPhaseTimes(unsigned long long *out13) {
     return (int)e;
 }
 #endif
+
+namespace {
+__global__ void ulcb_avg_complexity_kernel(const float *__restrict__ cx, uint64_t metaStride, const uint32_t *__restrict__ nBlocks, uint32_t nBlocksAll,
+                                           int nStreams, float *__restrict__ avg) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nStreams) return;
+    const uint32_t nb = nBlocks ? nBlocks[s] : nBlocksAll;
+    double sum = 0.0;                                                   // ComplexitySum += Encoder.BlockComplexity, block order (:164)
+    for (uint32_t b = 0; b < nb; b++) sum += (double)cx[(size_t)s * metaStride + b];
+    const double mean = nb ? sum / (double)nb : 0.0;                    // :177
+    avg[s] = (float)(rint(mean * 1e5) / 1e5);                           // printed with %.5f, typed back, read with %f (:41,:187)
+}
+}  // namespace
+
+cudaError_t ulcb_avg_complexity_launch(const float *dComplexity, uint64_t metaStride, const uint32_t *dNBlocks, uint32_t nBlocksAll,
+                                       int nStreams, float *dAvg, cudaStream_t stream) {
+    ulcb_avg_complexity_kernel<<<(nStreams + 127) / 128, 128, 0, stream>>>(dComplexity, metaStride, dNBlocks, nBlocksAll, nStreams, dAvg);
+    return cudaGetLastError();
+}
 
 bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4096; }
 int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }

@@ -43,7 +43,8 @@ struct UlcbEncStreamState {
     uint32_t calls;           // blocks consumed so far
 };
 
-enum { ULCB_ENC_VBR = 0, ULCB_ENC_CBR = 1, ULCB_ENC_ABR = 2 };
+enum { ULCB_ENC_VBR = 0, ULCB_ENC_CBR = 1, ULCB_ENC_ABR = 2,
+       ULCB_ENC_ANALYSE = 3 };   // window control + MDCT + BlockComplexity only: the first pass of two-pass ABR, writes no bytes
 
 struct UlcbEncodeArgs {
     UlcbEncTables   tb;
@@ -57,6 +58,7 @@ struct UlcbEncodeArgs {
     int             mode;              // ULCB_ENC_*
     float           param;             // VBR: target = 0x1.E4EFB7p3f*logf(100/Quality) (host libm); CBR/ABR: RateKbps
     float           avgComplexity;     // ABR
+    const float    *avgPerStream;      // ABR: [nStreams] per-stream AvgComplexity (device), overrides avgComplexity; nullable
     uint8_t        *out;               // [stream] arena of outStride bytes, blocks back to back
     uint64_t        outStride;
     uint32_t       *blockBytes;        // [stream][metaStride] bytes per block; nullable
@@ -83,4 +85,7 @@ size_t      ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs);
 size_t      ulcb_encode_ws_floats(int N, int nChan);
 int         ulcb_encode_threads(int N, int nChan);
 bool        ulcb_encode_uses_global_ws(int N, int nChan);
+// per-stream mean of the block complexities, rounded like the tool's "%.5f" print / "%f" read-back (tools/ulcEncodeTool.c:41,178-188)
+cudaError_t ulcb_avg_complexity_launch(const float *dComplexity, uint64_t metaStride, const uint32_t *dNBlocks, uint32_t nBlocksAll,
+                                       int nStreams, float *dAvg, cudaStream_t stream);
 cudaError_t ulcb_encode_launch(const UlcbEncodeArgs &args, int nChan, int gridBlocks, cudaStream_t stream);
