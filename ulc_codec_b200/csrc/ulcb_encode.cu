@@ -552,8 +552,67 @@ struct Encoder {
             }
         }
     }
+    // The same passes for a block that is ONE sub-block (no window switching, the common case): the recursion depth is
+    // uniform across the CTA, so buffer parity, node size and the pair index need no per-element sub-block lookup.
+    // Identical arithmetic per element.
+    __device__ void dct_down_long(int m, int lgm) {
+        const int hm = m >> 1, lgH = tb.log2N - 1, d = tb.log2N - lgm;
+        const float *const S0 = (d & 1) ? w.TA : w.XA, *const S1 = (d & 1) ? w.TB : w.XB;
+        float *const D0 = (d & 1) ? w.XA : w.TA, *const D1 = (d & 1) ? w.XB : w.TB;
+#pragma unroll 4
+        for (int P = tid; P < CN; P += NTHR) {
+            const int cc = P >> lgH, r = P & (H - 1);
+            const bool hb = cc >= NCH;
+            const int node = r >> (lgm - 1), i = r & (hm - 1);
+            const int off = (hb ? cc - NCH : cc) * N + (node << lgm);
+            const float *src = (hb ? S1 : S0) + off;
+            float *dst = (hb ? D1 : D0) + off;
+            float a = src[i], b = src[m - 1 - i];
+            if (node_is_dct4(d, node)) {                              // Fourier_DCT4_Template.h:49-68
+                float2 rt = __ldg(&tb.rot[hm + i]);
+                dst[i] = rt.x * a + rt.y * b;
+                float p = rt.y * a, q = rt.x * b;
+                dst[hm + i] = (i & 1) ? (q - p) : (p - q);
+            } else {                                                  // Fourier_DCT2_Template.h:24-40
+                dst[i] = a + b;
+                dst[hm + i] = a - b;
+            }
+        }
+    }
+    __device__ void dct_up_long(int m, int lgm) {
+        const int hm = m >> 1, lgH = tb.log2N - 1, d = tb.log2N - lgm;
+        const float *const S0 = (d & 1) ? w.XA : w.TA, *const S1 = (d & 1) ? w.XB : w.TB;   // children live at depth d+1
+        float *const D0 = (d & 1) ? w.TA : w.XA, *const D1 = (d & 1) ? w.TB : w.XB;
+#pragma unroll 4
+        for (int P = tid; P < CN; P += NTHR) {
+            const int cc = P >> lgH, r = P & (H - 1);
+            const bool hb = cc >= NCH;
+            const int node = r >> (lgm - 1), i = r & (hm - 1);
+            const int off = (hb ? cc - NCH : cc) * N + (node << lgm);
+            const float *src = (hb ? S1 : S0) + off;
+            float *dst = (hb ? D1 : D0) + off;
+            if (node_is_dct4(d, node)) {                              // Fourier_DCT4_Template.h:100-114
+                if (i == hm - 1) { dst[0] = src[0]; dst[m - 1] = src[hm]; }
+                else {
+                    float a = src[i + 1], b = src[m - 1 - i];
+                    dst[2 * i + 1] = a + b;
+                    dst[2 * i + 2] = a - b;
+                }
+            } else {                                                  // Fourier_DCT2_Template.h:62-77
+                dst[2 * i] = src[i];
+                dst[2 * i + 1] = src[hm + i];
+            }
+        }
+    }
     __device__ void transform() {
         const int lgN = tb.log2N;
+        if (sm.nsub == 1) {
+            for (int lgm = lgN; lgm >= 4; lgm--) { dct_down_long(1 << lgm, lgm); wsync<NTHR>(); }
+            dct_leaves();
+            wsync<NTHR>();
+            for (int lgm = 4; lgm <= lgN; lgm++) { dct_up_long(1 << lgm, lgm); wsync<NTHR>(); }
+            return;
+        }
         for (int lgm = lgN; lgm >= 4; lgm--) { dct_down(1 << lgm, lgm); wsync<NTHR>(); }
         dct_leaves();
         wsync<NTHR>();
