@@ -1111,7 +1111,29 @@ struct Detector {
 #pragma unroll
                     for (int c = 0; c < NCH; c++) stg[c * W + i] = prevBlk ? prevBlk[c * N + (int)(N + sBeg + i)] : 0.0f;
             }
-            if (nSamples > 0) {
+            if (nSamples > 0 && NCH == 2 && !args.pcmFloat) {
+                // stereo PCM16: one 32-bit load per sample pair, 16 of them in flight per lane
+                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(pcm);
+                for (int ib = i0 + lane; ib < W; ib += 512) {
+                    uint32_t wv[16]; bool ok[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const int i = ib + 32 * u;
+                        const long long sv = sBeg + i;
+                        ok[u] = i < W && sv < nSamples;
+                        wv[u] = ok[u] ? __ldg(p32 + sv) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const int i = ib + 32 * u;
+                        if (i < W) {
+                            const float a = (float)(int16_t)(wv[u] & 0xffffu) * 0x1.0p-15f, bb = (float)(int16_t)(wv[u] >> 16) * 0x1.0p-15f;
+                            stg[i] = ok[u] ? (a + bb) * 0.5f : 0.0f;
+                            stg[W + i] = ok[u] ? (a - bb) * 0.5f : 0.0f;
+                        }
+                    }
+                }
+            } else if (nSamples > 0) {
                 for (int ib = i0 + lane; ib < W; ib += 256) {             // 8 independent loads in flight per lane
                     float v[8][NCH]; bool ok[8];
 #pragma unroll
@@ -1174,19 +1196,23 @@ struct Detector {
             for (int sg = 0; sg < 8; sg++) {
                 float acc = 0.0f;
                 for (int n0 = 0; n0 < bin; n0 += 8) {                    // bin >= 32
-                    float xs[8];
+                    float xs[8], ds[8], ss[8];
 #pragma unroll
                     for (int q = 0; q < 8; q++) xs[q] = ptr[2 * dir * q];   // every slot is read before it is overwritten
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
+                    for (int q = 0; q < 8; q++) {                         // the dependent chain, nothing else in its way
                         const float d = xs[q] - st;
                         st += d * c;
-                        const float ps = __shfl_xor_sync(0xffffffffu, st, 1);   // the other band's updated envelope
-                        const float pr = d * ps;
+                        ds[q] = d; ss[q] = st;
+                        acc += st;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {                         // off the chain: 16 independent shuffles
+                        const float ps = __shfl_xor_sync(0xffffffffu, ss[q], 1);   // the other band's updated envelope
+                        const float pr = ds[q] * ps;
                         const float sq = pr * pr;
                         const float e = sq + __shfl_xor_sync(0xffffffffu, sq, 1);   // (dh*qbp)^2 + (db*qhp)^2 on lane 2
-                        if (store) ptr[2 * dir * q] = isPost ? st : e;
-                        acc += st;
+                        if (store) ptr[2 * dir * q] = isPost ? ss[q] : e;
                     }
                     ptr += 16 * dir;
                 }
