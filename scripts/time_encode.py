@@ -48,9 +48,10 @@ with capi.Context(44100, C, N) as ctx:
 
     import ctypes as C
     if hasattr(ctx.L, "ULCB_DebugPhaseTimes"):
-        buf = (C.c_ulonglong * 24)()
+        buf = (C.c_ulonglong * 32)()
         ctx.L.ULCB_DebugPhaseTimes(buf)
         nblk = max(1, buf[12])
         names = ["ingest", "wait-detector", "begin+fold", "dct", "analyse", "serial-sums", "spread", "keys+sort", "rate+encode", "emit"]
         tot = sum(buf[i] for i in range(10))
         print("phase cycles per block (thread 0): " + ", ".join(f"{n} {buf[i] / nblk:.0f}" for i, n in enumerate(names)) + f" | total {tot / nblk:.0f} | begin_block {buf[10] / nblk:.0f} detector busy {buf[13] / nblk:.0f} wait {buf[14] / nblk:.0f} [stage {buf[16] / nblk:.0f} energy {buf[17] / nblk:.0f} post {buf[18] / nblk:.0f} pre {buf[19] / nblk:.0f} blk {buf[20] / nblk:.0f} decide {buf[21] / nblk:.0f}]")
+        print("encode_pass cycles per block: " + ", ".join(f"{n} {buf[22 + i] / nblk:.0f}" for i, n in enumerate(["select", "zones", "zone-walk", "zone-info", "kept", "walk-count", "scan", "walk-write"])))

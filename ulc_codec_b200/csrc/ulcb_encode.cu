@@ -288,12 +288,18 @@ __device__ __forceinline__ int find_sub(const EncSmall &sm, int n) {     // sub-
 
 // ---- nybble sinks ----------------------------------------------------------------------------------
 struct CountSink { int n; __device__ __forceinline__ void put(int) { n++; } };
-struct WriteSink {
-    uint32_t *words; int pos, cap;
+struct WriteSink {                                   // a thread's nybbles are contiguous: gather a word, one atomicOr per word
+    uint32_t *words; int pos, cap; uint32_t acc = 0;
     __device__ __forceinline__ void put(int x) {
-        if (pos < cap) atomicOr(&words[pos >> 3], (uint32_t)(x & 15) << ((pos & 7) * 4));
+        if (pos < cap) acc |= (uint32_t)(x & 15) << ((pos & 7) * 4);
         pos++;
+        if ((pos & 7) == 0) flush_word(pos - 1);
     }
+    __device__ __forceinline__ void flush_word(int lastPos) {
+        if (acc) atomicOr(&words[lastPos >> 3], acc);
+        acc = 0;
+    }
+    __device__ __forceinline__ void finish() { if (pos & 7) flush_word(pos); }
 };
 
 // noise amplitude code of a run (ulcEncoder_NoiseFill.c:15-36)
@@ -932,6 +938,12 @@ struct Encoder {
         const int E = CN / NTHR, U = NCH * sm.nsub, i0 = tid * E;
         const int capNyb = 8 * ((CN >> 1) + 4);                                   // 2*CN + 16 bytes
 
+#ifdef ULCB_PHASE_TIMING
+        long long et0 = clock64();
+#define ETK(i) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_ulcbPhase[i], (unsigned long long)(t_ - et0)); et0 = t_; } } while (0)
+#else
+#define ETK(i) do { } while (0)
+#endif
         // G1: selection, compaction in index order
         int cntSel = 0;
         for (int e = 0; e < E; e++) { info[i0 + e] = 0; cntSel += (int)rank[i0 + e] < nOut; }
@@ -949,6 +961,7 @@ struct Encoder {
         if (write) for (int i = tid; i < (CN >> 1) + 4; i += NTHR) outW[i] = 0u;
         wsync<NTHR>();
 
+        ETK(22);
         // G2: greedy quantiser zones (ulcEncoder_Encode.c:200-269).  A zone that starts at selected coefficient m runs
         // until the first later one that would push max/min of the levels above 4; that end only depends on m, so
         // every selected coefficient computes "the zone that would start here" in parallel (jump pointer + quantiser),
@@ -959,7 +972,21 @@ struct Encoder {
             const int m1 = sm.unitSel[u + 1];
             float lo = fabsf(coef[selList[m]]), hi = lo;
             int mm = m + 1;
-            for (; mm < m1; mm++) {
+            bool open = true;
+            while (open && mm + 4 <= m1) {                            // four levels fetched at once, tested in order
+                const float l0 = fabsf(coef[selList[mm]]), l1 = fabsf(coef[selList[mm + 1]]);
+                const float l2 = fabsf(coef[selList[mm + 2]]), l3 = fabsf(coef[selList[mm + 3]]);
+                const float lv[4] = {l0, l1, l2, l3};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (open) {
+                        const float newLo = lv[q] < lo ? lv[q] : lo, newHi = lv[q] > hi ? lv[q] : hi;
+                        if (newHi > newLo * 4.0f) open = false;
+                        else { lo = newLo; hi = newHi; mm++; }
+                    }
+                }
+            }
+            for (; open && mm < m1; mm++) {
                 const float level = fabsf(coef[selList[mm]]);
                 const float newLo = level < lo ? level : lo, newHi = level > hi ? level : hi;
                 if (newHi > newLo * 4.0f) break;
@@ -972,6 +999,7 @@ struct Encoder {
             qcand[m] = (uint8_t)q;
         }
         wsync<NTHR>();
+        ETK(23);
         if (tid < U) {
             const int m0 = sm.unitSel[tid], m1 = sm.unitSel[tid + 1];
             int z = 0, prevQ = -1;
@@ -986,6 +1014,7 @@ struct Encoder {
         }
         wsync<NTHR>();
 
+        ETK(24);
         // G2b: per selected coefficient, its zone's quantiser and header flags
         for (int m = tid; m < nSel; m += NTHR) {
             int u = 0;
@@ -1003,6 +1032,7 @@ struct Encoder {
         }
         wsync<NTHR>();
 
+        ETK(25);
         // G3: kept coefficients and the last kept index before each thread's slots
         uint32_t keptMask = 0; int lastKeptP1 = 0;
         for (int e = 0; e < E; e++) {
@@ -1045,16 +1075,22 @@ struct Encoder {
             }
         };
 
+        ETK(26);
         CountSink cs{0};
         walk(cs, true);
+        __syncwarp();
+        ETK(27);
         int total, offs = block_excl_sum<NTHR>(cs.n, sm.scan, total);
+        ETK(28);
         const int hdr = (sm.wcCur & 8) ? 2 : 1;
         if (write) {
             WriteSink ws{outW, hdr + offs, capNyb};
             walk(ws, false);
-            if (tid == 0) { WriteSink h{outW, 0, capNyb}; h.put(sm.wcCur); if (sm.wcCur & 8) h.put(sm.wcCur >> 4); }
+            ws.finish();
+            if (tid == 0) { WriteSink h{outW, 0, capNyb}; h.put(sm.wcCur); if (sm.wcCur & 8) h.put(sm.wcCur >> 4); h.finish(); }
         }
         wsync<NTHR>();
+        ETK(29);
         return ((hdr + total) * 4 + 7) & ~7;
     }
 };
@@ -1191,34 +1227,40 @@ struct Detector {
             float *ptr = base + comp + (isPre ? 2 * (N - 1) : 0);
             const float c = lane == 0 ? tb.c1PostHp : lane == 1 ? tb.c1PostBp : lane == 2 ? tb.c1PreHp : lane == 3 ? tb.c1PreBp : tb.c1Blk;
             float st = lane == 0 ? env[0] : lane == 1 ? env[1] : lane == 2 ? preHp : lane == 3 ? preBp : env[2];
-            const bool store = (isPost && doPost) || (lane == 2 && doPre);
+            // Lanes 0-3 write their updated envelope back in place; the pre-mask lanes also park d = x - s in the (by now
+            // dead) staging planes, and the error energy (dh*qbp)^2 + (db*qhp)^2 is formed afterwards by all 32 lanes.
+            const bool store = (isPost && doPost) || (isPre && doPre);
+            float *dpark = stg + (lane == 3 ? W : 0) + (N - 1);         // d of sample n at plane[n]; the pre-mask runs backwards
             const int bin = N >> 3;
             for (int sg = 0; sg < 8; sg++) {
                 float acc = 0.0f;
                 for (int n0 = 0; n0 < bin; n0 += 8) {                    // bin >= 32
-                    float xs[8], ds[8], ss[8];
+                    float xs[8];
 #pragma unroll
                     for (int q = 0; q < 8; q++) xs[q] = ptr[2 * dir * q];   // every slot is read before it is overwritten
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {                         // the dependent chain, nothing else in its way
+                    for (int q = 0; q < 8; q++) {
                         const float d = xs[q] - st;
                         st += d * c;
-                        ds[q] = d; ss[q] = st;
+                        if (store) ptr[2 * dir * q] = st;
+                        if (isPre) dpark[-q] = d;
                         acc += st;
                     }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {                         // off the chain: 16 independent shuffles
-                        const float ps = __shfl_xor_sync(0xffffffffu, ss[q], 1);   // the other band's updated envelope
-                        const float pr = ds[q] * ps;
-                        const float sq = pr * pr;
-                        const float e = sq + __shfl_xor_sync(0xffffffffu, sq, 1);   // (dh*qbp)^2 + (db*qhp)^2 on lane 2
-                        if (store) ptr[2 * dir * q] = isPost ? ss[q] : e;
-                    }
                     ptr += 16 * dir;
+                    dpark -= 8;
                 }
                 if (isBlk && doBlk) {
                     seg[2 * sg] = seg[16 + 2 * sg]; seg[2 * sg + 1] = seg[16 + 2 * sg + 1];
                     seg[16 + 2 * sg] = acc; seg[16 + 2 * sg + 1] = (float)bin;   // the count is one 1.0f per sample (:126)
+                }
+            }
+            __syncwarp();
+            if (doPre) {                                                 // error energy of block it-1 over the HP slot (:98-103)
+#pragma unroll 4
+                for (int n = lane; n < N; n += 32) {
+                    const float2 sv = Q[n];                              // (qhp, qbp) after this sample's update
+                    const float a = stg[n] * sv.y, bb = stg[W + n] * sv.x;
+                    Q[n].x = a * a + bb * bb;
                 }
             }
             // carry the envelope states
@@ -1249,7 +1291,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
         wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
         wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H;
         if (!GWS) { detE = reinterpret_cast<float2 *>(p); p += sizeof(float2) * N * 3; }
-        detStage = reinterpret_cast<float *>(p); p += sizeof(float) * NCH * (N + 4);
+        detStage = reinterpret_cast<float *>(p); p += sizeof(float) * (NCH < 2 ? 2 : NCH) * (N + 4);   // >= 2 planes: the pre-mask lanes park d there
         float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
         if (GWS) detE = reinterpret_cast<float2 *>(big + 8 * CN + 64);
         wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
@@ -1441,7 +1483,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
 #ifdef ULCB_PHASE_TIMING
 extern "C" int ULCB_DebugPhaseTimes(unsigned long long *out13) {
     cudaDeviceSynchronize();
-    cudaError_t e = cudaMemcpyFromSymbol(out13, g_ulcbPhase, sizeof(unsigned long long) * 24);
+    cudaError_t e = cudaMemcpyFromSymbol(out13, g_ulcbPhase, sizeof(unsigned long long) * 32);
     unsigned long long z[32] = {0};
     cudaMemcpyToSymbol(g_ulcbPhase, z, sizeof z);
     return (int)e;
@@ -1471,7 +1513,7 @@ bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4
 int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }
 size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)8 * nChan * N + 64 + (size_t)6 * N; }   // + the detector's 3 block buffers
 size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs) {
-    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * nChan * (N + 4);
+    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * (nChan < 2 ? 2 : nChan) * (N + 4);
     if (!globalWs) s += sizeof(float) * ((size_t)7 * nChan * N + 64);
     return s + 16;
 }
