@@ -352,8 +352,18 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     const size_t offSt = offNb + sizeof(uint32_t) * nStreams, offBits = (offSt + sizeof(int32_t) * nStreams + 15) & ~(size_t)15;
     const size_t auxBytes = offBits + (blockBits ? sizeof(uint32_t) * nStreams * bitsStride : 0);
     int rc;
+    // PCM out is ~11x the bytes in.  When the caller's buffer is page-locked (cudaHostAlloc / cudaHostRegister) the kernel
+    // stores straight into it over PCIe, so the transfer overlaps the decode instead of following it; pageable buffers
+    // go through the device staging buffer and one D2H copy.
+    void *dOutPtr = nullptr;
+    {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
+            !getenv("ULCB_NO_ZEROCOPY")) dOutPtr = at.devicePointer;
+        else (void)cudaGetLastError();
+    }
     if ((rc = grow(ctx, &ctx->dIn, &ctx->dInCap, nBytes + 64))) return rc;
-    if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, outBytes))) return rc;
+    if (!dOutPtr) { if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, outBytes))) return rc; }
     if ((rc = grow(ctx, &ctx->dAux, &ctx->dAuxCap, auxBytes))) return rc;
     char *aux = (char *)ctx->dAux;
     CK(ctx, cudaMemcpyAsync(ctx->dIn, bytes, nBytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -361,10 +371,10 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     CK(ctx, cudaMemcpyAsync(aux + offOffs, streamOffs, sizeof(uint64_t) * (nStreams + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (nBlocks) CK(ctx, cudaMemcpyAsync(aux + offNb, nBlocks, sizeof(uint32_t) * nStreams, cudaMemcpyHostToDevice, ctx->stream));
     rc = decode_device(ctx, nStreams, (const uint8_t *)ctx->dIn, (const uint64_t *)(aux + offOffs),
-                       nBlocks ? (const uint32_t *)(aux + offNb) : nullptr, nBlocksAll, ctx->dOut, outStrideElems, format,
+                       nBlocks ? (const uint32_t *)(aux + offNb) : nullptr, nBlocksAll, dOutPtr ? dOutPtr : ctx->dOut, outStrideElems, format,
                        (int32_t *)(aux + offSt), blockBits ? (uint32_t *)(aux + offBits) : nullptr, bitsStride, nullptr, nullptr);
     if (rc) return rc;
-    CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dOutPtr) CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) CK(ctx, cudaMemcpyAsync(status, aux + offSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
     if (blockBits) CK(ctx, cudaMemcpyAsync(blockBits, aux + offBits, sizeof(uint32_t) * nStreams * bitsStride, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
