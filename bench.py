@@ -397,7 +397,7 @@ def main():
         assert (h_status == -1).all()
         e2e = {"value": world * ne * BLOCKS_PER_STREAM * N / RATE / dt, "unit": "xrealtime", "h2d_bytes_per_step": int(len(h_data)),
                "d2h_bytes_per_step": int(ne * stride * 2), "streams_per_gpu": ne, "ms_per_step": dt * 1e3,
-               "api": "ULCB_DecodeStreams (host pointers, pinned), bounded to e2e_streams streams per GPU"}
+               "api": "ULCB_DecodeStreams (host pointers, pinned; bytes in by H2D copy, PCM out stored by the kernel straight into the pinned buffer over PCIe), bounded to e2e_streams streams per GPU"}
 
     # ---- secondary measurement: batched VBR encode (configs[2]); the headline stays the decode line above ----
     enc = None
