@@ -221,7 +221,7 @@ struct Parser {
         bool hasStop = false;
         if (on) {
             int p = entry;
-#pragma unroll
+#pragma unroll 2
             for (int it = 0; it < 8; it++) {
                 if (p < 8 && !hasStop) {
                     const uint32_t bit = 8u << (4 * p);
@@ -322,7 +322,7 @@ struct Parser {
             int eb = qIn > 26 ? -1 : (5 + qIn) << 7;                               // bf16 exponent bias of the quantiser
             uint16_t *cf = sm.coef[c];
             const uint32_t mine = starts & below, special = W.is0 | W.is1 | W.is8 | W.isF, qtok = W.isF & ~W.stop;
-#pragma unroll
+#pragma unroll 2
             for (int o = 0; o < 8; o++) {
                 const uint32_t bit = 8u << (4 * o);
                 const bool tok = (mine & bit) != 0;
@@ -629,7 +629,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
                 // z[n] = (v[2n] + i v[N-1-2n]) E[n], n = lane + 32 j, stored at zb[j][lane]; v[N-1-2n] is the odd half of
                 // word 1023-n, which lane 31-lane holds at j' = 31-j
                 uint32_t *cw = reinterpret_cast<uint32_t *>(sm.coef[c]);
-#pragma unroll 2
+#pragma unroll 1
                 for (int j = 0; j < 16; j++) {
                     const int ja = j, jb = 31 - j;
                     const int na = lane + 32 * ja, nb = lane + 32 * jb;
@@ -688,7 +688,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
             if (flat == 0) {
                 // steady state (full overlap): sine window over the whole half block, win[N/2 + i]
                 const float2 *__restrict__ wv = win + H;
-#pragma unroll 4
+#pragma unroll 2
                 for (int k2 = 0; k2 < 16; k2++) {         // k < 512: i = N/2-1-2k, X[N/2+i] = -Im y, next tail = Re y
                     const int k = lane + 32 * k2;
                     const float2 y = zb[k2 * ZROW + lane];
@@ -697,7 +697,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
                     pend[k] = y.x;
                     zb[k2 * ZROW + lane] = make_float2(w.x * a - w.y * b, w.y * a + w.x * b);
                 }
-#pragma unroll 4
+#pragma unroll 2
                 for (int k2 = 16; k2 < 32; k2++) {        // k >= 512: i = 2k-N/2, X[N/2+i] = Re y, next tail = -Im y
                     const int k = lane + 32 * k2;
                     const float2 y = zb[k2 * ZROW + lane];
@@ -730,7 +730,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
                 // warp 0 stores the first half of the block (samples i = .x), warp 1 the second (samples N-1-i = .y); M/S undo
                 // (ulcDecoder.c:281-289).  Pair (t, t+1) = slots k_e = p + (c ? 0 : 512) and k_o = (c ? 1023 : 511) - p, p = lane + 32 q.
                 const float *m0 = reinterpret_cast<const float *>(sm.zbuf[0]) + c, *s0 = reinterpret_cast<const float *>(sm.zbuf[1]) + c;
-#pragma unroll 4
+#pragma unroll 2
                 for (int q = 0; q < 16; q++) {
                     const int ie = ((c ? q : q + 16) * ZROW + lane) * 2, io = ((c ? 31 - q : 15 - q) * ZROW + 31 - lane) * 2;
                     const float me = m0[ie], se = s0[ie], mo = m0[io], so = s0[io];
