@@ -185,10 +185,12 @@ struct Parser {
             curW = wb; digested = false;
         }
     }
-    __device__ __forceinline__ int read_nyb(long long pos) {
+    // the 4 nybbles that start at pos, low nybble first (a window's last lane also holds the next window's first word)
+    __device__ __forceinline__ uint32_t peek16(long long pos) {
         ensure(pos);
         const int rel = (int)(pos - curW * 8);
-        return (__shfl_sync(FULL, W.w, rel >> 3) >> ((rel & 7) * 4)) & 15;
+        const uint32_t lo = __shfl_sync(FULL, W.w, rel >> 3), hi = __shfl_sync(FULL, W.nx, rel >> 3);
+        return __funnelshift_r(lo, hi, (rel & 7) * 4) & 0xffffu;
     }
     static constexpr unsigned FULL = 0xffffffffu;
 
@@ -388,18 +390,25 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                 __syncwarp();
             }
             const long long blkStart = pos;
-            const int h0 = P.read_nyb(pos++);
-            if (h0 & 8) wc = h0 | (P.read_nyb(pos++) << 4); else wc = h0 | 0x10;
+            uint32_t hdr = P.peek16(pos);                               // block header (1-2 nybbles) + the first quantiser (1-2)
+            int hdrLeft = 4;
+            const int h0 = hdr & 15;
+            if (h0 & 8) { wc = h0 | (int)(((hdr >> 4) & 15) << 4); pos += 2; hdr >>= 8; hdrLeft = 2; }
+            else { wc = h0 | 0x10; pos += 1; hdr >>= 4; hdrLeft = 3; }
             const unsigned layout = kLayoutWs[wc >> 4];
             bool ok = true;
             for (int c = 0; c < 2 && ok; c++) {
                 int coefBase = 0, nRuns = 0, nTails = 0;
                 for (unsigned pat = layout;; ) {
                     const int S = N >> (pat & 7);
-                    int q = P.read_nyb(pos++);                         // sub-block header: bare quantiser (ulcDecoder.c:103-109)
+                    if (hdrLeft < 2) { hdr = P.peek16(pos); hdrLeft = 4; }
+                    int q = hdr & 15;                                  // sub-block header: bare quantiser (ulcDecoder.c:103-109)
+                    int used = 1;
                     bool silent = false;
                     if (q == 15) q = 30;                               // invalid lead-in; x86 shift semantics -> scale 0
-                    else if (q == 14) { q += P.read_nyb(pos++); if (q == 29) silent = true; }
+                    else if (q == 14) { q += (hdr >> 4) & 15; used = 2; if (q == 29) silent = true; }
+                    pos += used; hdr >>= 4 * used; hdrLeft -= used;
+                    if (!silent) hdrLeft = 0;                          // the token chains move pos: peek again afterwards
                     if (!silent) {
                         int remain = S;
                         for (;;) {
