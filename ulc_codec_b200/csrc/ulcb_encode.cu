@@ -302,6 +302,20 @@ struct WriteSink {                                   // a thread's nybbles are c
     __device__ __forceinline__ void finish() { if (pos & 7) flush_word(pos); }
 };
 
+// Counts like CountSink and keeps the thread's first 64 nybbles in its own 8-word slot, so the write pass is a shifted
+// copy instead of a second walk over the items (noise-fill decisions, quantiser headers, ...).
+struct StageSink {
+    uint32_t *slot; int n = 0; uint32_t acc = 0;
+    __device__ __forceinline__ void put(int x) {
+        if (n < 64) {
+            acc |= (uint32_t)(x & 15) << ((n & 7) * 4);
+            if ((n & 7) == 7) { slot[n >> 3] = acc; acc = 0; }
+        }
+        n++;
+    }
+    __device__ __forceinline__ void finish() { if (n < 64 && (n & 7)) slot[n >> 3] = acc; }
+};
+
 // noise amplitude code of a run (ulcEncoder_NoiseFill.c:15-36)
 __device__ int noise_q(const float *pairs, int band, int n, float q) {
     pairs += band & ~1;
@@ -1076,17 +1090,32 @@ struct Encoder {
         };
 
         ETK(26);
+        // write passes stage their nybbles (the zone scratch is dead by now: 32 bytes per thread)
+        uint32_t *stageSlot = reinterpret_cast<uint32_t *>(w.encScratch) + tid * 8;
         CountSink cs{0};
-        walk(cs, true);
+        if (write) { StageSink ss{stageSlot}; walk(ss, true); ss.finish(); cs.n = ss.n; }
+        else walk(cs, true);
         __syncwarp();
         ETK(27);
         int total, offs = block_excl_sum<NTHR>(cs.n, sm.scan, total);
         ETK(28);
         const int hdr = (sm.wcCur & 8) ? 2 : 1;
         if (write) {
-            WriteSink ws{outW, hdr + offs, capNyb};
-            walk(ws, false);
-            ws.finish();
+            if (cs.n <= 64) {                                         // shifted copy of the staged nybbles to hdr + offs
+                const int p0 = hdr + offs, sh = (p0 & 7) * 4, nW = (cs.n + 7) >> 3;
+                uint32_t prev = 0;
+                for (int q = 0; q <= nW; q++) {
+                    const uint32_t cur = q < nW ? stageSlot[q] : 0u;
+                    const uint32_t v = sh ? ((cur << sh) | (prev >> (32 - sh))) : cur;
+                    const int wi = (p0 >> 3) + q;
+                    if (v && wi * 8 < capNyb) atomicOr(&outW[wi], v);
+                    prev = cur;
+                }
+            } else {
+                WriteSink ws{outW, hdr + offs, capNyb};
+                walk(ws, false);
+                ws.finish();
+            }
             if (tid == 0) { WriteSink h{outW, 0, capNyb}; h.put(sm.wcCur); if (sm.wcCur & 8) h.put(sm.wcCur >> 4); h.finish(); }
         }
         wsync<NTHR>();
