@@ -599,6 +599,40 @@ struct Encoder {
             }
         }
     }
+    // Two recursion levels (node sizes m and m/2) in one pass: the level-m pairs i and m/2-1-i feed exactly the level-m/2
+    // pairs i of both children, so a thread carries its four values through both butterflies in registers - half the
+    // shared-memory traffic and half the barriers of two single-level passes.  Same operations per value.
+    __device__ void dct_down2_long(int lgm, bool srcIsX) {
+        const int m = 1 << lgm, hm = m >> 1, qm = m >> 2, lgH = tb.log2N - 1, d = tb.log2N - lgm;
+        const float *const S0 = srcIsX ? w.XA : w.TA, *const S1 = srcIsX ? w.XB : w.TB;
+        float *const D0 = srcIsX ? w.TA : w.XA, *const D1 = srcIsX ? w.TB : w.XB;
+        auto fly = [&](bool dct4, int half, int i, float a, float b, float &lo, float &hi) {
+            if (dct4) {                                               // Fourier_DCT4_Template.h:49-68
+                const float2 rt = __ldg(&tb.rot[half + i]);
+                lo = rt.x * a + rt.y * b;
+                const float p = rt.y * a, q = rt.x * b;
+                hi = (i & 1) ? (q - p) : (p - q);
+            } else { lo = a + b; hi = a - b; }                        // Fourier_DCT2_Template.h:24-40
+        };
+#pragma unroll 2
+        for (int Q = tid; Q < (CN >> 1); Q += NTHR) {
+            const int cc = Q >> (lgH - 1), r = Q & ((H >> 1) - 1);
+            const bool hb = cc >= NCH;
+            const int node = r >> (lgm - 2), i = r & (qm - 1), i2 = hm - 1 - i;
+            const int off = (hb ? cc - NCH : cc) * N + (node << lgm);
+            const float *src = (hb ? S1 : S0) + off;
+            float *dst = (hb ? D1 : D0) + off;
+            const float a0 = src[i], b0 = src[m - 1 - i], a1 = src[i2], b1 = src[hm + i];
+            const bool t0 = node_is_dct4(d, node);
+            float lo0, hi0, lo1, hi1;
+            fly(t0, hm, i, a0, b0, lo0, hi0);                         // level m, pair i      -> mid[i], mid[hm+i]
+            fly(t0, hm, i2, a1, b1, lo1, hi1);                        // level m, pair hm-1-i -> mid[hm-1-i], mid[m-1-i]
+            float o0, o1, o2, o3;
+            fly(node_is_dct4(d + 1, 2 * node), qm, i, lo0, lo1, o0, o1);          // lower child, pair i
+            fly(node_is_dct4(d + 1, 2 * node + 1), qm, i, hi0, hi1, o2, o3);      // upper child, pair i
+            dst[i] = o0; dst[qm + i] = o1; dst[hm + i] = o2; dst[hm + qm + i] = o3;
+        }
+    }
     __device__ void dct_up_long(int m, int lgm) {
         const int hm = m >> 1, lgH = tb.log2N - 1, d = tb.log2N - lgm;
         const float *const S0 = (d & 1) ? w.XA : w.TA, *const S1 = (d & 1) ? w.XB : w.TB;   // children live at depth d+1
@@ -627,6 +661,10 @@ struct Encoder {
     __device__ void transform() {
         const int lgN = tb.log2N;
         if (sm.nsub == 1) {
+            if (((lgN - 3) & 3) == 0) {                               // an even number of two-level passes leaves the data where the leaves expect it
+                bool srcIsX = true;
+                for (int lgm = lgN; lgm >= 5; lgm -= 2) { dct_down2_long(lgm, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
+            } else
             for (int lgm = lgN; lgm >= 4; lgm--) { dct_down_long(1 << lgm, lgm); wsync<NTHR>(); }
             dct_leaves();
             wsync<NTHR>();
