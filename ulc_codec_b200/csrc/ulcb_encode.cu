@@ -321,6 +321,7 @@ __device__ int noise_q(const float *pairs, int band, int n, float q) {
     pairs += band & ~1;
     n = (n + (band & 1) + 1) >> 1;
     float s = 0.0f, sw = 0.0f;
+#pragma unroll 4
     for (int i = 0; i < n; i++) { float2 p = *reinterpret_cast<const float2 *>(pairs + 2 * i); s += p.y; sw += p.x; }
     if (s == 0.0f) return 0;
     float amp = expf_ref(s / sw);
@@ -332,9 +333,11 @@ __device__ void hf_ext_params(const float *pairs, int band, int n, float q, int 
     pairs += band & ~1;
     n = (n + (band & 1) + 1) >> 1;
     float sx = 0.0f, sx2 = 0.0f, sxy = 0.0f, sy = 0.0f, sw = 0.0f;
-    for (int i = 0; i < n; i++) {
+    float xf = 0.0f;                                              // (float)i * 2.0f, exact: small even integers
+#pragma unroll 4
+    for (int i = 0; i < n; i++, xf += 2.0f) {
         float2 p = *reinterpret_cast<const float2 *>(pairs + 2 * i);
-        float x = (float)i * 2.0f, w = p.x, wy = p.y;
+        float x = xf, w = p.x, wy = p.y;
         sx += w * x; sx2 += w * x * x; sxy += x * wy; sy += wy; sw += w;
     }
     float det = sw * sx2 - sx * sx;
