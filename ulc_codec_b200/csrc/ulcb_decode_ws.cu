@@ -74,7 +74,7 @@ struct Smem {
     float2   zbuf[2][32 * ZROW];  // per transform warp: FFT work buffer / short-block work buffer / output swap
     Run      runs[2][MAXRUNS];
     Meta     meta[2];
-    uint32_t wring[4][36];        // parse warp: 33-word stream windows in flight (cp.async), ring of 4
+    uint32_t wfifo[128];          // parse warp: the next 128 words of the stream (cp.async, 32-word groups), circular
 };
 
 __device__ __forceinline__ float quant_scale(int q) {      // ulcDecoder.c:96-98
@@ -139,8 +139,8 @@ struct Parser {
     const StreamSrc &src;
     const int lane;
     Win W;
-    long long curW = -1;           // word index of the window start (multiple of 32)
-    long long reqUpTo = -100;      // last window index requested
+    long long curW = -1;           // word index of the window start (any word: a chain's window starts at its first word)
+    long long reqUpTo = -100;      // last 32-word group requested
     bool digested = false;
     bool emptyPending = false;     // the EMPTY hand-off of the previous block has not been waited for yet
 #ifdef ULCB_PHASE_TIMING
@@ -155,35 +155,36 @@ struct Parser {
         __syncwarp();
     }
 
-    // Make the 256-nybble window that holds `pos` current.  Windows are copied global -> shared memory with cp.async,
-    // three ahead of the parse (a stream is read front to back), so the HBM/L2 latency of a window is hidden behind
-    // the parse of the two before it and costs no registers.
-    __device__ __forceinline__ void request(long long wi) {              // 33 words of window wi -> ring slot wi & 3
-        const long long g = wi * 32 + lane;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.wring[wi & 3][lane]);
+    // The stream is copied global -> shared memory with cp.async in aligned 32-word groups into a 128-word circular
+    // buffer, up to three groups ahead of the parse (a stream is read front to back), so the HBM/L2 latency is hidden
+    // and costs no registers.  A window is any 33 consecutive words of it.
+    __device__ __forceinline__ void request(long long g32) {              // words [32 g32, 32 g32 + 32)
+        const long long g = g32 * 32 + lane;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.wfifo[g & 127]);
         const bool ok = g < src.nWordsValid;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src.abase + (ok ? g : 0)), "r"(ok ? 4 : 0) : "memory");
-        if (lane == 0) {
-            const bool ok2 = g + 32 < src.nWordsValid;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128u), "l"(src.abase + (ok2 ? g + 32 : 0)), "r"(ok2 ? 4 : 0) : "memory");
-        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    // Open the window that starts at word w0.
+    __device__ __forceinline__ void open(long long w0) {
+        const long long g0 = w0 >> 5;                                      // the window spans groups g0 and g0 + 1
+        if (g0 > reqUpTo + 1 || g0 + 3 < reqUpTo) reqUpTo = g0 - 1;         // not a step forward: start over from here
+        while (reqUpTo < g0 + 3) request(++reqUpTo);                        // g0 + 4 would overwrite g0
+        const int ahead = (int)(reqUpTo - (g0 + 1));                        // groups issued after the window's last
+        if (ahead >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (ahead == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        W.w = sm.wfifo[(w0 + lane) & 127]; W.nx = sm.wfifo[(w0 + lane + 1) & 127];
+        __syncwarp();
+        curW = w0; digested = false;
+    }
+    // A chain's window starts at the word that holds its first token, so no lane of the window is wasted on what came
+    // before it; a window that merely has to contain `pos` (header peek) is kept if it already does.
+    __device__ __forceinline__ void ensure_start(long long pos) { if ((pos >> 3) != curW) open(pos >> 3); }
     __device__ __forceinline__ void ensure(long long pos) {
-        const long long wb = (pos >> 3) & ~31ll;
-        if (wb != curW) {
-            const long long wi = wb >> 5;
-            if (wi > reqUpTo + 1 || wi + 3 <= reqUpTo) reqUpTo = wi - 1;   // not a step forward: start over from this window
-            while (reqUpTo < wi + 2) request(++reqUpTo);
-            const int ahead = (int)(reqUpTo - wi);                         // groups issued after this window's
-            if (ahead >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-            else if (ahead == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            W.w = sm.wring[wi & 3][lane]; W.nx = sm.wring[wi & 3][lane + 1];
-            __syncwarp();
-            curW = wb; digested = false;
-        }
+        const long long w = pos >> 3;
+        if (curW < 0 || w < curW || w >= curW + 32) open(w);
     }
     // the 4 nybbles that start at pos, low nybble first (a window's last lane also holds the next window's first word)
     __device__ __forceinline__ uint32_t peek16(long long pos) {
@@ -413,7 +414,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                         int remain = S;
                         for (;;) {
                             WTK(0);
-                            P.ensure(pos);
+                            P.ensure_start(pos);
                             WTK(2);
                             const int tp = (int)(pos - P.curW * 8);
                             Parser::ChainOut co;
