@@ -638,13 +638,23 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
             {
                 // z[n] = (v[2n] + i v[N-1-2n]) E[n], n = lane + 32 j, stored at zb[j][lane]; v[N-1-2n] is the odd half of
                 // word 1023-n, which lane 31-lane holds at j' = 31-j
+                // First only MOVE the raw words out of the hand-off buffer (into the .x of the slot their z will occupy: this
+                // lane's own column) and clear it, so the parse warp gets its buffer back after ~100 instructions instead of
+                // after the whole twiddle pass with its table loads.
                 uint32_t *cw = reinterpret_cast<uint32_t *>(sm.coef[c]);
+#pragma unroll 4
+                for (int j = 0; j < 32; j++) {
+                    const int n = lane + 32 * j;
+                    const uint32_t wv = cw[n];
+                    cw[n] = 0u;                                           // leave the buffer clear for the parse warp's next block
+                    zb[j * ZROW + lane].x = __uint_as_float(wv);
+                }
+                bar_arrive(BAR_EMPTY, NTHR);                              // coefficients and run records are consumed
 #pragma unroll 1
                 for (int j = 0; j < 16; j++) {
                     const int ja = j, jb = 31 - j;
                     const int na = lane + 32 * ja, nb = lane + 32 * jb;
-                    const uint32_t wa = cw[na], wb = cw[nb];
-                    cw[na] = 0u; cw[nb] = 0u;                             // leave the buffer clear for the parse warp's next block
+                    const uint32_t wa = __float_as_uint(zb[ja * ZROW + lane].x), wb = __float_as_uint(zb[jb * ZROW + lane].x);
                     float ea = __uint_as_float(wa << 16), oa = __uint_as_float(wa & 0xffff0000u);
                     float eb = __uint_as_float(wb << 16), ob = __uint_as_float(wb & 0xffff0000u);
                     if (nT) {
@@ -662,7 +672,6 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
                     zb[jb * ZROW + lane] = make_float2(eb * e1.x - ib * e1.y, eb * e1.y + ib * e1.x);
                 }
             }
-            bar_arrive(BAR_EMPTY, NTHR);                  // coefficients and run records are consumed
             WTK(3);
             // 1024-point FFT as 32 x 32.  ONE copy of the pass code (instruction-cache footprint), run twice:
             //   pass 0: lane l transforms column l (n = l + 32 j over j), multiplies by W_1024^(l k1), stores A[l][k1] at zb[k1][l]
