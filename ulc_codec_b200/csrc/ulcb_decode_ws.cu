@@ -72,7 +72,7 @@ struct Smem {
     uint16_t coef[2][N];          // bf16 dequantised coefficients, per channel
     float    pend[2][H];          // pending tail (k-layout or time order, see above)
     float2   zbuf[2][32 * ZROW];  // per transform warp: FFT work buffer / short-block work buffer / output swap
-    Run      runs[2][MAXRUNS];
+    Run      runs[2][2][MAXRUNS];  // [block parity][channel]: the transform warps read a block's records after releasing its coefficients
     Meta     meta[2];
     uint32_t wfifo[128];          // parse warp: the next 128 words of the stream (cp.async, 32-word groups), circular
 };
@@ -201,7 +201,7 @@ struct Parser {
     // -1 = corrupt.
     struct ChainOut { int endPos, kind, coefs, draws, q, zyx; };
 
-    __device__ int chain(int tp, int remain, int qcur, int idx0, int blkDraws, int c, int &nRuns, ChainOut &out) {
+    __device__ int chain(int tp, int remain, int qcur, int idx0, int blkDraws, int c, Run *runsOut, int &nRuns, ChainOut &out) {
         const int s0 = tp >> 3, e0 = tp & 7;
         CTK(9);
         if (!digested) { win_digest(W); digested = true; }
@@ -343,7 +343,7 @@ struct Parser {
                 if (tok && !(special & bit) && idx < N) cf[idx] = (uint16_t)val;   // coefficient
                 if (tok && s8 && slot < MAXRUNS && idx + n <= N) {                 // noise run: one record, filled by the transform warp
                     Run r; r.a = (uint32_t)idx | ((uint32_t)n << 12); r.b = (uint32_t)draw | (val << 16);
-                    sm.runs[c][slot] = r;
+                    runsOut[slot] = r;
                 }
                 const bool nz = tok && s8;
                 slot += nz ? 1 : 0; draw += nz ? n : 0;
@@ -419,7 +419,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                             const int tp = (int)(pos - P.curW * 8);
                             Parser::ChainOut co;
                             WCNT(4);
-                            const int r = P.chain(tp, remain, q, coefBase + (S - remain), (int)blkDraws, c, nRuns, co);
+                            const int r = P.chain(tp, remain, q, coefBase + (S - remain), (int)blkDraws, c, sm.runs[blk & 1][c], nRuns, co);
                             WTK(3);
                             if (r < 0) { ok = false; break; }
                             pos = P.curW * 8 + co.endPos;
@@ -434,7 +434,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                                         if (lane == 0 && nRuns < MAXRUNS) {
                                             Run rr; rr.a = (uint32_t)start | ((uint32_t)left << 12);
                                             rr.b = blkDraws | 0x3f800000u;          // unit amplitude; the tail's level is applied at load
-                                            sm.runs[c][nRuns] = rr;
+                                            sm.runs[blk & 1][c][nRuns] = rr;
                                             Tail t; t.start = start; t.end = start + left;
                                             t.amp = (float)(lv * lv) * quant_scale(co.q) * (1.0f / 16);
                                             const float decay = 1.0f + (float)(nn * nn) * -0x1.0p-19f;
@@ -544,13 +544,18 @@ __device__ __forceinline__ void store_pairs<true>(void *outBlk, int slotIdx, flo
 
 // noise fill of channel c from the run records (ulcDecoder.c:156-160,179-184): sign of draw g+i of a run that
 // starts at draw g is parity[g+i+1] ^ parity[g].  One lane per run, 64 coefficients per round of table reads.
-__device__ void noise_fill(Smem &sm, const Meta &mt, int c, const uint32_t *__restrict__ par, int lane) {
+// STASH = true: the coefficient words have already been moved into the FFT tile (word n in the .x of slot [n / 32][n % 32]).
+template <bool STASH>
+__device__ void noise_fill(Smem &sm, const Meta &mt, const Run *runs, int c, const uint32_t *__restrict__ par, int lane) {
     const int nR = mt.nRuns[c];
-    uint16_t *cf = sm.coef[c];
-    uint32_t *cw = reinterpret_cast<uint32_t *>(cf);
+    auto word = [&](int n) -> uint32_t * {
+        return STASH ? reinterpret_cast<uint32_t *>(&sm.zbuf[c][(n >> 5) * ZROW + (n & 31)].x)
+                     : reinterpret_cast<uint32_t *>(sm.coef[c]) + n;
+    };
+    auto half = [&](int i) -> uint16_t * { return reinterpret_cast<uint16_t *>(word(i >> 1)) + (i & 1); };
     for (int r0 = 0; r0 < nR; r0 += 32) {
         if (r0 + lane >= nR) continue;
-        const Run rr = sm.runs[c][r0 + lane];
+        const Run rr = runs[r0 + lane];
         int i = rr.a & 0xfff;
         const int end = i + (int)(rr.a >> 12);
         const uint32_t g0 = mt.drawBase + (rr.b & 0xffffu);
@@ -563,14 +568,14 @@ __device__ void noise_fill(Smem &sm, const Meta &mt, int c, const uint32_t *__re
             uint32_t hi = (sh < 32 ? __funnelshift_r(a1, a2, sh) : a2) ^ flip;
             int left = min(end - i, 64);
             if (i & 1) {                                                            // unaligned head
-                cf[i] = (uint16_t)(amp | ((lo & 1u) << 15));
+                *half(i) = (uint16_t)(amp | ((lo & 1u) << 15));
                 lo = __funnelshift_r(lo, hi, 1); hi >>= 1; i++; left--;
             }
             for (; left >= 2; left -= 2, i += 2) {
-                cw[i >> 1] = amp2 | ((lo & 1u) << 15) | ((lo & 2u) << 30);
+                *word(i >> 1) = amp2 | ((lo & 1u) << 15) | ((lo & 2u) << 30);
                 lo = __funnelshift_r(lo, hi, 2); hi >>= 2;
             }
-            if (left) { cf[i] = (uint16_t)(amp | ((lo & 1u) << 15)); i++; }
+            if (left) { *half(i) = (uint16_t)(amp | ((lo & 1u) << 15)); i++; }
         }
     }
     __syncwarp();
@@ -619,7 +624,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
             for (int j = 0; j < 16; j++) store_pairs<PCM16>(outBlk, c * 512 + lane + 32 * j, 0.f, 0.f, 0.f, 0.f);
             continue;
         }
-        noise_fill(sm, mt, c, tb.signParity, lane);
+        const Run *runs = sm.runs[blk & 1][c];
         WTK(2);
         float *dbg = args.dbgCoefs ? args.dbgCoefs + (((size_t)stream * args.nBlocksAll + blk) * 2 + c) * N : nullptr;
 
@@ -649,7 +654,9 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
                     cw[n] = 0u;                                           // leave the buffer clear for the parse warp's next block
                     zb[j * ZROW + lane].x = __uint_as_float(wv);
                 }
-                bar_arrive(BAR_EMPTY, NTHR);                              // coefficients and run records are consumed
+                bar_arrive(BAR_EMPTY, NTHR);                              // the coefficient buffer is free again
+                __syncwarp();
+                noise_fill<true>(sm, mt, runs, c, tb.signParity, lane);   // into the moved words; the records are double-buffered
 #pragma unroll 1
                 for (int j = 0; j < 16; j++) {
                     const int ja = j, jb = 31 - j;
@@ -770,6 +777,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
                 __syncwarp();
                 kLayout = false;
             }
+            noise_fill<false>(sm, mt, runs, c, tb.signParity, lane);
             int off = 0;
             for (unsigned pat = kLayoutWs[wc >> 4];;) {
                 const int sh = pat & 7, S = N >> sh, hS = S >> 1;
