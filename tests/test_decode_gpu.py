@@ -1,10 +1,11 @@
 """GPU parity tests for the batched decoder (through the C ABI) against the oracle.
 
-Tolerances (BASELINE.json north_star, criterion 1): float PCM within 1e-5 of the reference relative to
-the stream peak, PCM16 within +-1 LSB.  The reference's own DCT-IV carries a twiddle-recurrence error
-that grows with the block size (scalar build vs exact: 6e-6 of peak at N=2048, 1.3e-5 at 4096, 4.6e-5 at
-8192; its AVX build: <7e-6 everywhere - see tests/test_oracle_vs_ref.py), and the GPU transform is exact
-to ~1e-6, so for N > 2048 the bound against the scalar oracle is the reference's own self-noise.
+Tolerances (BASELINE.json north_star, criterion 1), asserted at the contract for every block size: float PCM
+within 1e-5 of the reference (the stock scalar build = the oracle) relative to the stream peak, PCM16 within
++-1 LSB.  Measured on the round-2 build (scripts/decode_errors.py, profiles/r02a_decode_errors.json):
+<= 4.2e-6 and 1 LSB on all eight goldens, N = 256..8192.  The reference's two builds differ from EACH OTHER
+by up to 2.0e-5 at N = 4096 (scalar vs AVX/FMA twiddle recurrences), so the AVX comparison below keeps the
+reference's own self-noise as its bound.
 """
 import numpy as np
 import pytest
@@ -14,7 +15,7 @@ from tests.fixtures import GOLDEN_NAMES, load_golden_stream, peak_rel_err
 
 pytestmark = pytest.mark.gpu
 
-FLOAT_TOL = {256: 1e-5, 512: 1e-5, 1024: 1e-5, 2048: 1e-5, 4096: 2.5e-5, 8192: 8e-5}
+FLOAT_TOL = {256: 1e-5, 512: 1e-5, 1024: 1e-5, 2048: 1e-5, 4096: 1e-5, 8192: 1e-5}
 
 
 @pytest.fixture(scope="module")
@@ -64,8 +65,7 @@ def test_decode_golden_pcm16(capi, name):
         pcm, status, _ = ctx.decode_streams([g["data"]], nb, fmt="pcm16")
     assert status[0] == -1
     d = np.abs(pcm[0].astype(np.int32) - ref16.astype(np.int32))
-    lim = 1 if g["block_size"] <= 2048 else 3
-    assert d.max() <= lim, (d.max(), float((d > 0).mean()))
+    assert d.max() <= 1, (d.max(), float((d > 0).mean()))
 
 
 def test_decode_batch_ragged(capi):

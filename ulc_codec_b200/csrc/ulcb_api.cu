@@ -37,6 +37,7 @@ struct ULCB_Context {
     void *dIn = nullptr;  size_t dInCap = 0;
     void *dOut = nullptr; size_t dOutCap = 0;
     void *dAux = nullptr; size_t dAuxCap = 0;
+    void *dSign = nullptr;              // noise-sign parity table (tb.signParity), rebuilt when it has to grow
 };
 
 namespace {
@@ -100,6 +101,26 @@ int upload(ULCB_Context *ctx, const std::vector<T> &h, const T **d) {
     return ULCB_OK;
 }
 
+// running parity of the xorshift32 MSBs (libulc/ulcDecoder.c:75-81): bit m = parity of draws 0..m-1.  (Re)built for at least
+// nBits bits; the drop-in decoder grows it when a stream outlives the table (ULC_DecodeBlock has no length bound).
+int build_sign_table(ULCB_Context *ctx, uint64_t nBits) {
+    std::vector<uint32_t> par((nBits + 31) / 32 + 4, 0u);
+    uint32_t seed = 1234567u, p = 0;
+    for (uint64_t m = 1; m < nBits; m++) {
+        seed ^= seed << 13; seed ^= seed >> 17; seed ^= seed << 5;
+        p ^= seed >> 31;
+        par[m >> 5] |= p << (m & 31);
+    }
+    void *d = nullptr;
+    CK(ctx, cudaMalloc(&d, par.size() * sizeof(uint32_t)));
+    if (cudaMemcpy(d, par.data(), par.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return ULCB_E_CUDA; }
+    if (ctx->dSign) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->dSign); }
+    ctx->dSign = d;
+    ctx->tb.signParity = reinterpret_cast<const uint32_t *>(d);
+    ctx->tb.nSignBits = nBits;
+    return ULCB_OK;
+}
+
 int build_tables(ULCB_Context *ctx) {
     const int N = ctx->N;
     UlcbTables &tb = ctx->tb;
@@ -131,20 +152,7 @@ int build_tables(ULCB_Context *ctx) {
         build_window(win, N);
         if ((rc = upload(ctx, win, &tb.win))) return rc;
     }
-    {
-        // running parity of the xorshift32 MSBs (libulc/ulcDecoder.c:75-81): bit m = parity of draws 0..m-1
-        uint64_t nBits = (uint64_t)ctx->maxBlocks * ctx->nChan * N + 64;
-        std::vector<uint32_t> par((nBits + 31) / 32 + 2, 0u);
-        uint32_t seed = 1234567u, p = 0;
-        for (uint64_t m = 1; m < nBits; m++) {
-            seed ^= seed << 13; seed ^= seed >> 17; seed ^= seed << 5;
-            p ^= seed >> 31;
-            par[m >> 5] |= p << (m & 31);
-        }
-        tb.nSignBits = nBits;
-        if ((rc = upload(ctx, par, &tb.signParity))) return rc;
-    }
-    return ULCB_OK;
+    return build_sign_table(ctx, (uint64_t)ctx->maxBlocks * ctx->nChan * N + 256);
 }
 
 // ---- encoder tables (host libm, so the constants are the reference's own) ----
@@ -290,6 +298,7 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->dIn) cudaFree(ctx->dIn);
     if (ctx->dOut) cudaFree(ctx->dOut);
     if (ctx->dAux) cudaFree(ctx->dAux);
+    if (ctx->dSign) cudaFree(ctx->dSign);
     if (ctx->encWs) cudaFree(ctx->encWs);
     if (ctx->corpusLut) cudaFree(ctx->corpusLut);
     if (ctx->dAvgCx) cudaFree(ctx->dAvgCx);
@@ -314,6 +323,9 @@ static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes,
     if (!ctx || nStreams < 0 || !dBytes || !dStreamOffs || !dOut) return ULCB_E_PARAM;
     if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
+    // the noise-sign table covers maxBlocksPerStream blocks; per-stream counts on the device are bounded inside the kernels
+    if (!dNBlocks && !state && nBlocksAll > ctx->maxBlocks) return ULCB_E_PARAM;
+    if (dBlockBits && bitsStride < (dNBlocks ? 1u : nBlocksAll)) return ULCB_E_PARAM;
     CK(ctx, cudaSetDevice(ctx->device));
     UlcbDecodeArgs a{};
     a.tb = ctx->tb;
@@ -346,6 +358,8 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     uint32_t maxBlk = nBlocksAll;
     if (nBlocks) { maxBlk = 0; for (int s = 0; s < nStreams; s++) if (nBlocks[s] > maxBlk) maxBlk = nBlocks[s]; }
     if (outStrideElems < (uint64_t)maxBlk * ctx->N * ctx->nChan) return ULCB_E_PARAM;
+    if (maxBlk > ctx->maxBlocks || (blockBits && bitsStride < maxBlk)) return ULCB_E_PARAM;
+    for (int s = 0; s < nStreams; s++) if (streamOffs[s + 1] < streamOffs[s]) return ULCB_E_PARAM;
     const size_t outBytes = (size_t)nStreams * outStrideElems * elem;
     // aux layout: offs | nBlocks | status | bits
     const size_t offOffs = 0, offNb = offOffs + sizeof(uint64_t) * (nStreams + 1);
@@ -432,8 +446,9 @@ struct DropinDecoder {
     UlcbStreamState *dState;
     float *dPend;
     uint8_t *dSrc; float *dDst; uint64_t *dOffs; uint32_t *dBits;
-    uint8_t *hSrc; float *hDst; uint32_t *hBits;      // pinned
+    uint8_t *hSrc; float *hDst; uint32_t *hMeta;      // pinned; hMeta = {bits, pad, pad, pad, UlcbStreamState}
     size_t srcBytes;
+    uint64_t calls;                                    // blocks decoded so far: bounds the noise draws consumed
 };
 
 int ULC_DecoderState_Init(struct ULC_DecoderState_t *State) {
@@ -445,7 +460,8 @@ int ULC_DecoderState_Init(struct ULC_DecoderState_t *State) {
     if (!d) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (ULCB_ContextCreate(&d->ctx, dev, 44100, nChan, N, 1u << 14) != ULCB_OK) { free(d); return -1; }
+    // the sign table starts at 1024 blocks and grows with the stream (ULC_DecodeBlock)
+    if (ULCB_ContextCreate(&d->ctx, dev, 44100, nChan, N, 1u << 10) != ULCB_OK) { free(d); return -1; }
     size_t cap = ULCB_MaxBlockBytes(nChan, N);
     d->srcBytes = cap < 16384 ? cap : 16384;
     bool ok = cudaMalloc(&d->dState, sizeof(UlcbStreamState)) == cudaSuccess &&
@@ -456,7 +472,7 @@ int ULC_DecoderState_Init(struct ULC_DecoderState_t *State) {
               cudaMalloc(&d->dBits, sizeof(uint32_t)) == cudaSuccess &&
               cudaMallocHost(&d->hSrc, d->srcBytes) == cudaSuccess &&
               cudaMallocHost(&d->hDst, sizeof(float) * nChan * N) == cudaSuccess &&
-              cudaMallocHost(&d->hBits, sizeof(uint32_t)) == cudaSuccess;
+              cudaMallocHost(&d->hMeta, 8 * sizeof(uint32_t)) == cudaSuccess;
     if (ok) {
         uint64_t offs[2] = {0, d->srcBytes};
         ok = cudaMemset(d->dState, 0, sizeof(UlcbStreamState)) == cudaSuccess &&
@@ -473,7 +489,7 @@ void ULC_DecoderState_Destroy(struct ULC_DecoderState_t *State) {
     DropinDecoder *d = (DropinDecoder *)State->BufferData;
     if (!d) return;
     cudaFree(d->dState); cudaFree(d->dPend); cudaFree(d->dSrc); cudaFree(d->dDst); cudaFree(d->dOffs); cudaFree(d->dBits);
-    cudaFreeHost(d->hSrc); cudaFreeHost(d->hDst); cudaFreeHost(d->hBits);
+    cudaFreeHost(d->hSrc); cudaFreeHost(d->hDst); cudaFreeHost(d->hMeta);
     ULCB_ContextDestroy(d->ctx);
     free(d);
     State->BufferData = NULL;
@@ -484,17 +500,24 @@ int ULC_DecodeBlock(struct ULC_DecoderState_t *State, float *DstData, const void
     if (!d) return 0;
     ULCB_Context *ctx = d->ctx;
     const int n = State->nChan * State->BlockSize;
+    // a stream may be arbitrarily long: keep the noise-sign table ahead of the draws it can have consumed (at most one per
+    // coefficient and block so far, libulc/ulcDecoder.c:156-184)
+    const uint64_t need = (d->calls + 2) * (uint64_t)n + 256;
+    if (need > ctx->tb.nSignBits && build_sign_table(ctx, need > 4 * ctx->tb.nSignBits ? need : 4 * ctx->tb.nSignBits) != ULCB_OK) return 0;
     memcpy(d->hSrc, SrcBuffer, d->srcBytes);
     if (cudaMemcpyAsync(d->dSrc, d->hSrc, d->srcBytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return 0;
     if (decode_device(ctx, 1, d->dSrc, d->dOffs, nullptr, 1, d->dDst, (uint64_t)n, ULCB_FMT_FLOAT32, nullptr, d->dBits, 1,
                       d->dState, d->dPend) != ULCB_OK) return 0;
     cudaMemcpyAsync(d->hDst, d->dDst, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(d->hBits, d->dBits, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&d->hMeta[0], d->dBits, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&d->hMeta[4], d->dState, sizeof(UlcbStreamState), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
     memcpy(DstData, d->hDst, sizeof(float) * n);
     UlcbStreamState st;
-    if (cudaMemcpy(&st, d->dState, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess) State->LastSubBlockSize = st.lastSubBlockSize;
-    return (int)*d->hBits;
+    memcpy(&st, &d->hMeta[4], sizeof st);
+    State->LastSubBlockSize = st.lastSubBlockSize;
+    d->calls++;
+    return (int)d->hMeta[0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,6 +567,10 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
     if (prm->mode == ULCB_MODE_ABR_2PASS && (state || taps)) return ULCB_E_PARAM;     // whole streams only
     if (prm->mode == ULCB_MODE_VBR && !(prm->rate > 0.0f)) return ULCB_E_PARAM;
     if (prm->mode == ULCB_MODE_ABR && !(prm->avgComplexity > 0.0f)) return ULCB_E_PARAM;
+    if (outStrideBytes == 0) return ULCB_E_PARAM;
+    // without per-stream sample counts every stream holds nBlocks*BlockSize sample points: they must lie inside its slot
+    if (!dNSamples && !dNBlocks && inStrideElems < (uint64_t)nBlocksAll * ctx->N * ctx->nChan) return ULCB_E_PARAM;
+    if ((dBlockBytes || dComplexity || dWindowCtrl) && !dNBlocks && metaStride < nBlocksAll) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
     CK(ctx, cudaSetDevice(ctx->device));
     UlcbEncodeArgs a{};
@@ -629,6 +656,7 @@ static int encode_host(ULCB_Context *ctx, int nStreams, const void *pcm, int for
     if (!ctx || nStreams < 0 || !pcm || !out || !params || nBlocksAll < 1) return ULCB_E_PARAM;
     if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
+    if (nSamples) for (int s = 0; s < nStreams; s++) if (nSamples[s] * (uint64_t)ctx->nChan > inStrideElems) return ULCB_E_PARAM;
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t elem = format == ULCB_FMT_PCM16 ? 2 : 4;
     const size_t inBytes = (size_t)nStreams * inStrideElems * elem, outBytes = (size_t)nStreams * outStrideBytes;

@@ -470,6 +470,9 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                         if (!pat || !ok) break;
                     }
                 }
+                // a block whose bytes run past the end of the stream (it parsed from the zero padding) is not decodable; neither
+                // is one whose noise draws lie beyond the sign table the context was created for (maxBlocksPerStream)
+                if (ok && (pos > endNyb || (unsigned long long)drawBase + blkDraws + 128ull > tb.nSignBits)) ok = false;
                 if (!ok) { live = false; deadAt = blk; }
                 else {
                     drawBase += blkDraws;

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <mutex>
 #include "ulcb_dct.cuh"
 #include "ulcb_decode.h"
 
@@ -366,7 +367,7 @@ struct Parser {
     }
 };
 
-__device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, const StreamSrc &src, long long pos0, int nBlocks, int lane) {
+__device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, const StreamSrc &src, long long pos0, int nBlocks, int lane, unsigned bufBase) {
     Parser P(sm, src, lane);
     long long pos = pos0;
     uint32_t drawBase = 0;
@@ -378,7 +379,11 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
         WTK(0);
         P.emptyPending = blk > 0;                                        // waited for at the block's first write (Parser::chain) or its end
         WTK(1);
-        Meta &mt = sm.meta[blk & 1];
+        // runs / meta are double-buffered by a CTA-lifetime block counter: the transform warps may still read the previous
+        // block's records (of this or of the previous stream) when the parse of the next block starts
+        const unsigned par = (bufBase + (unsigned)blk) & 1u;
+        Meta &mt = sm.meta[par];
+        int nRunsC[2] = {0, 0}, nTailsC[2] = {0, 0};
         if (deadAt < 0 && pos >= src.endNyb) deadAt = blk;             // stream exhausted
         bool live = deadAt < 0;
         int wc = 0x10;
@@ -419,7 +424,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                             const int tp = (int)(pos - P.curW * 8);
                             Parser::ChainOut co;
                             WCNT(4);
-                            const int r = P.chain(tp, remain, q, coefBase + (S - remain), (int)blkDraws, c, sm.runs[blk & 1][c], nRuns, co);
+                            const int r = P.chain(tp, remain, q, coefBase + (S - remain), (int)blkDraws, c, sm.runs[par][c], nRuns, co);
                             WTK(3);
                             if (r < 0) { ok = false; break; }
                             pos = P.curW * 8 + co.endPos;
@@ -434,7 +439,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                                         if (lane == 0 && nRuns < MAXRUNS) {
                                             Run rr; rr.a = (uint32_t)start | ((uint32_t)left << 12);
                                             rr.b = blkDraws | 0x3f800000u;          // unit amplitude; the tail's level is applied at load
-                                            sm.runs[blk & 1][c][nRuns] = rr;
+                                            sm.runs[par][c][nRuns] = rr;
                                             Tail t; t.start = start; t.end = start + left;
                                             t.amp = (float)(lv * lv) * quant_scale(co.q) * (1.0f / 16);
                                             const float decay = 1.0f + (float)(nn * nn) * -0x1.0p-19f;
@@ -455,8 +460,11 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                     pat >>= 4;
                     if (!pat || !ok) break;
                 }
-                if (lane == 0) { mt.nRuns[c] = min(nRuns, MAXRUNS); mt.nTails[c] = nTails; }
+                nRunsC[c] = min(nRuns, MAXRUNS); nTailsC[c] = nTails;      // stored with the rest of the meta, after the EMPTY wait
             }
+            // a block whose bytes run past the end of the stream (it parsed from the zero padding) is not decodable; neither
+            // is one whose noise draws lie beyond the sign table the context was created for (maxBlocksPerStream)
+            if (ok && (pos > src.endNyb || (unsigned long long)drawBase + blkDraws + 128ull > args.tb.nSignBits)) ok = false;
             if (!ok) { live = false; deadAt = blk; }
             else {
                 rawBits = (uint32_t)(pos - blkStart) * 4u;               // what ULC_DecodeBlock returns (ulcDecoder.c:301)
@@ -466,6 +474,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
         if (P.emptyPending) { bar_sync(BAR_EMPTY, NTHR); P.emptyPending = false; }   // block without a single token chain
         if (lane == 0) {
             mt.live = live; mt.wc = wc; mt.drawBase = drawBase;
+            mt.nRuns[0] = nRunsC[0]; mt.nRuns[1] = nRunsC[1]; mt.nTails[0] = nTailsC[0]; mt.nTails[1] = nTailsC[1];
             if (args.blockBits) args.blockBits[(size_t)stream * args.bitsStride + blk] = live ? rawBits : 0u;
         }
         if (live) drawBase += blkDraws;
@@ -591,7 +600,7 @@ __device__ __forceinline__ float tail_gain(const Meta &mt, int c, int nT, int id
 }
 
 template <bool PCM16>
-__device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, int nBlocks, int c, int lane) {
+__device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, int nBlocks, int c, int lane, unsigned bufBase) {
     const UlcbTables &tb = args.tb;
     float *pend = sm.pend[c];
     float2 *zb = sm.zbuf[c];
@@ -613,7 +622,8 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
         WTK(0);
         bar_sync(BAR_FULL, NTHR);
         WTK(1);
-        const Meta &mt = sm.meta[blk & 1];
+        const unsigned par = (bufBase + (unsigned)blk) & 1u;
+        const Meta &mt = sm.meta[par];
         const int live = mt.live, wc = mt.wc, nT = mt.nTails[c];
         char *outBlk = reinterpret_cast<char *>(args.out) +
             ((size_t)stream * args.outStride + (size_t)blk * N * 2) * (PCM16 ? 2 : 4);
@@ -624,7 +634,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
             for (int j = 0; j < 16; j++) store_pairs<PCM16>(outBlk, c * 512 + lane + 32 * j, 0.f, 0.f, 0.f, 0.f);
             continue;
         }
-        const Run *runs = sm.runs[blk & 1][c];
+        const Run *runs = sm.runs[par][c];
         WTK(2);
         float *dbg = args.dbgCoefs ? args.dbgCoefs + (((size_t)stream * args.nBlocksAll + blk) * 2 + c) * N : nullptr;
 
@@ -855,6 +865,7 @@ __global__ void __launch_bounds__(NTHR, ULCB_WS_MINB)
 ulcb_decode_ws_kernel(UlcbDecodeArgs args) {
     __shared__ __align__(16) Smem sm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned bufBase = 0;                                               // blocks this CTA has handled so far (buffer parity)
     for (int stream = blockIdx.x; stream < args.nStreams; stream += gridDim.x) {
         const int nBlocks = args.nBlocks ? (int)args.nBlocks[stream] : args.nBlocksAll;
         if (warp == 0) {
@@ -865,10 +876,11 @@ ulcb_decode_ws_kernel(UlcbDecodeArgs args) {
             ss.abase = reinterpret_cast<const uint32_t *>(src - mis);
             ss.nWordsValid = ((long long)mis + srcLen + 3) >> 2;
             ss.endNyb = 2 * ((long long)mis + srcLen);                  // aligned-space nybble index of the stream end
-            parse_warp(sm, args, stream, ss, 2 * (long long)mis, nBlocks, lane);
+            parse_warp(sm, args, stream, ss, 2 * (long long)mis, nBlocks, lane, bufBase);
         } else {
-            transform_warp<PCM16>(sm, args, stream, nBlocks, warp - 1, lane);
+            transform_warp<PCM16>(sm, args, stream, nBlocks, warp - 1, lane, bufBase);
         }
+        bufBase += (unsigned)nBlocks;
     }
 }
 
@@ -881,20 +893,29 @@ bool ulcb_decode_ws_supported(const UlcbDecodeArgs &args, int nChan) {
 
 cudaError_t ulcb_decode_ws_launch(const UlcbDecodeArgs &args, int pcm16, int smCount, cudaStream_t stream) {
     void (*k)(UlcbDecodeArgs) = pcm16 ? ulcb_decode_ws_kernel<true> : ulcb_decode_ws_kernel<false>;
-    static int perSm[2] = {0, 0};
-    if (!perSm[pcm16 ? 1 : 0]) {
-        int carve = cudaSharedmemCarveoutMaxShared;
-        if (const char *ev = getenv("ULCB_WS_CARVEOUT")) carve = atoi(ev);
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        if (e != cudaSuccess) return e;
-        int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NTHR, 0);
-        if (e != cudaSuccess) return e;
-        perSm[pcm16 ? 1 : 0] = n > 0 ? n : 1;
+    // occupancy / carve-out are per device: cached per (device, variant), set up under a lock
+    static std::mutex mu;
+    static int perSmTab[64][2];
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    int &slot = perSmTab[dev & 63][pcm16 ? 1 : 0];
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!slot) {
+            int carve = cudaSharedmemCarveoutMaxShared;
+            if (const char *ev = getenv("ULCB_WS_CARVEOUT")) carve = atoi(ev);
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            if (e != cudaSuccess) return e;
+            int n = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NTHR, 0);
+            if (e != cudaSuccess) return e;
+            slot = n > 0 ? n : 1;
+        }
     }
     // resident CTAs per SM: the most that fit, unless one or two fewer cut the last wave's idle tail by more than
     // the ~10 % of throughput each step down costs (measured: profiles/)
-    const int rmax = perSm[pcm16 ? 1 : 0];
+    const int rmax = slot;
     int best = rmax; double bestEff = 0.0;
     for (int r = rmax; r >= 1 && r >= rmax - 2; r--) {
         const long long slots = (long long)smCount * r;
