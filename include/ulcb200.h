@@ -142,7 +142,9 @@ size_t ULCB_MaxBlockBytes(int nChan, int blockSize);
  *                 (that block and the rest of the stream are written as silence); may be NULL
  *   dBlockBits    [nStreams][bitsStride] bits consumed per block as ULC_DecodeBlock would return
  *                 them (0 = not decoded); may be NULL
- * No block index is needed: block boundaries are discovered by parsing, as in the reference. */
+ * No block index is needed: block boundaries are discovered by parsing, as in the reference.
+ * (The call reads dStreamOffs / dNBlocks back once to size its scratch, so it synchronises the context's stream briefly
+ * before it launches.) */
 int ULCB_DecodeStreamsDevice(ULCB_Context *ctx, int nStreams,
                              const uint8_t *dBytes, const uint64_t *dStreamOffs,
                              const uint32_t *dNBlocks, uint32_t nBlocksAll,
@@ -156,6 +158,26 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams,
                        const uint32_t *nBlocks, uint32_t nBlocksAll,
                        void *out, uint64_t outStrideElems, int format,
                        int32_t *status, uint32_t *blockBits, uint64_t bitsStride);
+
+/* Batched decode WITH a block-size index: dBlockBytes[nStreams][blockBytesStride] holds the byte size of every block of
+ * every stream - exactly what ULCB_EncodeStreams[Device] returns in dBlockBytes, or what a container reader recorded.  The
+ * .ulc payload itself carries no such index (tools/ulc_Helper.h:10-20): the reference finds block k+1 by decoding block k
+ * (tools/ulcDecodeTool.c:153-164), and so do the entry points above (a token-length walk per stream on the device).  With
+ * the index every (stream, block) is decoded independently from the first instruction on.  An index that disagrees with
+ * the bitstream marks the stream undecodable from the first block whose parsed length differs (dStatus).  All other
+ * arguments as ULCB_DecodeStreamsDevice / ULCB_DecodeStreams. */
+int ULCB_DecodeStreamsIndexedDevice(ULCB_Context *ctx, int nStreams,
+                                    const uint8_t *dBytes, const uint64_t *dStreamOffs,
+                                    const uint32_t *dNBlocks, uint32_t nBlocksAll,
+                                    const uint32_t *dBlockBytes, uint64_t blockBytesStride,
+                                    void *dOut, uint64_t outStrideElems, int format,
+                                    int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride);
+int ULCB_DecodeStreamsIndexed(ULCB_Context *ctx, int nStreams,
+                              const uint8_t *bytes, const uint64_t *streamOffs,
+                              const uint32_t *nBlocks, uint32_t nBlocksAll,
+                              const uint32_t *blockBytes, uint64_t blockBytesStride,
+                              void *out, uint64_t outStrideElems, int format,
+                              int32_t *status, uint32_t *blockBits, uint64_t bitsStride);
 
 int ULCB_Sync(ULCB_Context *ctx);
 

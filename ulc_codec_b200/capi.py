@@ -22,12 +22,15 @@ _FMT = {"pcm16": FMT_PCM16, "s16": FMT_PCM16, "f32": FMT_FLOAT32, "float32": FMT
 EXPORTS = (
     "ULC_DecoderState_Init", "ULC_DecoderState_Destroy", "ULC_DecodeBlock",
     "ULCB_ContextCreate", "ULCB_ContextDestroy", "ULCB_LastCudaError", "ULCB_ErrorString",
-    "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_Sync", "ULCB_Stream",
+    "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_DecodeStreamsIndexedDevice",
+    "ULCB_DecodeStreamsIndexed", "ULCB_Sync", "ULCB_Stream",
     "ULCB_LaunchCount", "ULCB_TestDCT4", "ULCB_TestParse",
     "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
     "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
     "ULCB_GenerateCorpusDevice", "ULCB_ConvertSamplesDevice", "ULCB_GetAvgComplexity",
 )
+
+HAS_BLOCK_INDEX = True          # ULCB_DecodeStreamsIndexed[Device]: decode with a caller-supplied block-size index
 
 MODE_VBR, MODE_CBR, MODE_ABR = 0, 1, 2
 MODE_ABR_2PASS = 3
@@ -80,6 +83,8 @@ def load():
     L.ULCB_MaxBlockBytes.restype = C.c_size_t
     L.ULCB_DecodeStreamsDevice.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, i32, vp, vp, u64]
     L.ULCB_DecodeStreams.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, i32, vp, vp, u64]
+    L.ULCB_DecodeStreamsIndexedDevice.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, vp, u64, i32, vp, vp, u64]
+    L.ULCB_DecodeStreamsIndexed.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, vp, u64, i32, vp, vp, u64]
     L.ULCB_Sync.argtypes = [vp]
     L.ULCB_Stream.argtypes = [vp]
     L.ULCB_Stream.restype = vp
@@ -168,8 +173,9 @@ class Context:
         _check(self.L, self.h, self.L.ULCB_Sync(self.h), "ULCB_Sync")
 
     # ---- host-pointer batched decode (ULCB_DecodeStreams) ----
-    def decode_streams(self, streams, n_blocks, fmt: str = "pcm16", want_bits: bool = False):
+    def decode_streams(self, streams, n_blocks, fmt: str = "pcm16", want_bits: bool = False, block_bytes=None):
         """streams: list of uint8 arrays (raw block bytes).  n_blocks: int or per-stream sequence.
+        block_bytes: optional block-size index, one uint32 sequence per stream (ULCB_DecodeStreamsIndexed).
         Returns (pcm[nStreams, maxBlocks*N, nChan], status int32[nStreams], bits uint32[nStreams, maxBlocks] | None)."""
         data, offs = pack_streams(streams)
         ns = len(streams)
@@ -183,16 +189,32 @@ class Context:
         out = np.zeros((ns, max_blk * self.block_size, self.n_chan), np.int16 if f == FMT_PCM16 else np.float32)
         status = np.zeros(ns, np.int32)
         bits = np.zeros((ns, max_blk), np.uint32) if want_bits else None
-        rc = self.L.ULCB_DecodeStreams(
-            self.h, ns, data.ctypes.data, offs.ctypes.data, nb_arr.ctypes.data if nb_arr is not None else None, nb_all,
-            out.ctypes.data, stride, f, status.ctypes.data, bits.ctypes.data if want_bits else None, max_blk)
-        _check(self.L, self.h, rc, "ULCB_DecodeStreams")
+        common = (out.ctypes.data, stride, f, status.ctypes.data, bits.ctypes.data if want_bits else None, max_blk)
+        if block_bytes is None:
+            rc = self.L.ULCB_DecodeStreams(
+                self.h, ns, data.ctypes.data, offs.ctypes.data, nb_arr.ctypes.data if nb_arr is not None else None, nb_all, *common)
+            _check(self.L, self.h, rc, "ULCB_DecodeStreams")
+        else:
+            idx = np.zeros((ns, max(1, max_blk)), np.uint32)
+            for i, b in enumerate(block_bytes):
+                b = np.asarray(b, np.uint32)[:max_blk]
+                idx[i, :len(b)] = b
+            rc = self.L.ULCB_DecodeStreamsIndexed(
+                self.h, ns, data.ctypes.data, offs.ctypes.data, nb_arr.ctypes.data if nb_arr is not None else None, nb_all,
+                idx.ctypes.data, idx.shape[1], *common)
+            _check(self.L, self.h, rc, "ULCB_DecodeStreamsIndexed")
         return out, status, bits
 
     # ---- device-pointer batched decode (ULCB_DecodeStreamsDevice); pointers are plain ints ----
     def decode_streams_device(self, n_streams: int, d_bytes: int, d_offs: int, n_blocks_all: int, d_out: int,
                               out_stride: int, fmt: str = "pcm16", d_status: int = 0, d_nblocks: int = 0,
-                              d_bits: int = 0, bits_stride: int = 0):
+                              d_bits: int = 0, bits_stride: int = 0, d_block_bytes: int = 0, block_bytes_stride: int = 0):
+        if d_block_bytes:
+            rc = self.L.ULCB_DecodeStreamsIndexedDevice(self.h, n_streams, d_bytes, d_offs, d_nblocks or None, n_blocks_all,
+                                                        d_block_bytes, block_bytes_stride, d_out, out_stride, _FMT[fmt],
+                                                        d_status or None, d_bits or None, bits_stride)
+            _check(self.L, self.h, rc, "ULCB_DecodeStreamsIndexedDevice")
+            return
         rc = self.L.ULCB_DecodeStreamsDevice(self.h, n_streams, d_bytes, d_offs, d_nblocks or None, n_blocks_all,
                                              d_out, out_stride, _FMT[fmt], d_status or None, d_bits or None, bits_stride)
         _check(self.L, self.h, rc, "ULCB_DecodeStreamsDevice")

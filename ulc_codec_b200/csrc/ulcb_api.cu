@@ -38,6 +38,12 @@ struct ULCB_Context {
     void *dOut = nullptr; size_t dOutCap = 0;
     void *dAux = nullptr; size_t dAuxCap = 0;
     void *dSign = nullptr;              // noise-sign parity table (tb.signParity), rebuilt when it has to grow
+    // block-parallel decode pipeline (ulcb_decode_bp.cu): wave scratch, grown on demand
+    void *bpOff = nullptr;   size_t bpOffCap = 0;
+    void *bpDesc = nullptr;  size_t bpDescCap = 0;
+    void *bpBad = nullptr;   size_t bpBadCap = 0;
+    void *bpArena = nullptr; size_t bpArenaCap = 0;
+    void *hPlan = nullptr;   size_t hPlanCap = 0;   // pinned: stream offsets / block counts read back to plan the waves
 };
 
 namespace {
@@ -134,6 +140,16 @@ int build_tables(ULCB_Context *ctx) {
             w[k] = float2{(float)cos(a), (float)sin(a)};
         }
         if ((rc = upload(ctx, w, &tb.fftW))) return rc;
+    }
+    tb.tw32 = nullptr;
+    if (N == 2048) {
+        std::vector<float2> t(32 * 32);
+        for (int k1 = 0; k1 < 32; k1++)
+            for (int l = 0; l < 32; l++) {
+                double a = -2.0 * M_PI * (double)((l * k1) & 1023) / 1024.0;
+                t[k1 * 32 + l] = float2{(float)cos(a), (float)sin(a)};
+            }
+        if ((rc = upload(ctx, t, &tb.tw32))) return rc;
     }
     for (int sh = 0; sh < 4; sh++) {
         int S = N >> sh, M = S / 2;
@@ -299,6 +315,11 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->dOut) cudaFree(ctx->dOut);
     if (ctx->dAux) cudaFree(ctx->dAux);
     if (ctx->dSign) cudaFree(ctx->dSign);
+    if (ctx->bpOff) cudaFree(ctx->bpOff);
+    if (ctx->bpDesc) cudaFree(ctx->bpDesc);
+    if (ctx->bpBad) cudaFree(ctx->bpBad);
+    if (ctx->bpArena) cudaFree(ctx->bpArena);
+    if (ctx->hPlan) cudaFreeHost(ctx->hPlan);
     if (ctx->encWs) cudaFree(ctx->encWs);
     if (ctx->corpusLut) cudaFree(ctx->corpusLut);
     if (ctx->dAvgCx) cudaFree(ctx->dAvgCx);
@@ -316,17 +337,88 @@ int ULCB_Sync(ULCB_Context *ctx) {
     return ULCB_OK;
 }
 
+// Block-parallel pipeline (ulcb_decode_bp.cu).  hOffs / hNBlocks: host copies of the stream offsets / block counts when the
+// caller has them; otherwise they are read back from the device (one small copy + synchronise) to plan the waves.
+static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs, const uint32_t *dNBlocks,
+                     uint32_t nBlocksAll, const uint32_t *dBlockBytes, uint64_t blockBytesStride, void *dOut, uint64_t outStrideElems,
+                     int format, int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride, float *dbgCoefs,
+                     const uint64_t *hOffs, const uint32_t *hNBlocks) {
+    int rc;
+    if (!hOffs || (dNBlocks && !hNBlocks)) {
+        const size_t need = sizeof(uint64_t) * (nStreams + 1) + sizeof(uint32_t) * nStreams;
+        if (ctx->hPlanCap < need) {
+            if (ctx->hPlan) cudaFreeHost(ctx->hPlan);
+            ctx->hPlan = nullptr; ctx->hPlanCap = 0;
+            CK(ctx, cudaMallocHost(&ctx->hPlan, need));
+            ctx->hPlanCap = need;
+        }
+        uint64_t *po = (uint64_t *)ctx->hPlan;
+        uint32_t *pn = (uint32_t *)(po + nStreams + 1);
+        if (!hOffs) { CK(ctx, cudaMemcpyAsync(po, dStreamOffs, sizeof(uint64_t) * (nStreams + 1), cudaMemcpyDeviceToHost, ctx->stream)); hOffs = po; }
+        if (dNBlocks && !hNBlocks) { CK(ctx, cudaMemcpyAsync(pn, dNBlocks, sizeof(uint32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream)); hNBlocks = pn; }
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    uint32_t maxBlk = nBlocksAll;
+    if (dNBlocks) { maxBlk = 0; for (int s = 0; s < nStreams; s++) if (hNBlocks[s] > maxBlk) maxBlk = hNBlocks[s]; }
+    if (maxBlk == 0) return ULCB_OK;
+    if (maxBlk > ctx->maxBlocks) return ULCB_E_PARAM;
+    if (outStrideElems < (uint64_t)maxBlk * ctx->N * ctx->nChan) return ULCB_E_PARAM;
+    for (int s = 0; s < nStreams; s++) if (hOffs[s + 1] < hOffs[s]) return ULCB_E_PARAM;
+
+    // waves: as many streams as the arena cap holds
+    static const size_t capEnv = getenv("ULCB_BP_ARENA_MB") ? (size_t)atoll(getenv("ULCB_BP_ARENA_MB")) << 20 : (size_t)8192 << 20;
+    size_t cap = capEnv;
+    {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) { const size_t lim = (fr + ctx->bpArenaCap) / 2; if (cap > lim) cap = lim; }
+    }
+    static const int runLen = getenv("ULCB_BP_RUNLEN") ? atoi(getenv("ULCB_BP_RUNLEN")) : 32;
+    UlcbBpArgs a{};
+    a.tb = ctx->tb; a.nSignBits = ctx->tb.nSignBits;
+    a.nBlocksAll = (int)nBlocksAll; a.maxBlk = (int)maxBlk; a.runLen = runLen < 1 ? 1 : runLen;
+    a.bytes = dBytes; a.streamOffs = dStreamOffs; a.nBlocks = dNBlocks;
+    a.wend = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(dBytes) + hOffs[nStreams] + 8) & ~(uintptr_t)3);
+    a.blockBytes = dBlockBytes; a.blockBytesStride = blockBytesStride;
+    a.out = dOut; a.outStride = outStrideElems; a.status = dStatus; a.blockBits = dBlockBits; a.bitsStride = bitsStride;
+    a.dbgCoefs = dbgCoefs;
+    for (int s0 = 0; s0 < nStreams;) {
+        int s1 = s0 + 1;
+        while (s1 < nStreams && ulcb_decode_bp_arena_bytes(hOffs[s1 + 1] - hOffs[s0], s1 + 1 - s0, (int)maxBlk) <= cap) s1++;
+        const int n = s1 - s0;
+        if ((rc = grow(ctx, &ctx->bpOff, &ctx->bpOffCap, sizeof(uint32_t) * (size_t)n * (maxBlk + 1)))) return rc;
+        if ((rc = grow(ctx, &ctx->bpDesc, &ctx->bpDescCap, sizeof(UlcbBpDesc) * (size_t)n * maxBlk))) return rc;
+        if ((rc = grow(ctx, &ctx->bpBad, &ctx->bpBadCap, sizeof(int32_t) * (size_t)n))) return rc;
+        if ((rc = grow(ctx, &ctx->bpArena, &ctx->bpArenaCap, ulcb_decode_bp_arena_bytes(hOffs[s1] - hOffs[s0], n, (int)maxBlk)))) return rc;
+        a.s0 = s0; a.nStreams = n; a.base0 = hOffs[s0];
+        a.blkOff = (uint32_t *)ctx->bpOff; a.desc = (UlcbBpDesc *)ctx->bpDesc; a.firstBad = (int32_t *)ctx->bpBad; a.arena = (uint8_t *)ctx->bpArena;
+        int nl = 0;
+        CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, dBlockBytes != nullptr, ctx->stream, &nl));
+        ctx->launches += (uint64_t)nl;
+        s0 = s1;
+    }
+    return ULCB_OK;
+}
+
 static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs,
                          const uint32_t *dNBlocks, uint32_t nBlocksAll, void *dOut, uint64_t outStrideElems,
                          int format, int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride,
-                         UlcbStreamState *state, float *statePend, float *dbgCoefs = nullptr) {
+                         UlcbStreamState *state, float *statePend, float *dbgCoefs = nullptr,
+                         const uint32_t *dBlockBytes = nullptr, uint64_t blockBytesStride = 0,
+                         const uint64_t *hOffs = nullptr, const uint32_t *hNBlocks = nullptr) {
     if (!ctx || nStreams < 0 || !dBytes || !dStreamOffs || !dOut) return ULCB_E_PARAM;
     if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
     // the noise-sign table covers maxBlocksPerStream blocks; per-stream counts on the device are bounded inside the kernels
     if (!dNBlocks && !state && nBlocksAll > ctx->maxBlocks) return ULCB_E_PARAM;
     if (dBlockBits && bitsStride < (dNBlocks ? 1u : nBlocksAll)) return ULCB_E_PARAM;
+    if (dBlockBytes && blockBytesStride < (dNBlocks ? 1u : nBlocksAll)) return ULCB_E_PARAM;
     CK(ctx, cudaSetDevice(ctx->device));
+    // kernel choice: the block-parallel pipeline where it applies (BlockSize 2048 stereo, whole fresh streams); the
+    // stream-serial kernels for every other shape, for carried state (drop-in API), and on request (A/B timing, tests)
+    static const bool forceSerial = getenv("ULCB_DECODE_GENERIC") != nullptr || getenv("ULCB_DECODE_WS") != nullptr;
+    if (!state && !forceSerial && ulcb_decode_bp_supported(ctx->tb, ctx->nChan))
+        return decode_bp(ctx, nStreams, dBytes, dStreamOffs, dNBlocks, nBlocksAll, dBlockBytes, blockBytesStride, dOut, outStrideElems,
+                         format, dStatus, dBlockBits, bitsStride, dbgCoefs, hOffs, hNBlocks);
     UlcbDecodeArgs a{};
     a.tb = ctx->tb;
     a.nStreams = nStreams; a.nBlocksAll = (int)nBlocksAll;
@@ -346,9 +438,18 @@ int ULCB_DecodeStreamsDevice(ULCB_Context *ctx, int nStreams, const uint8_t *dBy
                          dStatus, dBlockBits, bitsStride, nullptr, nullptr);
 }
 
-int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, const uint64_t *streamOffs,
-                       const uint32_t *nBlocks, uint32_t nBlocksAll, void *out, uint64_t outStrideElems, int format,
-                       int32_t *status, uint32_t *blockBits, uint64_t bitsStride) {
+int ULCB_DecodeStreamsIndexedDevice(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs,
+                                    const uint32_t *dNBlocks, uint32_t nBlocksAll, const uint32_t *dBlockBytes, uint64_t blockBytesStride,
+                                    void *dOut, uint64_t outStrideElems, int format, int32_t *dStatus, uint32_t *dBlockBits,
+                                    uint64_t bitsStride) {
+    if (!dBlockBytes) return ULCB_E_PARAM;
+    return decode_device(ctx, nStreams, dBytes, dStreamOffs, dNBlocks, nBlocksAll, dOut, outStrideElems, format,
+                         dStatus, dBlockBits, bitsStride, nullptr, nullptr, nullptr, dBlockBytes, blockBytesStride);
+}
+
+static int decode_host(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, const uint64_t *streamOffs,
+                       const uint32_t *nBlocks, uint32_t nBlocksAll, const uint32_t *blockBytes, uint64_t blockBytesStride,
+                       void *out, uint64_t outStrideElems, int format, int32_t *status, uint32_t *blockBits, uint64_t bitsStride) {
     if (!ctx || nStreams < 0 || !bytes || !streamOffs || !out) return ULCB_E_PARAM;
     if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
@@ -358,13 +459,14 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     uint32_t maxBlk = nBlocksAll;
     if (nBlocks) { maxBlk = 0; for (int s = 0; s < nStreams; s++) if (nBlocks[s] > maxBlk) maxBlk = nBlocks[s]; }
     if (outStrideElems < (uint64_t)maxBlk * ctx->N * ctx->nChan) return ULCB_E_PARAM;
-    if (maxBlk > ctx->maxBlocks || (blockBits && bitsStride < maxBlk)) return ULCB_E_PARAM;
+    if (maxBlk > ctx->maxBlocks || (blockBits && bitsStride < maxBlk) || (blockBytes && blockBytesStride < maxBlk)) return ULCB_E_PARAM;
     for (int s = 0; s < nStreams; s++) if (streamOffs[s + 1] < streamOffs[s]) return ULCB_E_PARAM;
     const size_t outBytes = (size_t)nStreams * outStrideElems * elem;
-    // aux layout: offs | nBlocks | status | bits
+    // aux layout: offs | nBlocks | status | bits | block-size index
     const size_t offOffs = 0, offNb = offOffs + sizeof(uint64_t) * (nStreams + 1);
     const size_t offSt = offNb + sizeof(uint32_t) * nStreams, offBits = (offSt + sizeof(int32_t) * nStreams + 15) & ~(size_t)15;
-    const size_t auxBytes = offBits + (blockBits ? sizeof(uint32_t) * nStreams * bitsStride : 0);
+    const size_t offIdx = offBits + (blockBits ? sizeof(uint32_t) * nStreams * bitsStride : 0);
+    const size_t auxBytes = offIdx + (blockBytes ? sizeof(uint32_t) * nStreams * blockBytesStride : 0);
     int rc;
     // PCM out is ~11x the bytes in.  When the caller's buffer is page-locked (cudaHostAlloc / cudaHostRegister) the kernel
     // stores straight into it over PCIe, so the transfer overlaps the decode instead of following it; pageable buffers
@@ -384,15 +486,31 @@ int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     CK(ctx, cudaMemsetAsync((char *)ctx->dIn + nBytes, 0, 64, ctx->stream));
     CK(ctx, cudaMemcpyAsync(aux + offOffs, streamOffs, sizeof(uint64_t) * (nStreams + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (nBlocks) CK(ctx, cudaMemcpyAsync(aux + offNb, nBlocks, sizeof(uint32_t) * nStreams, cudaMemcpyHostToDevice, ctx->stream));
+    if (blockBytes) CK(ctx, cudaMemcpyAsync(aux + offIdx, blockBytes, sizeof(uint32_t) * nStreams * blockBytesStride, cudaMemcpyHostToDevice, ctx->stream));
     rc = decode_device(ctx, nStreams, (const uint8_t *)ctx->dIn, (const uint64_t *)(aux + offOffs),
                        nBlocks ? (const uint32_t *)(aux + offNb) : nullptr, nBlocksAll, dOutPtr ? dOutPtr : ctx->dOut, outStrideElems, format,
-                       (int32_t *)(aux + offSt), blockBits ? (uint32_t *)(aux + offBits) : nullptr, bitsStride, nullptr, nullptr);
+                       (int32_t *)(aux + offSt), blockBits ? (uint32_t *)(aux + offBits) : nullptr, bitsStride, nullptr, nullptr, nullptr,
+                       blockBytes ? (const uint32_t *)(aux + offIdx) : nullptr, blockBytesStride, streamOffs, nBlocks);
     if (rc) return rc;
     if (!dOutPtr) CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) CK(ctx, cudaMemcpyAsync(status, aux + offSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
     if (blockBits) CK(ctx, cudaMemcpyAsync(blockBits, aux + offBits, sizeof(uint32_t) * nStreams * bitsStride, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return ULCB_OK;
+}
+
+int ULCB_DecodeStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, const uint64_t *streamOffs,
+                       const uint32_t *nBlocks, uint32_t nBlocksAll, void *out, uint64_t outStrideElems, int format,
+                       int32_t *status, uint32_t *blockBits, uint64_t bitsStride) {
+    return decode_host(ctx, nStreams, bytes, streamOffs, nBlocks, nBlocksAll, nullptr, 0, out, outStrideElems, format, status, blockBits, bitsStride);
+}
+
+int ULCB_DecodeStreamsIndexed(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, const uint64_t *streamOffs,
+                              const uint32_t *nBlocks, uint32_t nBlocksAll, const uint32_t *blockBytes, uint64_t blockBytesStride,
+                              void *out, uint64_t outStrideElems, int format, int32_t *status, uint32_t *blockBits, uint64_t bitsStride) {
+    if (!blockBytes) return ULCB_E_PARAM;
+    return decode_host(ctx, nStreams, bytes, streamOffs, nBlocks, nBlocksAll, blockBytes, blockBytesStride, out, outStrideElems, format,
+                       status, blockBits, bitsStride);
 }
 
 int ULCB_TestParse(ULCB_Context *ctx, const uint8_t *bytes, uint64_t nBytes, uint32_t nBlocks, float *coefs, uint32_t *blockBits) {

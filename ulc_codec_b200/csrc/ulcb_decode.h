@@ -39,3 +39,37 @@ cudaError_t ulcb_decode_launch(const UlcbDecodeArgs &args, int nChan, int pcm16,
 // routes to it when it applies; ULCB_DECODE_GENERIC=1 in the environment forces the generic kernel (A/B timing).
 bool        ulcb_decode_ws_supported(const UlcbDecodeArgs &args, int nChan);
 cudaError_t ulcb_decode_ws_launch(const UlcbDecodeArgs &args, int pcm16, int smCount, cudaStream_t stream);
+
+// ---- block-parallel pipeline (ulcb_decode_bp.cu): BlockSize 2048, stereo, fresh streams ----
+struct UlcbBpDesc {                   // one per block, written by the parse kernel
+    uint32_t bits;                    // bits consumed as ULC_DecodeBlock returns them; 0 = not decodable
+    uint32_t wcRuns;                  // window control | run records of channel 0 << 8 | of channel 1 << 20
+    uint32_t draws;                   // noise draws of the block; after the scan: draws before the block in its stream
+    uint16_t nCoef[2];                // coefficient words per channel
+};
+
+struct UlcbBpArgs {
+    UlcbTables      tb;
+    uint64_t        nSignBits;
+    int             s0, nStreams;     // this wave: streams [s0, s0 + nStreams) of the call
+    int             nBlocksAll, maxBlk, runLen;
+    const uint8_t  *bytes;            // all streams of the call
+    const uint32_t *wend;             // first word that must not be read (end of bytes + slack, aligned down)
+    const uint64_t *streamOffs;       // [call streams + 1]
+    uint64_t        base0;            // streamOffs[s0]
+    const uint32_t *nBlocks;          // [call streams] or nullptr
+    const uint32_t *blockBytes;       // caller's block-size index [call streams][blockBytesStride], or nullptr (walk)
+    uint64_t        blockBytesStride;
+    void           *out; uint64_t outStride;
+    int32_t        *status; uint32_t *blockBits; uint64_t bitsStride;
+    float          *dbgCoefs;
+    // wave scratch
+    uint32_t       *blkOff;           // [nStreams][maxBlk + 1] byte offset of every block in its stream
+    UlcbBpDesc     *desc;             // [nStreams][maxBlk]
+    int32_t        *firstBad;         // [nStreams] first undecodable block (nBlocks when none)
+    uint8_t        *arena;            // sparse block content
+};
+
+bool        ulcb_decode_bp_supported(const UlcbTables &tb, int nChan);
+size_t      ulcb_decode_bp_arena_bytes(uint64_t payloadBytes, int nStreams, int maxBlk);
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, bool haveIndex, cudaStream_t stream, int *launches);

@@ -1,0 +1,873 @@
+// ulcb_decode_bp.cu - block-parallel batched decoder (BlockSize 2048, stereo): the benchmark path of configs[1].
+//
+// libulc/ulcDecoder.c:198-302 decodes a stream strictly block after block, but every dependency between blocks is
+// either known from a block-size index or a cheap scan:
+//
+//   byte offset of block k+1     a block-size index: the one this library's encoder emits (dBlockBytes), the caller's,
+//                                or - for foreign .ulc payloads, which carry none (tools/ulc_Helper.h:10-20) - the
+//                                token-length walk of bp_walk_kernel (what tools/ulcDecodeTool.c:153-164 does by decoding)
+//   position in the noise RNG    per-block draw counts (parse) -> exclusive scan per stream -> sign-parity table
+//   LastSubBlockSize             the previous block's window-control nybble
+//   half-block lap               a function of the previous block's coefficients ONLY (the un-fold keeps the first S/2
+//                                DCT outputs, Fourier_IMDCT_Template.h:66-93; a window-switched block's delay line holds
+//                                nothing older than the block itself), so a run of consecutive blocks can start anywhere
+//                                after re-doing ONE block
+//
+// Pipeline (per wave of streams, all on the context's stream):
+//   bp_index_kernel / bp_walk_kernel   block byte offsets per stream
+//   bp_parse_kernel      ONE LANE PER BLOCK walks the nybble grammar (ulcDecoder.c:99-197) sequentially - about 1000 tokens of
+//                        ~50 instructions instead of the 8-phase speculative resolver - and writes the block's content in
+//                        sparse form to an HBM arena: one 32-bit word per coded coefficient (position | bf16 value: every
+//                        value the format can express is n * 2^-e with n <= 64, exact in bf16), one 16-byte record per noise
+//                        run / decaying tail, plus a 16-byte descriptor (bits consumed, window control, draw count)
+//   bp_scan_kernel       per stream: exclusive scan of the draw counts, first undecodable block, status / blockBits out
+//   bp_transform_kernel  one 64-thread CTA (Mid warp + Side warp) per (stream, run of consecutive blocks): the block's words
+//                        arrive by TMA bulk copy (cp.async.bulk + mbarrier) while the previous block is transformed, are
+//                        scattered into the FFT tile, noise runs are expanded eight at a time (4 lanes each) from the
+//                        sign-parity table, then DCT-IV as 32 x 32 register FFT, un-fold against the lane-private pending
+//                        tail, M/S undo, PCM16 / float stores.
+//
+// Traffic per block: bytes in (~0.74 KB) + sparse words written and read back (~2 x 3 KB) + PCM out (8 KB).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "ulcb_dct.cuh"
+#include "ulcb_decode.h"
+
+namespace {
+
+constexpr int N = 2048, H = N / 2, NCH = 2;
+constexpr int ZROW = 33;                              // padded row of the 32 x 32 complex work tile
+constexpr int RECSLOT = 1024;                         // words of the TMA landing slot per warp
+constexpr unsigned FULLM = 0xffffffffu;
+
+// Decimation layouts, one nybble per sub-block, LSB first: bits0-2 shift, bit3 transient
+// (libulc/ulcHelper.h:24-46, FormatSpecs.md:35-51)
+__constant__ uint16_t kLayoutBp[16] = {
+    0x0000, 0x0008, 0x0019, 0x0091, 0x012A, 0x01A2, 0x02A1, 0x0A21,
+    0x123B, 0x12B3, 0x13B2, 0x1B32, 0x23B1, 0x2B31, 0x3B21, 0xB321,
+};
+
+__device__ __forceinline__ float quant_scale(int q) {      // ulcDecoder.c:96-98
+    return 0x1.0p-31f * (float)((1u << 26) >> (q & 31));
+}
+
+// arena offset (bytes) of the record region of the block that starts at byte `a` of the wave's payload and has global
+// index `gidx` in the wave: 8 bytes per payload byte (one word per nybble bounds the words a block can produce: a coefficient
+// costs one nybble and one word, a run four nybbles and four words) plus 32 bytes of slack per block, 16-byte aligned.
+__device__ __forceinline__ uint64_t region_start(uint64_t a, uint64_t gidx) { return 16ull * ((a + 1) >> 1) + 32ull * gidx; }
+__device__ __forceinline__ uint64_t region_bytes(uint32_t len) { return 16ull * ((len + 1u) >> 1) + 16ull; }
+
+// ================================================================================================
+// Sequential token walk of one block by one lane (ulcDecoder.c:99-197, 211-231)
+// ================================================================================================
+struct ParseOut { uint32_t nyb, wc, draws, nCoef0, nCoefTot, nRun0, nRunTot; };
+
+template <bool EMIT>
+__device__ __forceinline__ bool parse_block(const uint8_t *p, const uint32_t *wend, uint32_t maxNyb, const uint16_t *lut,
+                                            uint32_t *up, uint4 *down, ParseOut &o) {
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(p - mis);
+    auto ldw = [&](const uint32_t *q) -> uint32_t { return q < wend ? __ldg(q) : 0u; };
+    uint64_t buf = ((uint64_t)ldw(wp) | ((uint64_t)ldw(wp + 1) << 32)) >> (8 * mis);
+    int navail = 16 - 2 * (int)mis;
+    uint32_t nextw = ldw(wp + 2);
+    wp += 3;
+    uint32_t consumed = 0;
+#define BP_SKIP(k)                                                                                   \
+    do {                                                                                             \
+        const int k_ = (k);                                                                          \
+        buf >>= 4 * k_; navail -= k_; consumed += (uint32_t)k_;                                      \
+        if (navail <= 8) { buf |= (uint64_t)nextw << (4 * navail); navail += 8; nextw = ldw(wp); wp++; } \
+    } while (0)
+    uint32_t e0 = 0, e1 = 0, e2 = 0, nw = 0;
+#define BP_EMITW(val)                                                                                \
+    do {                                                                                             \
+        const uint32_t v_ = (val), s_ = nw & 3u;                                                     \
+        if (s_ == 0) e0 = v_; else if (s_ == 1) e1 = v_; else if (s_ == 2) e2 = v_;                  \
+        else *reinterpret_cast<uint4 *>(up + (nw - 3)) = make_uint4(e0, e1, e2, v_);                 \
+        nw++;                                                                                        \
+    } while (0)
+
+    uint32_t x = (uint32_t)buf;
+    uint32_t wc;
+    if (x & 8u) { wc = x & 0xffu; BP_SKIP(2); }            // ulcDecoder.c:211-216
+    else        { wc = (x & 15u) | 0x10u; BP_SKIP(1); }
+    const uint32_t layout = kLayoutBp[wc >> 4];
+    uint32_t pat = layout;
+    int c = 0, pos = 0, subEnd = N >> (pat & 7);
+    bool hdr = true, ok = true;
+    int q = 0, eb = -1;                                     // eb = bf16 exponent bias of the quantiser, -1 = scale 0
+    uint32_t draws = 0, nRun = 0, nCoef0 = 0, nRun0 = 0;
+    for (;;) {
+        x = (uint32_t)buf;
+        const uint32_t v0 = x & 15u, v1 = (x >> 4) & 15u;
+        int len = 1, adv = 0;
+        if (hdr) {
+            // sub-block header: bare quantiser (ulcDecoder.c:103-112).  A lone Fh is an invalid lead-in: the reference's
+            // shift by -2 gives scale 0 on x86
+            hdr = false;
+            if (v0 == 15u) q = 30;
+            else if (v0 == 14u) { len = 2; if (v1 == 15u) adv = subEnd - pos; else q = 14 + (int)v1; }
+            else q = (int)v0;
+            eb = q > 26 ? -1 : (5 + q) << 7;
+        } else if (!((0x8103u >> v0) & 1u)) {
+            // -7..-2, +2..+7: sign * v^2 * Quant (ulcDecoder.c:119-124)
+            adv = 1;
+            if (EMIT && eb >= 0) BP_EMITW(((uint32_t)pos << 16) | (uint32_t)(lut[v0] - eb));
+        } else if (v0 == 0u) {
+            len = 2; adv = (int)v1 + 1;                     // 0h,Xh: 1..16 zeros
+        } else {
+            const uint32_t v2 = (x >> 8) & 15u, v3 = (x >> 12) & 15u, b12 = (v1 << 4) | v2;
+            if (v0 == 1u) { len = 3; adv = (int)b12 + 33; } // 1h,Yh,Xh: 33..288 zeros
+            else if (v0 == 8u) {                            // 8h,Zh,Yh,Xh: 16..527 noise, level ((X>>1)+1)^2 * Quant / 4
+                len = 4; adv = (int)((b12 << 1) | (v3 & 1u)) + 16;
+                if (EMIT && adv <= subEnd - pos) {
+                    const uint32_t amp = eb >= 0 ? (uint32_t)(lut[16 + (v3 >> 1)] - eb) : 0u;
+                    *(down - 1 - nRun) = make_uint4((uint32_t)pos, (uint32_t)adv, draws, amp);
+                }
+                nRun++;
+                draws += (uint32_t)adv;
+            } else {
+                if (v1 < 14u) { len = 2; q = (int)v1; eb = (5 + q) << 7; }                     // Fh,0h..Dh
+                else if (v1 == 14u) {
+                    len = 3;
+                    if (v2 == 15u) adv = subEnd - pos;                                            // Fh,Eh,Fh: zeros to the end
+                    else { q = 14 + (int)v2; eb = q > 26 ? -1 : (5 + q) << 7; }                 // Fh,Eh,0h..Ch (Dh,Eh: scale 0)
+                } else {                                                                          // Fh,Fh,Zh,Yh,Xh: decaying noise to the end
+                    len = 5; adv = subEnd - pos;
+                    if (EMIT) *(down - 1 - nRun) = make_uint4((uint32_t)pos, (uint32_t)adv, draws,
+                                                              0x80000000u | ((x >> 8) & 0xfffu) | ((uint32_t)q << 12));
+                    nRun++;
+                    draws += (uint32_t)adv;
+                }
+            }
+        }
+        if (adv > subEnd - pos) { ok = false; break; }     // run overshoot: corrupt (ulcDecoder.c:127,139,154)
+        pos += adv;
+        BP_SKIP(len);
+        if (consumed > maxNyb) { ok = false; break; }      // ran off the bytes this block may use
+        if (pos == subEnd) {
+            pat >>= 4;
+            if (!pat) {
+                if (c == 0) { nCoef0 = nw; nRun0 = nRun; }
+                if (++c == NCH) break;
+                pat = layout; pos = 0;
+            }
+            subEnd = pos + (N >> (pat & 7));
+            hdr = true;
+        }
+    }
+    if (EMIT && (nw & 3u)) *reinterpret_cast<uint4 *>(up + (nw & ~3u)) = make_uint4(e0, e1, e2, 0u);
+#undef BP_SKIP
+#undef BP_EMITW
+    o.nyb = consumed; o.wc = wc; o.draws = draws; o.nCoef0 = nCoef0; o.nCoefTot = nw; o.nRun0 = nRun0; o.nRunTot = nRun;
+    return ok;
+}
+
+// bf16 patterns before the quantiser's exponent (5 + q) is subtracted: [0..15] sign * v^2 for coefficient nybble v (two's
+// complement), [16..23] lv^2 / 4 for noise level lv - 1
+__device__ __forceinline__ void init_lut(uint16_t *lut) {
+    const int t = threadIdx.x;
+    if (t < 24) {
+        float f;
+        if (t < 16) { const int sv = (t ^ 8) - 8; f = (float)(sv < 0 ? -(sv * sv) : sv * sv); }
+        else { const int lv = t - 15; f = (float)(lv * lv) * 0.25f; }
+        lut[t] = (uint16_t)(__float_as_uint(f) >> 16);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// block offsets from a caller-supplied block-size index: one warp per stream, exclusive scan
+// ------------------------------------------------------------------------------------------------
+__global__ void bp_index_kernel(UlcbBpArgs a) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= a.nStreams) return;
+    const int gs = a.s0 + s;
+    const int nb = a.nBlocks ? (int)a.nBlocks[gs] : a.nBlocksAll;
+    const uint32_t *bb = a.blockBytes + (size_t)gs * a.blockBytesStride;
+    uint32_t *off = a.blkOff + (size_t)s * (a.maxBlk + 1);
+    const uint64_t slen = a.streamOffs[gs + 1] - a.streamOffs[gs];
+    uint64_t run = 0;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        uint32_t v = b < nb ? bb[b] : 0u;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(FULLM, inc, d); if (lane >= d) inc += t; }
+        uint64_t ex = run + inc - v;
+        if (b < nb) off[b] = (uint32_t)(ex < slen ? ex : slen);      // a block that starts at / beyond the end is undecodable
+        run += __shfl_sync(FULLM, inc, 31);
+    }
+    if (lane == 0) off[nb] = (uint32_t)(run < slen ? run : slen);
+}
+
+// ------------------------------------------------------------------------------------------------
+// foreign streams (no index): one lane per stream walks the token lengths block after block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bp_walk_kernel(UlcbBpArgs a) {
+    __shared__ uint16_t lut[24];
+    init_lut(lut);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.nStreams) return;
+    const int gs = a.s0 + s;
+    const int nb = a.nBlocks ? (int)a.nBlocks[gs] : a.nBlocksAll;
+    uint32_t *off = a.blkOff + (size_t)s * (a.maxBlk + 1);
+    const uint64_t sbeg = a.streamOffs[gs], slen = a.streamOffs[gs + 1] - sbeg;
+    uint64_t pos = 0;
+    bool dead = false;
+    for (int b = 0; b < nb; b++) {
+        off[b] = (uint32_t)pos;
+        if (!dead && pos < slen) {
+            ParseOut o;
+            const uint64_t left = slen - pos;
+            const uint32_t maxNyb = left > 0x3fffffffull ? 0x7fffffffu : (uint32_t)(2 * left);
+            if (parse_block<false>(a.bytes + sbeg + pos, a.wend, maxNyb, lut, nullptr, nullptr, o)) pos += (o.nyb + 1) >> 1;
+            else dead = true;                                       // the rest of the stream cannot be located (README.md:33: no resync)
+        } else dead = true;
+    }
+    off[nb] = (uint32_t)pos;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parse: one lane per block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bp_parse_kernel(UlcbBpArgs a) {
+    __shared__ uint16_t lut[24];
+    init_lut(lut);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)(gid / a.maxBlk), b = (int)(gid - (long long)s * a.maxBlk);
+    if (s >= a.nStreams) return;
+    const int gs = a.s0 + s;
+    const int nb = a.nBlocks ? (int)a.nBlocks[gs] : a.nBlocksAll;
+    if (b >= nb) return;
+    const uint32_t *off = a.blkOff + (size_t)s * (a.maxBlk + 1);
+    const uint32_t o0 = off[b], o1 = off[b + 1];
+    const uint64_t sbeg = a.streamOffs[gs];
+    UlcbBpDesc d;
+    d.bits = 0; d.wcRuns = 0x10; d.draws = 0; d.nCoef[0] = d.nCoef[1] = 0;
+    if (o1 > o0) {
+        const uint32_t len = o1 - o0;
+        const uint64_t gidx = (uint64_t)s * (a.maxBlk + 1) + b;
+        uint8_t *reg = a.arena + region_start(sbeg - a.base0 + o0, gidx);
+        ParseOut po;
+        const bool ok = parse_block<true>(a.bytes + sbeg + o0, a.wend, 2 * len, lut, reinterpret_cast<uint32_t *>(reg),
+                                          reinterpret_cast<uint4 *>(reg + region_bytes(len)), po);
+        // the index must agree with the grammar: the block ends inside its last byte (ulcEncoder_Encode.c:357-358)
+        if (ok && ((po.nyb + 1) >> 1) == len) {
+            d.bits = po.nyb * 4u;                                   // what ULC_DecodeBlock returns (ulcDecoder.c:301)
+            d.wcRuns = po.wc | (po.nRun0 << 8) | ((po.nRunTot - po.nRun0) << 20);
+            d.draws = po.draws;
+            d.nCoef[0] = (uint16_t)po.nCoef0; d.nCoef[1] = (uint16_t)(po.nCoefTot - po.nCoef0);
+        }
+    }
+    a.desc[(size_t)s * a.maxBlk + b] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan: one warp per stream - noise-draw offsets, first undecodable block, status and blockBits
+// ------------------------------------------------------------------------------------------------
+__global__ void bp_scan_kernel(UlcbBpArgs a) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= a.nStreams) return;
+    const int gs = a.s0 + s;
+    const int nb = a.nBlocks ? (int)a.nBlocks[gs] : a.nBlocksAll;
+    UlcbBpDesc *desc = a.desc + (size_t)s * a.maxBlk;
+    uint64_t run = 0;
+    int firstBad = -1;
+    for (int b0 = 0; b0 < nb && firstBad < 0; b0 += 32) {
+        const int b = b0 + lane;
+        uint32_t dr = 0, bits = 1;
+        if (b < nb) { dr = desc[b].draws; bits = desc[b].bits; }
+        uint64_t inc = dr;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(FULLM, inc, d); if (lane >= d) inc += t; }
+        const uint64_t ex = run + inc - dr;
+        // undecodable: grammar / index error, or noise draws beyond the sign table the context was created for
+        const bool bad = bits == 0 || ex + dr + 128ull > a.nSignBits;
+        const unsigned bal = __ballot_sync(FULLM, bad);
+        if (bal) firstBad = b0 + __ffs(bal) - 1;
+        if (b < nb && (firstBad < 0 || b < firstBad)) desc[b].draws = (uint32_t)ex;
+        run += __shfl_sync(FULLM, inc, 31);
+    }
+    if (a.blockBits) {
+        uint32_t *bo = a.blockBits + (size_t)gs * a.bitsStride;
+        for (int b = lane; b < nb; b += 32) bo[b] = (firstBad < 0 || b < firstBad) ? desc[b].bits : 0u;
+    }
+    if (lane == 0) {
+        a.firstBad[s] = firstBad < 0 ? nb : firstBad;
+        if (a.status) a.status[gs] = firstBad;                      // -1 = every block decoded
+    }
+}
+
+// ================================================================================================
+// transform
+// ================================================================================================
+__host__ __device__ constexpr int brev5(int x) {
+    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+__device__ __forceinline__ constexpr float cos32(int k) {
+    constexpr float t[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f,
+                             0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f, 0.0f, -0.19509032201612825f,
+                             -0.38268343236508978f, -0.55557023301960218f, -0.70710678118654757f, -0.83146961230254524f,
+                             -0.92387953251128674f, -0.98078528040323043f};
+    return t[k];
+}
+__device__ __forceinline__ constexpr float sin32(int k) { return k < 8 ? cos32(8 - k) : -cos32(24 - k); }
+
+// 32-point forward FFT (e^{-2 pi i nk/32}) on registers, radix-2 decimation in frequency:
+// natural order in, X[brev5(r)] left in register r.
+__device__ __forceinline__ void fft32(float (&xr)[32], float (&xi)[32]) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            if ((i & half) == 0) {
+                const int j = i + half, k = (i & (half - 1)) << s;
+                const float ar = xr[i], ai = xi[i], br = xr[j], bi = xi[j];
+                xr[i] = ar + br; xi[i] = ai + bi;
+                const float dr = ar - br, di = ai - bi;
+                if (k == 0)      { xr[j] = dr; xi[j] = di; }
+                else if (k == 8) { xr[j] = di; xi[j] = -dr; }
+                else {
+                    const float c = cos32(k), sn = sin32(k);
+                    xr[j] = dr * c + di * sn;
+                    xi[j] = di * c - dr * sn;
+                }
+            }
+        }
+    }
+}
+
+// time index held by k-layout slot k
+__device__ __forceinline__ int slot_time(int k) { return k >= N / 4 ? 2 * k - H : H - 1 - 2 * k; }
+
+template <bool PCM16>
+__device__ __forceinline__ void store_pairs(void *outBlk, int slotIdx, float l0, float r0, float l1, float r1);
+template <>
+__device__ __forceinline__ void store_pairs<false>(void *outBlk, int slotIdx, float l0, float r0, float l1, float r1) {
+    __stcs(reinterpret_cast<float4 *>(outBlk) + slotIdx, make_float4(l0, r0, l1, r1));
+}
+__device__ __forceinline__ uint32_t pcm16_pair(float l, float r) {   // tools/WavIO_Helper.c:57-63: clamp, lrintf
+    l = fminf(fmaxf(l * 32768.0f, -32768.0f), 32767.0f);
+    r = fminf(fmaxf(r * 32768.0f, -32768.0f), 32767.0f);
+    return (uint32_t)(uint16_t)(int16_t)__float2int_rn(l) | ((uint32_t)(uint16_t)(int16_t)__float2int_rn(r) << 16);
+}
+template <>
+__device__ __forceinline__ void store_pairs<true>(void *outBlk, int slotIdx, float l0, float r0, float l1, float r1) {
+    __stcs(reinterpret_cast<uint2 *>(outBlk) + slotIdx, make_uint2(pcm16_pair(l0, r0), pcm16_pair(l1, r1)));
+}
+
+struct Tail { int start, end; float amp, l2; };     // decaying noise to the end of a sub-block (ulcDecoder.c:172-186)
+
+struct WarpSm {
+    float2   zb[32 * ZROW];       // FFT tile / coefficient words / short-block scratch / output swap
+    float    pend[H];             // pending tail (k-layout or time order)
+    uint32_t rec[RECSLOT];        // TMA landing slot: this channel's coefficient words of the next block (noise work list in between)
+    Tail     tail[8];
+    int      nTails, pad[3];
+};
+struct CtaSm {
+    WarpSm w[2];
+    unsigned long long mbar[2];
+};
+constexpr int COEF16_OFS = 4224;  // byte offset of the bf16 coefficient array of a window-switched block inside zb (the
+                                  // sub-block scratch occupies the first 4 KB)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();                 // a copy that never lands is a bug, not a reason to hang the GPU
+    }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+// what one warp needs to know about one block
+struct BlkInfo {
+    uint32_t bits, wc, drawBase;
+    int nCoef, nRuns, runIdx0;      // this channel's coefficient words / run records; index of its first run record
+    const uint32_t *words;          // this channel's first coefficient word (global)
+    const uint4 *runsEnd;           // end of the block's region: run record i sits at runsEnd[-1 - i]
+};
+
+__device__ __forceinline__ BlkInfo load_info(const UlcbBpArgs &a, int s, int b, int c, const uint32_t *off, uint64_t sbegRel) {
+    const UlcbBpDesc d = a.desc[(size_t)s * a.maxBlk + b];
+    BlkInfo bi;
+    bi.bits = d.bits; bi.wc = d.wcRuns & 0xffu; bi.drawBase = d.draws;
+    const int nRun0 = (d.wcRuns >> 8) & 0xfff, nRun1 = d.wcRuns >> 20;
+    bi.nCoef = d.nCoef[c]; bi.nRuns = c ? nRun1 : nRun0; bi.runIdx0 = c ? nRun0 : 0;
+    const uint32_t o0 = off[b], len = off[b + 1] - o0;
+    const uint8_t *reg = a.arena + region_start(sbegRel + o0, (uint64_t)s * (a.maxBlk + 1) + b);
+    bi.words = reinterpret_cast<const uint32_t *>(reg) + (c ? d.nCoef[0] : 0);
+    bi.runsEnd = reinterpret_cast<const uint4 *>(reg + region_bytes(len));
+    return bi;
+}
+
+// Issue the bulk copy of up to RECSLOT words of this channel starting at word `done` (lane 0 only).  The source is
+// aligned down to 16 bytes; returns through `skew` how many leading words of the slot belong to something else.
+__device__ __forceinline__ int issue_words(WarpSm &w, unsigned long long *mb, const BlkInfo &bi, int done, int lane, int &skew) {
+    const uintptr_t src = reinterpret_cast<uintptr_t>(bi.words + done);
+    skew = (int)((src >> 2) & 3u);
+    int cnt = bi.nCoef - done;
+    if (cnt > RECSLOT - skew) cnt = RECSLOT - skew;
+    if (cnt > 0 && lane == 0) {
+        const unsigned bytes = (unsigned)(((skew + cnt) * 4 + 15) & ~15);
+        mbar_expect_tx(mb, bytes);
+        tma_load(w.rec, reinterpret_cast<const void *>(src - 4 * (uintptr_t)skew), bytes, mb);
+    }
+    return cnt;
+}
+
+// Noise fill from the run records (ulcDecoder.c:156-160,179-184): the sign of draw g+i of a run that starts at draw g is
+// parity[g+i+1] ^ parity[g].  The runs of a channel (a few dozen, 16..527 coefficients each, ~25 typical) are cut into items
+// of 16 coefficient words; the warp works through the flat item list eight items at a time, four lanes per item, four
+// words per lane, so that long and short runs cost the same per coefficient.  The item list lives in the (idle) TMA slot.
+// LONGBLK: coefficient word n lives in the .x of tile slot [n / 32][n % 32]; otherwise in the dense bf16 array.
+struct RunRec { int s, e; uint32_t g0, amp2, flip, pad; };
+constexpr int MAXITEMS = 2 * (RECSLOT - 32 * 6) ;   // u16 items behind 32 run records
+
+template <bool LONGBLK>
+__device__ __noinline__ void noise_fill(WarpSm &w, const BlkInfo &bi, const uint32_t *__restrict__ par, int lane) {
+    const int grp = lane >> 2, j = lane & 3;
+    uint32_t *dense = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(w.zb) + COEF16_OFS);
+    RunRec *rt = reinterpret_cast<RunRec *>(w.rec);
+    uint16_t *items = reinterpret_cast<uint16_t *>(w.rec + 32 * 6);
+    auto word = [&](int n) -> uint32_t * {
+        return LONGBLK ? reinterpret_cast<uint32_t *>(&w.zb[(n >> 5) * ZROW + (n & 31)].x) : dense + n;
+    };
+    for (int r0 = 0; r0 < bi.nRuns; r0 += 32) {
+        // ---- one run per lane: record, item count, item list ----
+        const int r = r0 + lane;
+        uint4 rr = make_uint4(0, 0, 0, 0);
+        if (r < bi.nRuns) rr = __ldg(bi.runsEnd - 1 - (bi.runIdx0 + r));
+        const int s = (int)rr.x, e = s + (int)rr.y;
+        const uint32_t g0 = bi.drawBase + rr.z;
+        uint32_t amp = rr.w & 0xffffu;
+        if (rr.w & 0x80000000u) {
+            // decaying tail: unit amplitude here, level and decay applied when the coefficients are loaded
+            amp = 0x3f80u;
+            if (rr.y) {
+                const int lv = (int)(rr.w & 15u) + 1, nn = (int)((((rr.w >> 4) & 15u) << 4) | ((rr.w >> 8) & 15u));
+                const int q = (int)((rr.w >> 12) & 31u);
+                Tail t; t.start = s; t.end = e;
+                t.amp = (float)(lv * lv) * quant_scale(q) * (1.0f / 16);
+                const float decay = 1.0f + (float)(nn * nn) * -0x1.0p-19f;
+                t.l2 = decay != 1.0f ? log2f(decay) : 0.0f;
+                const int slot = atomicAdd(&w.nTails, 1);
+                if (slot < 8) w.tail[slot] = t;
+            }
+        }
+        RunRec me;
+        me.s = s; me.e = e; me.g0 = g0; me.amp2 = amp | (amp << 16);
+        me.flip = 0u - ((__ldg(&par[g0 >> 5]) >> (g0 & 31)) & 1u); me.pad = 0;
+        rt[lane] = me;
+        const int nIt = rr.y ? ((((e - 1) >> 1) - (s >> 1)) >> 4) + 1 : 0;      // items of 16 words
+        int inc = nIt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULLM, inc, d); if (lane >= d) inc += t; }
+        const int total = __shfl_sync(FULLM, inc, 31);
+        // rounds of at most MAXITEMS items (one round except for pathological blocks)
+        for (int base = 0; base < total; base += MAXITEMS) {
+            const int first = inc - nIt;                                         // my first item (global numbering)
+            for (int k = max(first, base); k < inc && k < base + MAXITEMS; k++) items[k - base] = (uint16_t)(lane | ((k - first) << 5));
+            __syncwarp();
+            const int cnt = min(total - base, MAXITEMS);
+            for (int it = grp; it < cnt; it += 8) {
+                const uint32_t iv = items[it];
+                const RunRec rc = rt[iv & 31u];
+                const int wq = (rc.s >> 1) + 16 * (int)(iv >> 5) + 4 * j;
+                const int p0 = 2 * wq;
+                if (p0 < rc.e) {
+                    const uint32_t m0 = rc.g0 + (uint32_t)(p0 - rc.s) + 1u;     // parity bit of position p0 (p0 >= s - 1)
+                    const uint32_t a0 = __ldg(&par[m0 >> 5]), a1 = __ldg(&par[(m0 >> 5) + 1]);
+                    const uint32_t bits = __funnelshift_r(a0, a1, m0 & 31) ^ rc.flip;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int pl = p0 + 2 * k, ph = pl + 1;
+                        const bool vl = pl >= rc.s && pl < rc.e, vh = ph < rc.e;   // ph > pl >= s - 1
+                        const uint32_t val = rc.amp2 | (((bits >> (2 * k)) & 1u) << 15) | (((bits >> (2 * k + 1)) & 1u) << 31);
+                        uint32_t *dst = word(wq + k);
+                        if (vl && vh) *dst = val;
+                        else if (vl) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)val;
+                        else if (vh) *(reinterpret_cast<uint16_t *>(dst) + 1) = (uint16_t)(val >> 16);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ float tail_gain(const WarpSm &w, int nT, int idx) {
+    float g = 1.0f;
+    for (int t = 0; t < nT; t++) {
+        const Tail &tl = w.tail[t];
+        if (idx >= tl.start && idx < tl.end) g = tl.amp * exp2f((float)(idx - tl.start) * tl.l2);
+    }
+    return g;
+}
+
+// pending tail: k-layout <-> time order (only when the block type changes)
+__device__ __noinline__ void pend_to_klayout(float *pend, int lane) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = pend[slot_time(lane + 32 * j)];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; j++) pend[lane + 32 * j] = v[j];
+    __syncwarp();
+}
+__device__ __noinline__ void pend_to_time(float *pend, int lane) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = pend[lane + 32 * j];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; j++) pend[slot_time(lane + 32 * j)] = v[j];
+    __syncwarp();
+}
+
+#ifndef ULCB_BP_MINB
+#define ULCB_BP_MINB 6
+#endif
+
+template <bool PCM16, bool DBG>
+__global__ void __launch_bounds__(64, ULCB_BP_MINB)
+bp_transform_kernel(UlcbBpArgs a) {
+    __shared__ __align__(128) CtaSm sm;
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int runsPerStream = (a.maxBlk + a.runLen - 1) / a.runLen;
+    const int s = blockIdx.x / runsPerStream, run = blockIdx.x - s * runsPerStream;
+    const int gs = a.s0 + s;
+    const int nb = a.nBlocks ? (int)a.nBlocks[gs] : a.nBlocksAll;
+    const int bFirst = run * a.runLen;
+    if (bFirst >= nb) return;
+    const int bLast = min(nb, bFirst + a.runLen);
+    const int firstBad = a.firstBad[s];
+    const uint32_t *off = a.blkOff + (size_t)s * (a.maxBlk + 1);
+    const uint64_t sbegRel = a.streamOffs[gs] - a.base0;
+    const UlcbTables &tb = a.tb;
+    const float2 *__restrict__ E = tb.dctE[0];
+    const float2 *__restrict__ T32 = tb.tw32;
+    const float2 *__restrict__ win = tb.win;
+    const uint32_t *__restrict__ par = tb.signParity;
+
+    WarpSm &w = sm.w[c];
+    float2 *zb = w.zb;
+    float *pend = w.pend;
+    float *scr = reinterpret_cast<float *>(w.zb);
+    uint16_t *coef16 = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(w.zb) + COEF16_OFS);
+    unsigned long long *mb = &sm.mbar[c];
+    if (lane == 0) { mbar_init(mb, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) pend[lane + 32 * j] = 0.0f;
+    bool kLayout = true;                               // zeros read the same either way
+    int lastSub = 0;
+    unsigned phase = 0;
+    __syncwarp();
+
+    // the block before the run is transformed only for the pending tail it leaves (nothing older survives in it)
+    int blk = bFirst > 0 ? bFirst - 1 : 0;
+    if (blk >= firstBad) blk = bFirst;                 // ... unless the stream is already dead there
+    BlkInfo cur{};
+    int skew = 0, inflight = 0;
+    if (blk < firstBad) {
+        cur = load_info(a, s, blk, c, off, sbegRel);
+        inflight = issue_words(w, mb, cur, 0, lane, skew);
+    }
+
+#pragma unroll 1
+    for (; blk < bLast; blk++) {
+        const bool warm = blk < bFirst;
+        char *outBlk = reinterpret_cast<char *>(a.out) + ((size_t)gs * a.outStride + (size_t)blk * N * 2) * (PCM16 ? 2 : 4);
+        if (blk >= firstBad) {
+            // corrupt / exhausted stream: silence (the reference tool aborts here, ulcDecodeTool.c:153-157)
+#pragma unroll 4
+            for (int j = 0; j < 16; j++) store_pairs<PCM16>(outBlk, c * 512 + lane + 32 * j, 0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const int wc = (int)cur.wc;
+        const bool longBlk = (wc >> 4) == 1;
+        float *dbg = DBG ? a.dbgCoefs + (((size_t)gs * a.nBlocksAll + blk) * 2 + c) * N : nullptr;
+
+        // ---- clear the coefficient words, then scatter this channel's words into them ----
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(w.zb);
+#pragma unroll 4
+            for (int i = 0; i < (32 * ZROW * 8) / 16 / 32; i++) z[lane + 32 * i] = make_uint4(0, 0, 0, 0);
+            if (lane < ((32 * ZROW * 8) / 16) % 32) z[lane + 32 * ((32 * ZROW * 8) / 16 / 32)] = make_uint4(0, 0, 0, 0);
+            if (lane == 0) w.nTails = 0;
+        }
+        __syncwarp();
+        for (int done = 0; done < cur.nCoef;) {
+            if (!inflight) inflight = issue_words(w, mb, cur, done, lane, skew);
+            mbar_wait(mb, phase); phase ^= 1u;
+#pragma unroll 4
+            for (int i = lane; i < inflight; i += 32) {
+                const uint32_t rw = w.rec[skew + i];
+                const int pos = (int)(rw >> 16);
+                uint16_t *dst = longBlk
+                    ? reinterpret_cast<uint16_t *>(&zb[(pos >> 6) * ZROW + ((pos >> 1) & 31)].x) + (pos & 1)
+                    : coef16 + pos;
+                *dst = (uint16_t)rw;
+            }
+            __syncwarp();
+            done += inflight; inflight = 0;
+        }
+        // noise runs (uses the landing slot for its work list), then start the next block's copy behind this block's transform
+        if (longBlk) {
+            if (!kLayout) { pend_to_klayout(pend, lane); kLayout = true; }
+            noise_fill<true>(w, cur, par, lane);
+        } else {
+            if (kLayout) { pend_to_time(pend, lane); kLayout = false; }
+            noise_fill<false>(w, cur, par, lane);
+        }
+        const int nT = min(w.nTails, 8);
+        {
+            const bool haveNext = blk + 1 < bLast && blk + 1 < firstBad;
+            const BlkInfo prev = cur;
+            (void)prev;
+            if (haveNext) { cur = load_info(a, s, blk + 1, c, off, sbegRel); inflight = issue_words(w, mb, cur, 0, lane, skew); }
+            else inflight = 0;
+        }
+
+        if (longBlk) {
+            // ======================= long block: register path =======================
+            float xr[32], xi[32];
+            if (nT == 0 && !DBG) {
+                // z[n] = (v[2n] + i v[N-1-2n]) E[n], n = lane + 32 j: v[2n] is the even half of word n (own column of the tile),
+                // v[N-1-2n] the odd half of word 1023-n = column 31-lane, row 31-j.  Straight into the registers of pass 0.
+                const float *own = &zb[lane].x, *mir = &zb[31 * ZROW + 31 - lane].x;
+                const float2 *Ep = E + lane;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t wa = __float_as_uint(own[j * ZROW * 2]), wm = __float_as_uint(mir[-j * ZROW * 2]);
+                    const float ev = __uint_as_float(wa << 16), od = __uint_as_float(wm & 0xffff0000u);
+                    const float2 e = __ldg(Ep + 32 * j);
+                    xr[j] = ev * e.x - od * e.y; xi[j] = ev * e.y + od * e.x;
+                }
+                __syncwarp();
+            } else {
+                // rare: decaying noise tails (gain applied here) / coefficient tap.  Rolled: z goes through the tile.
+#pragma unroll 1
+                for (int j = 0; j < 16; j++) {
+                    const int ja = j, jb = 31 - j;
+                    const int na = lane + 32 * ja, nb2 = lane + 32 * jb;
+                    const uint32_t wa = __float_as_uint(zb[ja * ZROW + lane].x), wb = __float_as_uint(zb[jb * ZROW + lane].x);
+                    float ea = __uint_as_float(wa << 16), oa = __uint_as_float(wa & 0xffff0000u);
+                    float eb = __uint_as_float(wb << 16), ob = __uint_as_float(wb & 0xffff0000u);
+                    if (nT) {
+                        ea *= tail_gain(w, nT, 2 * na); oa *= tail_gain(w, nT, 2 * na + 1);
+                        eb *= tail_gain(w, nT, 2 * nb2); ob *= tail_gain(w, nT, 2 * nb2 + 1);
+                    }
+                    if (DBG) {
+                        reinterpret_cast<float2 *>(dbg)[na] = make_float2(ea, oa);
+                        reinterpret_cast<float2 *>(dbg)[nb2] = make_float2(eb, ob);
+                    }
+                    const float ia = __shfl_xor_sync(FULLM, ob, 31);      // v[N-1-2na]
+                    const float ib = __shfl_xor_sync(FULLM, oa, 31);      // v[N-1-2nb]
+                    const float2 e0 = __ldg(&E[na]), e1 = __ldg(&E[nb2]);
+                    zb[ja * ZROW + lane] = make_float2(ea * e0.x - ia * e0.y, ea * e0.y + ia * e0.x);
+                    zb[jb * ZROW + lane] = make_float2(eb * e1.x - ib * e1.y, eb * e1.y + ib * e1.x);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j++) { const float2 v = zb[j * ZROW + lane]; xr[j] = v.x; xi[j] = v.y; }
+                __syncwarp();
+            }
+            // 1024-point FFT as 32 x 32, ONE copy of the 32-point code run for both passes:
+            //   pass 0: lane l transforms column l (n = l + 32 j over j), multiplies by W_1024^(l k1), stores A[l][k1] at zb[k1][l]
+            //   pass 1: lane k1 transforms row k1 (over l); y[k] = Z[k] E[k], k = k1 + 32 k2, stays in registers
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass) {
+#pragma unroll
+                    for (int r = 0; r < 32; r++) { const float2 v = zb[lane * ZROW + r]; xr[r] = v.x; xi[r] = v.y; }
+                    __syncwarp();
+                }
+                fft32(xr, xi);                            // register r now holds output index brev5(r)
+                const float2 *__restrict__ tp = (pass ? E : T32) + lane;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const float2 t = __ldg(tp + brev5(r) * 32);
+                    const float xa = xr[r], xb = xi[r];
+                    xr[r] = xa * t.x - xb * t.y; xi[r] = xa * t.y + xb * t.x;
+                }
+                if (!pass) {
+#pragma unroll
+                    for (int r = 0; r < 32; r++) zb[brev5(r) * ZROW + lane] = make_float2(xr[r], xi[r]);
+                    __syncwarp();
+                }
+            }
+            // un-fold (Fourier_IMDCT_Template.h:66-93) against the pending tail, all at the same k = lane + 32 k2
+            int ov = N >> (wc & 7);                       // the long block is its own transient sub-block (layout 0x8)
+            if (ov > lastSub) ov = lastSub;
+            lastSub = N;
+            if (ov == N) {
+                // steady state (full overlap): sine window over the whole half block, win[N/2 + i]
+                const float2 *__restrict__ wlo = win + H + (H - 1 - 2 * lane), *__restrict__ whi = win + H + (2 * lane - H);
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const int k2 = brev5(r), k = lane + 32 * k2;
+                    const float pa = pend[k];
+                    if (k2 < 16) {                        // i = N/2-1-2k, X[N/2+i] = -Im y, next tail = Re y
+                        const float2 wv = __ldg(wlo - 64 * k2);
+                        const float b = -xi[r];
+                        pend[k] = xr[r];
+                        zb[k2 * ZROW + lane] = make_float2(wv.x * pa - wv.y * b, wv.y * pa + wv.x * b);
+                    } else {                              // i = 2k-N/2, X[N/2+i] = Re y, next tail = -Im y
+                        const float2 wv = __ldg(whi + 64 * k2);
+                        const float b = xr[r];
+                        pend[k] = -xi[r];
+                        zb[k2 * ZROW + lane] = make_float2(wv.x * pa - wv.y * b, wv.y * pa + wv.x * b);
+                    }
+                }
+            } else {
+                // first block of a stream / after a short block / transient long block: through the tile, rolled
+#pragma unroll
+                for (int r = 0; r < 32; r++) zb[brev5(r) * ZROW + lane] = make_float2(xr[r], xi[r]);
+                __syncwarp();
+                const int flat = (N - ov) >> 1;
+                const int wofs = (ov >> 1) - flat;
+#pragma unroll 2
+                for (int k2 = 0; k2 < 32; k2++) {
+                    const int k = lane + 32 * k2;
+                    const float2 y = zb[k2 * ZROW + lane];
+                    const bool up = k2 >= 16;
+                    const int i = up ? 2 * k - H : H - 1 - 2 * k;
+                    const float b  = up ? y.x : -y.y;         // X[N/2 + i]
+                    const float np = up ? -y.y : y.x;         // X[N/2 - 1 - i]
+                    const float pa = pend[k];
+                    pend[k] = np;
+                    float lo, hi;
+                    if (i < flat) { lo = pa; hi = b; }
+                    else { const float2 wv = __ldg(&win[wofs + i]); lo = wv.x * pa - wv.y * b; hi = wv.y * pa + wv.x * b; }
+                    zb[k2 * ZROW + lane] = make_float2(lo, hi);   // time samples i and N-1-i
+                }
+            }
+            if (!warm) {
+                __syncthreads();
+                // warp 0 stores the first half of the block (samples i = .x), warp 1 the second (samples N-1-i = .y); M/S undo
+                // (ulcDecoder.c:281-289).  Pair (t, t+1) = slots k_e = p + (c ? 0 : 512) and k_o = (c ? 1023 : 511) - p, p = lane + 32 q.
+                const float *m0 = reinterpret_cast<const float *>(sm.w[0].zb) + c, *s0 = reinterpret_cast<const float *>(sm.w[1].zb) + c;
+#pragma unroll 2
+                for (int q = 0; q < 16; q++) {
+                    const int ie = ((c ? q : q + 16) * ZROW + lane) * 2, io = ((c ? 31 - q : 15 - q) * ZROW + 31 - lane) * 2;
+                    const float me = m0[ie], se = s0[ie], mo = m0[io], so = s0[io];
+                    store_pairs<PCM16>(outBlk, c * 512 + lane + 32 * q, me + se, me - se, mo + so, mo - so);
+                }
+                __syncthreads();
+            } else __syncwarp();
+        } else {
+            // ======================= window-switched block: shared-memory path, time order =======================
+            int offc = 0;
+            for (unsigned pat = kLayoutBp[wc >> 4];;) {
+                const int sh = pat & 7, S = N >> sh, hS = S >> 1;
+                for (int i = lane; i < S; i += 32) {
+                    float x = __uint_as_float((uint32_t)coef16[offc + i] << 16);
+                    if (nT) x *= tail_gain(w, nT, offc + i);
+                    if (DBG) dbg[offc + i] = x;
+                    scr[i] = x;
+                }
+                __syncwarp();
+                dct4_inplace<8, true>(scr, S, 1, S, sh, tb);
+
+                int ov = S;
+                if (pat & 8) ov >>= (wc & 7);
+                if (ov > lastSub) ov = lastSub;
+                lastSub = S;
+                const int flat = (S - ov) >> 1, held = H - hS;
+                const float2 *__restrict__ wv = win + (ov >> 1);
+                float uLo[16], uHi[16], tn[16];
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    const int i = lane + 32 * r;
+                    if (i < hS) {
+                        const float pa = pend[held + i], b = scr[hS + i];
+                        if (i < flat) { uLo[r] = pa; uHi[r] = b; }
+                        else { const float2 ww = __ldg(&wv[i - flat]); uLo[r] = ww.x * pa - ww.y * b; uHi[r] = ww.y * pa + ww.x * b; }
+                        tn[r] = scr[hS - 1 - i];
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    const int i = lane + 32 * r;
+                    if (i < hS) { scr[i] = uLo[r]; scr[S - 1 - i] = uHi[r]; pend[held + i] = tn[r]; }
+                }
+                __syncwarp();
+                {   // delay line (ulcDecoder.c:248-272): [pend[0..held) ++ u[0..S)] rotated left by S, three reversals
+                    const int tot = held + S;
+                    auto at = [&](int p) -> float & { return (p < held) ? pend[p] : scr[p - held]; };
+                    auto reverse = [&](int lo, int hi) {
+                        const int np = (hi - lo) >> 1;
+                        for (int k = lane; k < np; k += 32) { float &x = at(lo + k), &y = at(hi - 1 - k); const float t = x; x = y; y = t; }
+                        __syncwarp();
+                    };
+                    reverse(0, S); reverse(S, tot); reverse(0, tot);
+                }
+                if (!warm) {
+                    __syncthreads();
+                    const float *m = reinterpret_cast<const float *>(sm.w[0].zb), *sd = reinterpret_cast<const float *>(sm.w[1].zb);
+                    for (int p = lane; p < (hS >> 1); p += 32) {
+                        const int t = c * hS + 2 * p;
+                        const float m0 = m[t], m1 = m[t + 1], s0 = sd[t], s1 = sd[t + 1];
+                        store_pairs<PCM16>(outBlk, (offc + t) >> 1, m0 + s0, m0 - s0, m1 + s1, m1 - s1);
+                    }
+                    __syncthreads();
+                }
+                offc += S;
+                pat >>= 4;
+                if (!pat) break;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// Fast path applicability: BlockSize 2048, stereo, fresh streams (no carried per-stream state).
+bool ulcb_decode_bp_supported(const UlcbTables &tb, int nChan) { return tb.N == N && nChan == NCH && tb.tw32 != nullptr; }
+
+size_t ulcb_decode_bp_arena_bytes(uint64_t payloadBytes, int nStreams, int maxBlk) {
+    return (size_t)(16ull * ((payloadBytes + 1) >> 1) + 32ull * (uint64_t)nStreams * (uint64_t)(maxBlk + 1) + 256ull);
+}
+
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, bool haveIndex, cudaStream_t stream, int *launches) {
+    if (a.nStreams <= 0 || a.maxBlk <= 0) return cudaSuccess;
+    const int wpc = 4;                                            // warps per CTA of the per-stream kernels
+    if (haveIndex) bp_index_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
+    else           bp_walk_kernel<<<(a.nStreams + 127) / 128, 128, 0, stream>>>(a);
+    const long long nThr = (long long)a.nStreams * a.maxBlk;
+    bp_parse_kernel<<<(unsigned)((nThr + 127) / 128), 128, 0, stream>>>(a);
+    bp_scan_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
+    const int runsPerStream = (a.maxBlk + a.runLen - 1) / a.runLen;
+    const long long grid = (long long)a.nStreams * runsPerStream;
+    if (a.dbgCoefs) {
+        if (pcm16) bp_transform_kernel<true, true><<<(unsigned)grid, 64, 0, stream>>>(a);
+        else       bp_transform_kernel<false, true><<<(unsigned)grid, 64, 0, stream>>>(a);
+    } else {
+        if (pcm16) bp_transform_kernel<true, false><<<(unsigned)grid, 64, 0, stream>>>(a);
+        else       bp_transform_kernel<false, false><<<(unsigned)grid, 64, 0, stream>>>(a);
+    }
+    if (launches) *launches += 4;
+    return cudaGetLastError();
+}
