@@ -143,12 +143,16 @@ int build_tables(ULCB_Context *ctx) {
     }
     tb.tw32 = nullptr;
     if (N == 2048) {
-        std::vector<float2> t(32 * 32);
-        for (int k1 = 0; k1 < 32; k1++)
-            for (int l = 0; l < 32; l++) {
-                double a = -2.0 * M_PI * (double)((l * k1) & 1023) / 1024.0;
-                t[k1 * 32 + l] = float2{(float)cos(a), (float)sin(a)};
+        // per-lane bases of the folded inter-pass twiddle G[l][k1] = A_l Q_l^k1 (ulcb_decode_bp.cu): [0] = A_l, [1 + t] = Q_l^(2^t)
+        std::vector<float2> t(6 * 32);
+        for (int l = 0; l < 32; l++) {
+            const double aa = -M_PI * (8.0 * l + 2.0) / 16384.0;
+            t[l] = float2{(float)cos(aa), (float)sin(aa)};
+            for (int b = 0; b < 5; b++) {
+                const double qa = -M_PI * (4.0 * l + 1.0) * (double)(1 << b) / 2048.0;
+                t[32 * (b + 1) + l] = float2{(float)cos(qa), (float)sin(qa)};
             }
+        }
         if ((rc = upload(ctx, t, &tb.tw32))) return rc;
     }
     for (int sh = 0; sh < 4; sh++) {

@@ -341,6 +341,17 @@ __device__ __forceinline__ void fft32(float (&xr)[32], float (&xi)[32]) {
     }
 }
 
+// exp(-i pi j / 64) = (rotC(j), -rotS(j)), j < 32: the part of the DCT-IV pre / post twiddle E[l + 32 j] = E[l] * exp(-i pi j / 64) that does
+// not depend on the lane - compile-time constants in the unrolled passes
+__device__ __forceinline__ constexpr float rotC(int j) {
+    constexpr float t[32] = {1.00000000000000000e+00f, 9.98795456205172405e-01f, 9.95184726672196929e-01f, 9.89176509964781014e-01f, 9.80785280403230431e-01f, 9.70031253194543974e-01f, 9.56940335732208824e-01f, 9.41544065183020806e-01f, 9.23879532511286738e-01f, 9.03989293123443338e-01f, 8.81921264348355050e-01f, 8.57728610000272118e-01f, 8.31469612302545236e-01f, 8.03207531480644943e-01f, 7.73010453362736993e-01f, 7.40951125354959106e-01f, 7.07106781186547573e-01f, 6.71558954847018330e-01f, 6.34393284163645488e-01f, 5.95699304492433468e-01f, 5.55570233019602289e-01f, 5.14102744193221661e-01f, 4.71396736825997809e-01f, 4.27555093430282196e-01f, 3.82683432365089837e-01f, 3.36889853392220051e-01f, 2.90284677254462331e-01f, 2.42980179903263982e-01f, 1.95090322016128331e-01f, 1.46730474455361748e-01f, 9.80171403295607702e-02f, 4.90676743274181260e-02f};
+    return t[j];
+}
+__device__ __forceinline__ constexpr float rotS(int j) {
+    constexpr float t[32] = {0.00000000000000000e+00f, 4.90676743274180149e-02f, 9.80171403295606036e-02f, 1.46730474455361748e-01f, 1.95090322016128248e-01f, 2.42980179903263871e-01f, 2.90284677254462331e-01f, 3.36889853392220051e-01f, 3.82683432365089782e-01f, 4.27555093430282085e-01f, 4.71396736825997642e-01f, 5.14102744193221661e-01f, 5.55570233019602178e-01f, 5.95699304492433357e-01f, 6.34393284163645488e-01f, 6.71558954847018330e-01f, 7.07106781186547462e-01f, 7.40951125354959106e-01f, 7.73010453362736993e-01f, 8.03207531480644832e-01f, 8.31469612302545236e-01f, 8.57728610000272118e-01f, 8.81921264348354939e-01f, 9.03989293123443338e-01f, 9.23879532511286738e-01f, 9.41544065183020806e-01f, 9.56940335732208935e-01f, 9.70031253194543974e-01f, 9.80785280403230431e-01f, 9.89176509964781014e-01f, 9.95184726672196818e-01f, 9.98795456205172405e-01f};
+    return t[j];
+}
+
 // time index held by k-layout slot k
 __device__ __forceinline__ int slot_time(int k) { return k >= N / 4 ? 2 * k - H : H - 1 - 2 * k; }
 
@@ -351,9 +362,11 @@ __device__ __forceinline__ void store_pairs<false>(void *outBlk, int slotIdx, fl
     __stcs(reinterpret_cast<float4 *>(outBlk) + slotIdx, make_float4(l0, r0, l1, r1));
 }
 __device__ __forceinline__ uint32_t pcm16_pair(float l, float r) {   // tools/WavIO_Helper.c:57-63: clamp, lrintf
-    l = fminf(fmaxf(l * 32768.0f, -32768.0f), 32767.0f);
-    r = fminf(fmaxf(r * 32768.0f, -32768.0f), 32767.0f);
-    return (uint32_t)(uint16_t)(int16_t)__float2int_rn(l) | ((uint32_t)(uint16_t)(int16_t)__float2int_rn(r) << 16);
+    // cvt.rni.sat = round half to even, then saturate to [-32768, 32767]: the same value as lrintf of the clamped product
+    short a, b;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(a) : "f"(l * 32768.0f));
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(b) : "f"(r * 32768.0f));
+    return (uint32_t)(uint16_t)a | ((uint32_t)(uint16_t)b << 16);
 }
 template <>
 __device__ __forceinline__ void store_pairs<true>(void *outBlk, int slotIdx, float l0, float r0, float l1, float r1) {
@@ -364,14 +377,15 @@ struct Tail { int start, end; float amp, l2; };     // decaying noise to the end
 
 struct WarpSm {
     float2   zb[32 * ZROW];       // FFT tile / coefficient words / short-block scratch / output swap
-    float    pend[H];             // pending tail (k-layout or time order)
-    uint32_t rec[RECSLOT];        // TMA landing slot: this channel's coefficient words of the next block (noise work list in between)
+    uint32_t rec[RECSLOT];        // TMA landing slot: this channel's coefficient words of the next block; in between the noise work
+                                  // list and, for a window-switched block, the pending tail in time order
     Tail     tail[8];
     int      nTails, pad[3];
 };
 struct CtaSm {
     WarpSm w[2];
     unsigned long long mbar[2];
+    uint32_t tmemBase, pad[3];
 };
 constexpr int COEF16_OFS = 4224;  // byte offset of the bf16 coefficient array of a window-switched block inside zb (the
                                   // sub-block scratch occupies the first 4 KB)
@@ -498,15 +512,21 @@ __device__ __noinline__ void noise_fill(WarpSm &w, const BlkInfo &bi, const uint
                     const uint32_t m0 = rc.g0 + (uint32_t)(p0 - rc.s) + 1u;     // parity bit of position p0 (p0 >= s - 1)
                     const uint32_t a0 = __ldg(&par[m0 >> 5]), a1 = __ldg(&par[(m0 >> 5) + 1]);
                     const uint32_t bits = __funnelshift_r(a0, a1, m0 & 31) ^ rc.flip;
+                    if (p0 >= rc.s && p0 + 8 <= rc.e) {                          // interior: four whole words
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int pl = p0 + 2 * k, ph = pl + 1;
-                        const bool vl = pl >= rc.s && pl < rc.e, vh = ph < rc.e;   // ph > pl >= s - 1
-                        const uint32_t val = rc.amp2 | (((bits >> (2 * k)) & 1u) << 15) | (((bits >> (2 * k + 1)) & 1u) << 31);
-                        uint32_t *dst = word(wq + k);
-                        if (vl && vh) *dst = val;
-                        else if (vl) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)val;
-                        else if (vh) *(reinterpret_cast<uint16_t *>(dst) + 1) = (uint16_t)(val >> 16);
+                        for (int k = 0; k < 4; k++)
+                            *word(wq + k) = rc.amp2 | (((bits >> (2 * k)) & 1u) << 15) | (((bits >> (2 * k + 1)) & 1u) << 31);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int pl = p0 + 2 * k, ph = pl + 1;
+                            const bool vl = pl >= rc.s && pl < rc.e, vh = ph < rc.e;   // ph > pl >= s - 1
+                            const uint32_t val = rc.amp2 | (((bits >> (2 * k)) & 1u) << 15) | (((bits >> (2 * k + 1)) & 1u) << 31);
+                            uint32_t *dst = word(wq + k);
+                            if (vl && vh) *dst = val;
+                            else if (vl) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)val;
+                            else if (vh) *(reinterpret_cast<uint16_t *>(dst) + 1) = (uint16_t)(val >> 16);
+                        }
                     }
                 }
             }
@@ -525,28 +545,48 @@ __device__ __forceinline__ float tail_gain(const WarpSm &w, int nT, int idx) {
     return g;
 }
 
-// pending tail: k-layout <-> time order (only when the block type changes)
-__device__ __noinline__ void pend_to_klayout(float *pend, int lane) {
-    float v[32];
+// ---- the pending tail lives in Tensor Memory ----
+// Between blocks the un-fold needs, per lane, exactly the 32 values it left there one block earlier (slot k = lane + 32 k2 of
+// the "k-layout": time sample 2k - N/2 for k >= N/4, N/2 - 1 - 2k below).  That is lane-private state, which is what TMEM's
+// 32x32b access shape addresses: lane t of warp w owns TMEM lane 32 (w % 4) + t, column k2.  32 columns per CTA hold both
+// channels' tails (warp 0 = lanes 0-31, warp 1 = lanes 32-63) and cost no shared memory and no registers between blocks.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// k-layout (TMEM) -> time order (shared memory) and back, around a window-switched block
+__device__ __noinline__ void pend_to_time(uint32_t taddr, float *pend, int lane) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] = pend[slot_time(lane + 32 * j)];
-    __syncwarp();
+    for (int g = 0; g < 4; g++) {
+        float v[8];
+        tmem_ld8(taddr + 8 * g, v);
 #pragma unroll
-    for (int j = 0; j < 32; j++) pend[lane + 32 * j] = v[j];
+        for (int t = 0; t < 8; t++) pend[slot_time(lane + 32 * (8 * g + t))] = v[t];
+    }
     __syncwarp();
 }
-__device__ __noinline__ void pend_to_time(float *pend, int lane) {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) v[j] = pend[lane + 32 * j];
+__device__ __noinline__ void pend_to_klayout(uint32_t taddr, const float *pend, int lane) {
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 32; j++) pend[slot_time(lane + 32 * j)] = v[j];
+    for (int g = 0; g < 4; g++) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[t] = pend[slot_time(lane + 32 * (8 * g + t))];
+        tmem_st8(taddr + 8 * g, v);
+    }
+    tmem_wait_st();
     __syncwarp();
 }
 
 #ifndef ULCB_BP_MINB
-#define ULCB_BP_MINB 6
+#define ULCB_BP_MINB 8
 #endif
 
 template <bool PCM16, bool DBG>
@@ -565,21 +605,32 @@ bp_transform_kernel(UlcbBpArgs a) {
     const uint32_t *off = a.blkOff + (size_t)s * (a.maxBlk + 1);
     const uint64_t sbegRel = a.streamOffs[gs] - a.base0;
     const UlcbTables &tb = a.tb;
-    const float2 *__restrict__ E = tb.dctE[0];
     const float2 *__restrict__ T32 = tb.tw32;
     const float2 *__restrict__ win = tb.win;
     const uint32_t *__restrict__ par = tb.signParity;
 
     WarpSm &w = sm.w[c];
     float2 *zb = w.zb;
-    float *pend = w.pend;
+    float *pend = reinterpret_cast<float *>(w.rec);     // time-ordered copy, window-switched blocks only
     float *scr = reinterpret_cast<float *>(w.zb);
     uint16_t *coef16 = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(w.zb) + COEF16_OFS);
     unsigned long long *mb = &sm.mbar[c];
     if (lane == 0) { mbar_init(mb, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-#pragma unroll 4
-    for (int j = 0; j < 32; j++) pend[lane + 32 * j] = 0.0f;
-    bool kLayout = true;                               // zeros read the same either way
+    if (c == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&sm.tmemBase)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = sm.tmemBase;
+    const uint32_t taddr = tbase + ((uint32_t)(c * 32) << 16);
+    {
+        const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g = 0; g < 4; g++) tmem_st8(taddr + 8 * g, z8);
+        tmem_wait_st();
+    }
     int lastSub = 0;
     unsigned phase = 0;
     __syncwarp();
@@ -632,22 +683,16 @@ bp_transform_kernel(UlcbBpArgs a) {
             __syncwarp();
             done += inflight; inflight = 0;
         }
-        // noise runs (uses the landing slot for its work list), then start the next block's copy behind this block's transform
-        if (longBlk) {
-            if (!kLayout) { pend_to_klayout(pend, lane); kLayout = true; }
-            noise_fill<true>(w, cur, par, lane);
-        } else {
-            if (kLayout) { pend_to_time(pend, lane); kLayout = false; }
-            noise_fill<false>(w, cur, par, lane);
-        }
+        // noise runs (the landing slot holds their work list), then - long block - start the next block's copy behind this
+        // block's transform; a window-switched block keeps the slot for its time-ordered pending tail until it is done
+        if (longBlk) noise_fill<true>(w, cur, par, lane);
+        else         noise_fill<false>(w, cur, par, lane);
         const int nT = min(w.nTails, 8);
-        {
-            const bool haveNext = blk + 1 < bLast && blk + 1 < firstBad;
-            const BlkInfo prev = cur;
-            (void)prev;
-            if (haveNext) { cur = load_info(a, s, blk + 1, c, off, sbegRel); inflight = issue_words(w, mb, cur, 0, lane, skew); }
-            else inflight = 0;
-        }
+        const bool haveNext = blk + 1 < bLast && blk + 1 < firstBad;
+        BlkInfo nxt{};
+        if (haveNext) nxt = load_info(a, s, blk + 1, c, off, sbegRel);
+        inflight = 0;
+        if (haveNext && longBlk) inflight = issue_words(w, mb, nxt, 0, lane, skew);
 
         if (longBlk) {
             // ======================= long block: register path =======================
@@ -655,14 +700,13 @@ bp_transform_kernel(UlcbBpArgs a) {
             if (nT == 0 && !DBG) {
                 // z[n] = (v[2n] + i v[N-1-2n]) E[n], n = lane + 32 j: v[2n] is the even half of word n (own column of the tile),
                 // v[N-1-2n] the odd half of word 1023-n = column 31-lane, row 31-j.  Straight into the registers of pass 0.
+                // The lane-dependent factor E[lane] of the twiddle moves behind pass 0 (it is common to the whole column).
                 const float *own = &zb[lane].x, *mir = &zb[31 * ZROW + 31 - lane].x;
-                const float2 *Ep = E + lane;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const uint32_t wa = __float_as_uint(own[j * ZROW * 2]), wm = __float_as_uint(mir[-j * ZROW * 2]);
                     const float ev = __uint_as_float(wa << 16), od = __uint_as_float(wm & 0xffff0000u);
-                    const float2 e = __ldg(Ep + 32 * j);
-                    xr[j] = ev * e.x - od * e.y; xi[j] = ev * e.y + od * e.x;
+                    xr[j] = ev * rotC(j) + od * rotS(j); xi[j] = od * rotC(j) - ev * rotS(j);
                 }
                 __syncwarp();
             } else {
@@ -684,9 +728,10 @@ bp_transform_kernel(UlcbBpArgs a) {
                     }
                     const float ia = __shfl_xor_sync(FULLM, ob, 31);      // v[N-1-2na]
                     const float ib = __shfl_xor_sync(FULLM, oa, 31);      // v[N-1-2nb]
-                    const float2 e0 = __ldg(&E[na]), e1 = __ldg(&E[nb2]);
-                    zb[ja * ZROW + lane] = make_float2(ea * e0.x - ia * e0.y, ea * e0.y + ia * e0.x);
-                    zb[jb * ZROW + lane] = make_float2(eb * e1.x - ib * e1.y, eb * e1.y + ib * e1.x);
+                    const float ca = cosf(0.049087385212340517f * (float)ja), sa = sinf(0.049087385212340517f * (float)ja);   // pi / 64
+                    const float cb = cosf(0.049087385212340517f * (float)jb), sb = sinf(0.049087385212340517f * (float)jb);
+                    zb[ja * ZROW + lane] = make_float2(ea * ca + ia * sa, ia * ca - ea * sa);
+                    zb[jb * ZROW + lane] = make_float2(eb * cb + ib * sb, ib * cb - eb * sb);
                 }
                 __syncwarp();
 #pragma unroll
@@ -694,8 +739,10 @@ bp_transform_kernel(UlcbBpArgs a) {
                 __syncwarp();
             }
             // 1024-point FFT as 32 x 32, ONE copy of the 32-point code run for both passes:
-            //   pass 0: lane l transforms column l (n = l + 32 j over j), multiplies by W_1024^(l k1), stores A[l][k1] at zb[k1][l]
-            //   pass 1: lane k1 transforms row k1 (over l); y[k] = Z[k] E[k], k = k1 + 32 k2, stays in registers
+            //   pass 0: lane l transforms column l (n = l + 32 j over j), multiplies by G[l][k1] = E[l] W_1024^(l k1) E[k1] - the
+            //           inter-pass twiddle with both lane-dependent halves of the DCT-IV twiddles folded in; G[l][k1] = A_l Q_l^k1 is
+            //           built from six per-lane values by a product tree - and stores A[l][k1] at zb[k1][l]
+            //   pass 1: lane k1 transforms row k1 (over l); y[k] = Z[k] exp(-i pi k2 / 64), k = k1 + 32 k2, stays in registers
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
                 if (pass) {
@@ -704,20 +751,45 @@ bp_transform_kernel(UlcbBpArgs a) {
                     __syncwarp();
                 }
                 fft32(xr, xi);                            // register r now holds output index brev5(r)
-                const float2 *__restrict__ tp = (pass ? E : T32) + lane;
-#pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    const float2 t = __ldg(tp + brev5(r) * 32);
-                    const float xa = xr[r], xb = xi[r];
-                    xr[r] = xa * t.x - xb * t.y; xi[r] = xa * t.y + xb * t.x;
-                }
                 if (!pass) {
+                    const float2 gA = __ldg(T32 + lane);
+                    float2 P[5];
 #pragma unroll
-                    for (int r = 0; r < 32; r++) zb[brev5(r) * ZROW + lane] = make_float2(xr[r], xi[r]);
+                    for (int t = 0; t < 5; t++) P[t] = __ldg(T32 + 32 * (t + 1) + lane);
+#pragma unroll
+                    for (int b4 = 0; b4 < 2; b4++) {
+                        const float2 g4 = b4 ? cmul(gA, P[4]) : gA;
+#pragma unroll
+                        for (int b3 = 0; b3 < 2; b3++) {
+                            const float2 g3 = b3 ? cmul(g4, P[3]) : g4;
+#pragma unroll
+                            for (int b2 = 0; b2 < 2; b2++) {
+                                const float2 g2 = b2 ? cmul(g3, P[2]) : g3;
+#pragma unroll
+                                for (int b1 = 0; b1 < 2; b1++) {
+                                    const float2 g1 = b1 ? cmul(g2, P[1]) : g2;
+#pragma unroll
+                                    for (int b0 = 0; b0 < 2; b0++) {
+                                        const float2 g = b0 ? cmul(g1, P[0]) : g1;
+                                        const int k1 = b4 * 16 + b3 * 8 + b2 * 4 + b1 * 2 + b0, r = brev5(k1);
+                                        zb[k1 * ZROW + lane] = make_float2(xr[r] * g.x - xi[r] * g.y, xr[r] * g.y + xi[r] * g.x);
+                                    }
+                                }
+                            }
+                        }
+                    }
                     __syncwarp();
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 32; r++) {
+                        const int k2 = brev5(r);
+                        const float xa = xr[r], xb = xi[r];
+                        xr[r] = xa * rotC(k2) + xb * rotS(k2); xi[r] = xb * rotC(k2) - xa * rotS(k2);
+                    }
                 }
             }
-            // un-fold (Fourier_IMDCT_Template.h:66-93) against the pending tail, all at the same k = lane + 32 k2
+            // un-fold (Fourier_IMDCT_Template.h:66-93) against the pending tail, all at the same k = lane + 32 k2; the tail comes
+            // from / goes back to TMEM eight columns at a time
             int ov = N >> (wc & 7);                       // the long block is its own transient sub-block (layout 0x8)
             if (ov > lastSub) ov = lastSub;
             lastSub = N;
@@ -725,44 +797,50 @@ bp_transform_kernel(UlcbBpArgs a) {
                 // steady state (full overlap): sine window over the whole half block, win[N/2 + i]
                 const float2 *__restrict__ wlo = win + H + (H - 1 - 2 * lane), *__restrict__ whi = win + H + (2 * lane - H);
 #pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    const int k2 = brev5(r), k = lane + 32 * k2;
-                    const float pa = pend[k];
-                    if (k2 < 16) {                        // i = N/2-1-2k, X[N/2+i] = -Im y, next tail = Re y
-                        const float2 wv = __ldg(wlo - 64 * k2);
-                        const float b = -xi[r];
-                        pend[k] = xr[r];
-                        zb[k2 * ZROW + lane] = make_float2(wv.x * pa - wv.y * b, wv.y * pa + wv.x * b);
-                    } else {                              // i = 2k-N/2, X[N/2+i] = Re y, next tail = -Im y
-                        const float2 wv = __ldg(whi + 64 * k2);
-                        const float b = xr[r];
-                        pend[k] = -xi[r];
-                        zb[k2 * ZROW + lane] = make_float2(wv.x * pa - wv.y * b, wv.y * pa + wv.x * b);
+                for (int g = 0; g < 4; g++) {
+                    float pa[8], np[8];
+                    tmem_ld8(taddr + 8 * g, pa);
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        const int k2 = 8 * g + t, r = brev5(k2);
+                        if (k2 < 16) {                    // i = N/2-1-2k, X[N/2+i] = -Im y, next tail = Re y
+                            const float2 wv = __ldg(wlo - 64 * k2);
+                            const float b = -xi[r];
+                            np[t] = xr[r];
+                            zb[k2 * ZROW + lane] = make_float2(wv.x * pa[t] - wv.y * b, wv.y * pa[t] + wv.x * b);
+                        } else {                          // i = 2k-N/2, X[N/2+i] = Re y, next tail = -Im y
+                            const float2 wv = __ldg(whi + 64 * k2);
+                            const float b = xr[r];
+                            np[t] = -xi[r];
+                            zb[k2 * ZROW + lane] = make_float2(wv.x * pa[t] - wv.y * b, wv.y * pa[t] + wv.x * b);
+                        }
                     }
+                    tmem_st8(taddr + 8 * g, np);
                 }
             } else {
-                // first block of a stream / after a short block / transient long block: through the tile, rolled
-#pragma unroll
-                for (int r = 0; r < 32; r++) zb[brev5(r) * ZROW + lane] = make_float2(xr[r], xi[r]);
-                __syncwarp();
+                // first block of a stream / after a short block / transient long block: flat part + narrower window
                 const int flat = (N - ov) >> 1;
                 const int wofs = (ov >> 1) - flat;
-#pragma unroll 2
-                for (int k2 = 0; k2 < 32; k2++) {
-                    const int k = lane + 32 * k2;
-                    const float2 y = zb[k2 * ZROW + lane];
-                    const bool up = k2 >= 16;
-                    const int i = up ? 2 * k - H : H - 1 - 2 * k;
-                    const float b  = up ? y.x : -y.y;         // X[N/2 + i]
-                    const float np = up ? -y.y : y.x;         // X[N/2 - 1 - i]
-                    const float pa = pend[k];
-                    pend[k] = np;
-                    float lo, hi;
-                    if (i < flat) { lo = pa; hi = b; }
-                    else { const float2 wv = __ldg(&win[wofs + i]); lo = wv.x * pa - wv.y * b; hi = wv.y * pa + wv.x * b; }
-                    zb[k2 * ZROW + lane] = make_float2(lo, hi);   // time samples i and N-1-i
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    float pa[8], np[8];
+                    tmem_ld8(taddr + 8 * g, pa);
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        const int k2 = 8 * g + t, r = brev5(k2), k = lane + 32 * k2;
+                        const bool up = k2 >= 16;
+                        const int i = up ? 2 * k - H : H - 1 - 2 * k;
+                        const float b = up ? xr[r] : -xi[r];      // X[N/2 + i]
+                        np[t] = up ? -xi[r] : xr[r];              // X[N/2 - 1 - i]
+                        float lo, hi;
+                        if (i < flat) { lo = pa[t]; hi = b; }
+                        else { const float2 wv = __ldg(&win[wofs + i]); lo = wv.x * pa[t] - wv.y * b; hi = wv.y * pa[t] + wv.x * b; }
+                        zb[k2 * ZROW + lane] = make_float2(lo, hi);   // time samples i and N-1-i
+                    }
+                    tmem_st8(taddr + 8 * g, np);
                 }
             }
+            tmem_wait_st();
             if (!warm) {
                 __syncthreads();
                 // warp 0 stores the first half of the block (samples i = .x), warp 1 the second (samples N-1-i = .y); M/S undo
@@ -778,6 +856,7 @@ bp_transform_kernel(UlcbBpArgs a) {
             } else __syncwarp();
         } else {
             // ======================= window-switched block: shared-memory path, time order =======================
+            pend_to_time(taddr, pend, lane);
             int offc = 0;
             for (unsigned pat = kLayoutBp[wc >> 4];;) {
                 const int sh = pat & 7, S = N >> sh, hS = S >> 1;
@@ -838,8 +917,15 @@ bp_transform_kernel(UlcbBpArgs a) {
                 pat >>= 4;
                 if (!pat) break;
             }
+            pend_to_klayout(taddr, pend, lane);
+            if (haveNext) inflight = issue_words(w, mb, nxt, 0, lane, skew);
         }
+        cur = nxt;
     }
+    // every tcgen05 access of this CTA is complete (wait::st above): hand the columns back
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (c == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tbase) : "memory");
 }
 
 }  // namespace
