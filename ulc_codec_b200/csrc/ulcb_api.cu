@@ -376,7 +376,7 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
         size_t fr = 0, tot = 0;
         if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) { const size_t lim = (fr + ctx->bpArenaCap) / 2; if (cap > lim) cap = lim; }
     }
-    static const int runLen = getenv("ULCB_BP_RUNLEN") ? atoi(getenv("ULCB_BP_RUNLEN")) : 32;
+    static const int runLen = getenv("ULCB_BP_RUNLEN") ? atoi(getenv("ULCB_BP_RUNLEN")) : 64;
     UlcbBpArgs a{};
     a.tb = ctx->tb; a.nSignBits = ctx->tb.nSignBits;
     a.nBlocksAll = (int)nBlocksAll; a.maxBlk = (int)maxBlk; a.runLen = runLen < 1 ? 1 : runLen;

@@ -40,6 +40,10 @@ constexpr int N = 2048, H = N / 2, NCH = 2;
 constexpr int ZROW = 33;                              // padded row of the 32 x 32 complex work tile
 constexpr int RECSLOT = 1024;                         // words of the TMA landing slot per warp
 constexpr unsigned FULLM = 0xffffffffu;
+#ifndef ULCB_BP_PFDIST
+#define ULCB_BP_PFDIST 4
+#endif
+constexpr int PFDIST = ULCB_BP_PFDIST;                // parse: 16-byte vectors the L1 prefetch runs ahead of the loads
 
 // Decimation layouts, one nybble per sub-block, LSB first: bits0-2 shift, bit3 transient
 // (libulc/ulcHelper.h:24-46, FormatSpecs.md:35-51)
@@ -63,105 +67,153 @@ __device__ __forceinline__ uint64_t region_bytes(uint32_t len) { return 16ull * 
 // ================================================================================================
 struct ParseOut { uint32_t nyb, wc, draws, nCoef0, nCoefTot, nRun0, nRunTot; };
 
+// One token per loop trip and lane.  32 lanes walk 32 different blocks, so every branch of the loop body that a few percent
+// of the tokens take is executed on almost every trip; the body is therefore written branch-free for the four token
+// kinds that make up 99.5 % of a stream (coefficient, short zero run, noise run, quantiser change) and branches only
+// for the rest (sub-block ends and headers, long zero runs, extended quantisers, stop codes, tails).
 template <bool EMIT>
 __device__ __forceinline__ bool parse_block(const uint8_t *p, const uint32_t *wend, uint32_t maxNyb, const uint16_t *lut,
                                             uint32_t *up, uint4 *down, ParseOut &o) {
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(p - mis);
-    auto ldw = [&](const uint32_t *q) -> uint32_t { return q < wend ? __ldg(q) : 0u; };
-    uint64_t buf = ((uint64_t)ldw(wp) | ((uint64_t)ldw(wp + 1) << 32)) >> (8 * mis);
-    int navail = 16 - 2 * (int)mis;
-    uint32_t nextw = ldw(wp + 2);
-    wp += 3;
-    uint32_t consumed = 0;
-#define BP_SKIP(k)                                                                                   \
-    do {                                                                                             \
-        const int k_ = (k);                                                                          \
-        buf >>= 4 * k_; navail -= k_; consumed += (uint32_t)k_;                                      \
-        if (navail <= 8) { buf |= (uint64_t)nextw << (4 * navail); navail += 8; nextw = ldw(wp); wp++; } \
+    // Nybble reader.  A lane reads its block front to back, but 32 lanes of a warp read 32 different blocks: a load that
+    // misses stalls the whole warp, and with one miss per lane every ~40 tokens that is a stall on nearly every trip.  So the
+    // bytes come in 16-byte loads that are issued a full 16 bytes (~20 tokens) before their first word is needed and wait
+    // in a register FIFO: `cur` holds the current nybble at bit `sh`, `nxt` the following word, q0..q3 the next `cnt` words,
+    // `fly` the 16 bytes in flight.
+    const uintptr_t pa = reinterpret_cast<uintptr_t>(p);
+    const uint4 *vbase = reinterpret_cast<const uint4 *>(pa & ~(uintptr_t)15);
+    const long long vavail = (reinterpret_cast<const char *>(wend) - reinterpret_cast<const char *>(vbase)) >> 2;   // readable words from vbase
+    const uint32_t wlim = vavail <= 0 ? 0u : (uint32_t)min(vavail, 0x7ffffff0ll);
+    // The in-flight registers are loaded IN PLACE by inline assembly ("+r"): assigned as a C++ value inside the refill branch
+    // they are copied at the loop's join, and that copy waits for the load on the very trip that issued it.
+    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+    auto ld16 = [&](uint32_t i) {                           // 16 bytes number i from vbase -> f0..f3, zero beyond the readable end
+        if (4u * i + 4u <= wlim) {
+            asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "+r"(f0), "+r"(f1), "+r"(f2), "+r"(f3) : "l"(vbase + i));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(vbase + i + PFDIST));     // may point past the buffer: a prefetch does not fault
+        } else {
+            // the last, partial 16 bytes of the buffer: word by word, still in place
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.lt.u32 p, %4, %7;\n\t@p ld.global.nc.u32 %0, [%8];\n\t@!p mov.u32 %0, 0;\n\t"
+                "setp.lt.u32 p, %5, %7;\n\t@p ld.global.nc.u32 %1, [%8+4];\n\t@!p mov.u32 %1, 0;\n\t"
+                "setp.lt.u32 p, %6, %7;\n\t@p ld.global.nc.u32 %2, [%8+8];\n\t@!p mov.u32 %2, 0;\n\t"
+                "mov.u32 %3, 0;\n\t}"
+                : "+r"(f0), "+r"(f1), "+r"(f2), "+r"(f3)
+                : "r"(4u * i), "r"(4u * i + 1u), "r"(4u * i + 2u), "r"(wlim), "l"(vbase + i));
+        }
+    };
+    ld16(0);
+    uint32_t cur = f0, nxt = f1, q0 = f2, q1 = f3, q2 = 0, q3 = 0, cnt = 2, vi = 2;
+    ld16(1);
+#define BP_ADVANCE()                                                                         \
+    do {                                                                                     \
+        cur = nxt; nxt = q0; q0 = q1; q1 = q2; q2 = q3; cnt--;                               \
+        if (cnt == 0) { q0 = f0; q1 = f1; q2 = f2; q3 = f3; cnt = 4; ld16(vi); vi++; }       \
     } while (0)
+    for (uint32_t k0 = (uint32_t)((pa & 15) >> 2); k0; k0--) BP_ADVANCE();
+    uint32_t sh = 8u * (uint32_t)(pa & 3);
+    int left = (int)maxNyb;                                // nybbles this block may still consume
+#define BP_SKIP(k)                                                                           \
+    do {                                                                                     \
+        const uint32_t k_ = (uint32_t)(k);                                                   \
+        sh += 4u * k_; left -= (int)k_;                                                      \
+        if (sh >= 32u) { sh -= 32u; BP_ADVANCE(); }                                          \
+    } while (0)
+    const unsigned lutAddr = (unsigned)__cvta_generic_to_shared(lut);
+    auto lutAt = [&](uint32_t i) -> uint32_t {             // one shared-memory load off a register-held base
+        unsigned short v;
+        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(lutAddr + 2u * i));
+        return (uint32_t)v;
+    };
     uint32_t e0 = 0, e1 = 0, e2 = 0, nw = 0;
-#define BP_EMITW(val)                                                                                \
-    do {                                                                                             \
-        const uint32_t v_ = (val), s_ = nw & 3u;                                                     \
-        if (s_ == 0) e0 = v_; else if (s_ == 1) e1 = v_; else if (s_ == 2) e2 = v_;                  \
-        else *reinterpret_cast<uint4 *>(up + (nw - 3)) = make_uint4(e0, e1, e2, v_);                 \
-        nw++;                                                                                        \
+    // coefficient words leave four at a time (16-byte stores): every store instruction of this kernel touches 32 different
+    // sectors, and the L1 store path, shared with the loads, takes them one at a time
+#define BP_EMITW(val)                                                                        \
+    do {                                                                                     \
+        const uint32_t v_ = (val), s_ = nw & 3u;                                             \
+        if (s_ == 3u) *reinterpret_cast<uint4 *>(up + (nw - 3)) = make_uint4(e0, e1, e2, v_); \
+        e0 = s_ == 0u ? v_ : e0; e1 = s_ == 1u ? v_ : e1; e2 = s_ == 2u ? v_ : e2;           \
+        nw++;                                                                                \
     } while (0)
 
-    uint32_t x = (uint32_t)buf;
+    uint32_t x = __funnelshift_r(cur, nxt, sh);
     uint32_t wc;
     if (x & 8u) { wc = x & 0xffu; BP_SKIP(2); }            // ulcDecoder.c:211-216
     else        { wc = (x & 15u) | 0x10u; BP_SKIP(1); }
     const uint32_t layout = kLayoutBp[wc >> 4];
     uint32_t pat = layout;
-    int c = 0, pos = 0, subEnd = N >> (pat & 7);
-    bool hdr = true, ok = true;
+    int c = 0, pos = 0, subEnd = 0;
+    bool ok = true, done = false;
     int q = 0, eb = -1;                                     // eb = bf16 exponent bias of the quantiser, -1 = scale 0
     uint32_t draws = 0, nRun = 0, nCoef0 = 0, nRun0 = 0;
-    for (;;) {
-        x = (uint32_t)buf;
-        const uint32_t v0 = x & 15u, v1 = (x >> 4) & 15u;
-        int len = 1, adv = 0;
-        if (hdr) {
-            // sub-block header: bare quantiser (ulcDecoder.c:103-112).  A lone Fh is an invalid lead-in: the reference's
-            // shift by -2 gives scale 0 on x86
-            hdr = false;
-            if (v0 == 15u) q = 30;
-            else if (v0 == 14u) { len = 2; if (v1 == 15u) adv = subEnd - pos; else q = 14 + (int)v1; }
-            else q = (int)v0;
-            eb = q > 26 ? -1 : (5 + q) << 7;
-        } else if (!((0x8103u >> v0) & 1u)) {
-            // -7..-2, +2..+7: sign * v^2 * Quant (ulcDecoder.c:119-124)
-            adv = 1;
-            if (EMIT && eb >= 0) BP_EMITW(((uint32_t)pos << 16) | (uint32_t)(lut[v0] - eb));
-        } else if (v0 == 0u) {
-            len = 2; adv = (int)v1 + 1;                     // 0h,Xh: 1..16 zeros
-        } else {
-            const uint32_t v2 = (x >> 8) & 15u, v3 = (x >> 12) & 15u, b12 = (v1 << 4) | v2;
-            if (v0 == 1u) { len = 3; adv = (int)b12 + 33; } // 1h,Yh,Xh: 33..288 zeros
-            else if (v0 == 8u) {                            // 8h,Zh,Yh,Xh: 16..527 noise, level ((X>>1)+1)^2 * Quant / 4
-                len = 4; adv = (int)((b12 << 1) | (v3 & 1u)) + 16;
-                if (EMIT && adv <= subEnd - pos) {
-                    const uint32_t amp = eb >= 0 ? (uint32_t)(lut[16 + (v3 >> 1)] - eb) : 0u;
-                    *(down - 1 - nRun) = make_uint4((uint32_t)pos, (uint32_t)adv, draws, amp);
+    // sub-block boundary: next sub-block / channel (unless `first`), then its header - a bare quantiser (ulcDecoder.c:103-112);
+    // repeats while the header says "silent" (Eh,Fh).  Sets `done` after the last sub-block of the last channel.
+    auto boundary = [&](bool first) {
+        for (;;) {
+            if (!first) {
+                pat >>= 4;
+                if (!pat) {
+                    if (c == 0) { nCoef0 = nw; nRun0 = nRun; }
+                    if (++c == NCH) { done = true; return; }
+                    pat = layout; pos = 0;
                 }
+            }
+            first = false;
+            subEnd = pos + (N >> (pat & 7));
+            const uint32_t hx = __funnelshift_r(cur, nxt, sh);
+            const uint32_t h0 = hx & 15u, h1 = (hx >> 4) & 15u;
+            int len = 1;
+            if (h0 == 15u) q = 30;                          // a lone Fh is an invalid lead-in: the reference's shift by -2 gives scale 0 on x86
+            else if (h0 == 14u) { len = 2; if (h1 == 15u) pos = subEnd; else q = 14 + (int)h1; }   // Eh,Fh: silent sub-block
+            else q = (int)h0;
+            eb = q > 26 ? -1 : (5 + q) << 7;
+            BP_SKIP(len);
+            if (left < 0) { ok = false; done = true; return; }
+            if (pos != subEnd) return;
+        }
+    };
+    boundary(true);
+    while (!done) {
+        x = __funnelshift_r(cur, nxt, sh);
+        const uint32_t v0 = x & 15u, v1 = (x >> 4) & 15u, v2 = (x >> 8) & 15u, v3 = (x >> 12) & 15u;
+        const bool isC = !((0x8103u >> v0) & 1u), isZ = v0 == 0u, isN = v0 == 8u, isQ = v0 == 15u && v1 < 14u;
+        const int n8 = (int)((v1 << 5) | (v2 << 1) | (v3 & 1u)) + 16;
+        int adv = isC ? 1 : (isZ ? (int)v1 + 1 : (isN ? n8 : 0));
+        int len = isC ? 1 : (isN ? 4 : 2);
+        if (!(isC || isZ || isN || isQ)) {
+            // ---- rare tokens ----
+            if (v0 == 1u) { len = 3; adv = (int)((v1 << 4) | v2) + 33; }                          // 1h,Yh,Xh: 33..288 zeros
+            else if (v1 == 14u) {
+                len = 3;
+                if (v2 == 15u) adv = subEnd - pos;                                                // Fh,Eh,Fh: zeros to the end
+                else { q = 14 + (int)v2; eb = q > 26 ? -1 : (5 + q) << 7; }                     // Fh,Eh,0h..Ch (Dh,Eh: scale 0)
+            } else {                                                                              // Fh,Fh,Zh,Yh,Xh: decaying noise to the end
+                len = 5; adv = subEnd - pos;
+                if (EMIT) *(down - 1 - nRun) = make_uint4((uint32_t)pos, (uint32_t)adv, draws,
+                                                          0x80000000u | ((x >> 8) & 0xfffu) | ((uint32_t)q << 12));
                 nRun++;
                 draws += (uint32_t)adv;
-            } else {
-                if (v1 < 14u) { len = 2; q = (int)v1; eb = (5 + q) << 7; }                     // Fh,0h..Dh
-                else if (v1 == 14u) {
-                    len = 3;
-                    if (v2 == 15u) adv = subEnd - pos;                                            // Fh,Eh,Fh: zeros to the end
-                    else { q = 14 + (int)v2; eb = q > 26 ? -1 : (5 + q) << 7; }                 // Fh,Eh,0h..Ch (Dh,Eh: scale 0)
-                } else {                                                                          // Fh,Fh,Zh,Yh,Xh: decaying noise to the end
-                    len = 5; adv = subEnd - pos;
-                    if (EMIT) *(down - 1 - nRun) = make_uint4((uint32_t)pos, (uint32_t)adv, draws,
-                                                              0x80000000u | ((x >> 8) & 0xfffu) | ((uint32_t)q << 12));
-                    nRun++;
-                    draws += (uint32_t)adv;
-                }
             }
         }
         if (adv > subEnd - pos) { ok = false; break; }     // run overshoot: corrupt (ulcDecoder.c:127,139,154)
+        if (isQ) { q = (int)v1; eb = (5 + q) << 7; }       // Fh,0h..Dh
+        if (EMIT) {
+            // -7..-2, +2..+7: sign * v^2 * Quant (ulcDecoder.c:119-124)
+            if (isC && eb >= 0) BP_EMITW(((uint32_t)pos << 16) | (lutAt(v0) - (uint32_t)eb));
+            // 8h,Zh,Yh,Xh: 16..527 noise, level ((X>>1)+1)^2 * Quant / 4
+            if (isN) *(down - 1 - nRun) = make_uint4((uint32_t)pos, (uint32_t)adv, draws, eb >= 0 ? lutAt(16u + (v3 >> 1)) - (uint32_t)eb : 0u);
+        }
+        if (isN) { nRun++; draws += (uint32_t)adv; }
         pos += adv;
         BP_SKIP(len);
-        if (consumed > maxNyb) { ok = false; break; }      // ran off the bytes this block may use
-        if (pos == subEnd) {
-            pat >>= 4;
-            if (!pat) {
-                if (c == 0) { nCoef0 = nw; nRun0 = nRun; }
-                if (++c == NCH) break;
-                pat = layout; pos = 0;
-            }
-            subEnd = pos + (N >> (pat & 7));
-            hdr = true;
-        }
+        if (left < 0) { ok = false; break; }               // ran off the bytes this block may use
+        if (pos == subEnd) boundary(false);
     }
     if (EMIT && (nw & 3u)) *reinterpret_cast<uint4 *>(up + (nw & ~3u)) = make_uint4(e0, e1, e2, 0u);
 #undef BP_SKIP
+#undef BP_ADVANCE
 #undef BP_EMITW
-    o.nyb = consumed; o.wc = wc; o.draws = draws; o.nCoef0 = nCoef0; o.nCoefTot = nw; o.nRun0 = nRun0; o.nRunTot = nRun;
+    o.nyb = maxNyb - (uint32_t)left; o.wc = wc; o.draws = draws; o.nCoef0 = nCoef0; o.nCoefTot = nw; o.nRun0 = nRun0; o.nRunTot = nRun;
     return ok;
 }
 
