@@ -172,6 +172,30 @@ int build_tables(ULCB_Context *ctx) {
         build_window(win, N);
         if ((rc = upload(ctx, win, &tb.win))) return rc;
     }
+    {
+        // FormatSpecs.md:53-131 / libulc/ulcDecoder.c:113-186: token lengths and the coefficients they cover
+        std::vector<uint16_t> lut(65536);
+        for (uint32_t w = 0; w < 65536; w++) {
+            int len = 0, adv = 0;
+            while (len < 4) {
+                const int rem = 4 - len;
+                const int v0 = (w >> (4 * len)) & 15, v1 = (w >> (4 * len + 4)) & 15, v2 = (w >> (4 * len + 8)) & 15, v3 = (w >> (4 * len + 12)) & 15;
+                int tl, ta;
+                if (v0 == 0)       { if (rem < 2) break; tl = 2; ta = v1 + 1; }                                   // 0h,Xh
+                else if (v0 == 1)  { if (rem < 3) break; tl = 3; ta = ((v1 << 4) | v2) + 33; }                    // 1h,Yh,Xh
+                else if (v0 == 8)  { if (rem < 4) break; tl = 4; ta = ((v1 << 5) | (v2 << 1) | (v3 & 1)) + 16; }  // 8h,Zh,Yh,Xh
+                else if (v0 == 15) {
+                    if (rem < 2) break;
+                    if (v1 < 14) { tl = 2; ta = 0; }                                                              // Fh,0h..Dh
+                    else if (v1 == 14) { if (rem < 3 || v2 == 15) break; tl = 3; ta = 0; }                        // Fh,Eh,Xh (Fh,Eh,Fh: stop)
+                    else break;                                                                                   // Fh,Fh: tail
+                } else { tl = 1; ta = 1; }
+                len += tl; adv += ta;
+            }
+            lut[w] = (uint16_t)((len << 10) | adv);
+        }
+        if ((rc = upload(ctx, lut, &tb.walkLut))) return rc;
+    }
     return build_sign_table(ctx, (uint64_t)ctx->maxBlocks * ctx->nChan * N + 256);
 }
 
@@ -385,18 +409,27 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
     a.blockBytes = dBlockBytes; a.blockBytesStride = blockBytesStride;
     a.out = dOut; a.outStride = outStrideElems; a.status = dStatus; a.blockBits = dBlockBits; a.bitsStride = bitsStride;
     a.dbgCoefs = dbgCoefs;
+    {
+        // block byte offsets of the whole call at once: the token-length walk of foreign streams is one lane per stream and
+        // bound by latency, not by how many streams it walks
+        int rc0;
+        if ((rc0 = grow(ctx, &ctx->bpOff, &ctx->bpOffCap, sizeof(uint32_t) * (size_t)nStreams * (maxBlk + 1)))) return rc0;
+        a.s0 = 0; a.nStreams = nStreams; a.base0 = hOffs[0]; a.blkOff = (uint32_t *)ctx->bpOff;
+        int nl = 0;
+        CK(ctx, ulcb_decode_bp_offsets(a, dBlockBytes != nullptr, ctx->smCount, ctx->stream, &nl));
+        ctx->launches += (uint64_t)nl;
+    }
     for (int s0 = 0; s0 < nStreams;) {
         int s1 = s0 + 1;
         while (s1 < nStreams && ulcb_decode_bp_arena_bytes(hOffs[s1 + 1] - hOffs[s0], s1 + 1 - s0, (int)maxBlk) <= cap) s1++;
         const int n = s1 - s0;
-        if ((rc = grow(ctx, &ctx->bpOff, &ctx->bpOffCap, sizeof(uint32_t) * (size_t)n * (maxBlk + 1)))) return rc;
         if ((rc = grow(ctx, &ctx->bpDesc, &ctx->bpDescCap, sizeof(UlcbBpDesc) * (size_t)n * maxBlk))) return rc;
         if ((rc = grow(ctx, &ctx->bpBad, &ctx->bpBadCap, sizeof(int32_t) * (size_t)n))) return rc;
         if ((rc = grow(ctx, &ctx->bpArena, &ctx->bpArenaCap, ulcb_decode_bp_arena_bytes(hOffs[s1] - hOffs[s0], n, (int)maxBlk)))) return rc;
         a.s0 = s0; a.nStreams = n; a.base0 = hOffs[s0];
-        a.blkOff = (uint32_t *)ctx->bpOff; a.desc = (UlcbBpDesc *)ctx->bpDesc; a.firstBad = (int32_t *)ctx->bpBad; a.arena = (uint8_t *)ctx->bpArena;
+        a.blkOff = (uint32_t *)ctx->bpOff + (size_t)s0 * (maxBlk + 1); a.desc = (UlcbBpDesc *)ctx->bpDesc; a.firstBad = (int32_t *)ctx->bpBad; a.arena = (uint8_t *)ctx->bpArena;
         int nl = 0;
-        CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, dBlockBytes != nullptr, ctx->stream, &nl));
+        CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, ctx->stream, &nl));
         ctx->launches += (uint64_t)nl;
         s0 = s1;
     }

@@ -64,7 +64,7 @@ struct UlcbBpArgs {
     int32_t        *status; uint32_t *blockBits; uint64_t bitsStride;
     float          *dbgCoefs;
     // wave scratch
-    uint32_t       *blkOff;           // [nStreams][maxBlk + 1] byte offset of every block in its stream
+    uint32_t       *blkOff;           // [nStreams][maxBlk + 1] byte offset of every block in its stream (first stream = s0)
     UlcbBpDesc     *desc;             // [nStreams][maxBlk]
     int32_t        *firstBad;         // [nStreams] first undecodable block (nBlocks when none)
     uint8_t        *arena;            // sparse block content
@@ -72,4 +72,5 @@ struct UlcbBpArgs {
 
 bool        ulcb_decode_bp_supported(const UlcbTables &tb, int nChan);
 size_t      ulcb_decode_bp_arena_bytes(uint64_t payloadBytes, int nStreams, int maxBlk);
-cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, bool haveIndex, cudaStream_t stream, int *launches);
+cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &args, bool haveIndex, int smCount, cudaStream_t stream, int *launches);
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, cudaStream_t stream, int *launches);

@@ -73,7 +73,7 @@ struct ParseOut { uint32_t nyb, wc, draws, nCoef0, nCoefTot, nRun0, nRunTot; };
 // for the rest (sub-block ends and headers, long zero runs, extended quantisers, stop codes, tails).
 template <bool EMIT>
 __device__ __forceinline__ bool parse_block(const uint8_t *p, const uint32_t *wend, uint32_t maxNyb, const uint16_t *lut,
-                                            uint32_t *up, uint4 *down, ParseOut &o) {
+                                            uint32_t *up, uint4 *down, ParseOut &o, const uint16_t *walkLut = nullptr) {
     // Nybble reader.  A lane reads its block front to back, but 32 lanes of a warp read 32 different blocks: a load that
     // misses stalls the whole warp, and with one miss per lane every ~40 tokens that is a stall on nearly every trip.  So the
     // bytes come in 16-byte loads that are issued a full 16 bytes (~20 tokens) before their first word is needed and wait
@@ -173,7 +173,22 @@ __device__ __forceinline__ bool parse_block(const uint8_t *p, const uint32_t *we
         }
     };
     boundary(true);
+    const unsigned walkAddr = EMIT ? 0u : (unsigned)__cvta_generic_to_shared(walkLut);
     while (!done) {
+        if (!EMIT) {
+            // length-only walk: whole 16-bit windows (up to four tokens) through the table while they stay inside the sub-block;
+            // the token that reaches its end, and every token the table does not take (stop codes, tails), goes the long way
+            for (;;) {
+                x = __funnelshift_r(cur, nxt, sh);
+                unsigned short ev;
+                asm("ld.shared.u16 %0, [%1];" : "=h"(ev) : "r"(walkAddr + 2u * (x & 0xffffu)));
+                const uint32_t e = ev, wl = e >> 10;
+                const int np = pos + (int)(e & 1023u);
+                if (wl == 0u || np >= subEnd) break;
+                pos = np;
+                BP_SKIP(wl);
+            }
+        }
         x = __funnelshift_r(cur, nxt, sh);
         const uint32_t v0 = x & 15u, v1 = (x >> 4) & 15u, v2 = (x >> 8) & 15u, v3 = (x >> 12) & 15u;
         const bool isC = !((0x8103u >> v0) & 1u), isZ = v0 == 0u, isN = v0 == 8u, isQ = v0 == 15u && v1 < 14u;
@@ -258,8 +273,14 @@ __global__ void bp_index_kernel(UlcbBpArgs a) {
 // ------------------------------------------------------------------------------------------------
 // foreign streams (no index): one lane per stream walks the token lengths block after block
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) bp_walk_kernel(UlcbBpArgs a) {
+__global__ void __launch_bounds__(256) bp_walk_kernel(UlcbBpArgs a) {
+    extern __shared__ __align__(16) uint16_t walkLut[];     // 65536 entries (ulcb_tables.h: walkLut)
     __shared__ uint16_t lut[24];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tb.walkLut);
+        uint4 *dst = reinterpret_cast<uint4 *>(walkLut);
+        for (int i = threadIdx.x; i < 65536 * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
     init_lut(lut);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.nStreams) return;
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(128) bp_walk_kernel(UlcbBpArgs a) {
             ParseOut o;
             const uint64_t left = slen - pos;
             const uint32_t maxNyb = left > 0x3fffffffull ? 0x7fffffffu : (uint32_t)(2 * left);
-            if (parse_block<false>(a.bytes + sbeg + pos, a.wend, maxNyb, lut, nullptr, nullptr, o)) pos += (o.nyb + 1) >> 1;
+            if (parse_block<false>(a.bytes + sbeg + pos, a.wend, maxNyb, lut, nullptr, nullptr, o, walkLut)) pos += (o.nyb + 1) >> 1;
             else dead = true;                                       // the rest of the stream cannot be located (README.md:33: no resync)
         } else dead = true;
     }
@@ -989,11 +1010,36 @@ size_t ulcb_decode_bp_arena_bytes(uint64_t payloadBytes, int nStreams, int maxBl
     return (size_t)(16ull * ((payloadBytes + 1) >> 1) + 32ull * (uint64_t)nStreams * (uint64_t)(maxBlk + 1) + 256ull);
 }
 
-cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, bool haveIndex, cudaStream_t stream, int *launches) {
+// Block byte offsets of every stream of the call (a.s0 = 0, a.nStreams = all, a.blkOff = the call's table): from the caller's
+// block-size index, or by walking the token lengths of foreign streams.
+cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &a, bool haveIndex, int smCount, cudaStream_t stream, int *launches) {
+    if (a.nStreams <= 0 || a.maxBlk <= 0) return cudaSuccess;
+    if (haveIndex) {
+        const int wpc = 4;
+        bp_index_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
+    } else {
+        // one lane per stream, latency-bound: spread the lanes over all SMs, one warp per CTA until there are more warps than SMs
+        int warps = (a.nStreams + 32 * smCount - 1) / (32 * smCount);
+        if (warps < 1) warps = 1;
+        if (warps > 8) warps = 8;
+        const int thr = 32 * warps;
+        const size_t smem = 65536 * sizeof(uint16_t);
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(bp_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
+        bp_walk_kernel<<<(a.nStreams + thr - 1) / thr, thr, smem, stream>>>(a);
+    }
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// One wave: parse -> scan -> transform (a.blkOff points at the wave's first stream).
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, cudaStream_t stream, int *launches) {
     if (a.nStreams <= 0 || a.maxBlk <= 0) return cudaSuccess;
     const int wpc = 4;                                            // warps per CTA of the per-stream kernels
-    if (haveIndex) bp_index_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
-    else           bp_walk_kernel<<<(a.nStreams + 127) / 128, 128, 0, stream>>>(a);
     const long long nThr = (long long)a.nStreams * a.maxBlk;
     bp_parse_kernel<<<(unsigned)((nThr + 127) / 128), 128, 0, stream>>>(a);
     bp_scan_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
@@ -1006,6 +1052,6 @@ cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, bool haveIndex
         if (pcm16) bp_transform_kernel<true, false><<<(unsigned)grid, 64, 0, stream>>>(a);
         else       bp_transform_kernel<false, false><<<(unsigned)grid, 64, 0, stream>>>(a);
     }
-    if (launches) *launches += 4;
+    if (launches) *launches += 3;
     return cudaGetLastError();
 }
