@@ -173,28 +173,52 @@ int build_tables(ULCB_Context *ctx) {
         if ((rc = upload(ctx, win, &tb.win))) return rc;
     }
     {
-        // FormatSpecs.md:53-131 / libulc/ulcDecoder.c:113-186: token lengths and the coefficients they cover
-        std::vector<uint16_t> lut(65536);
-        for (uint32_t w = 0; w < 65536; w++) {
-            int len = 0, adv = 0;
-            while (len < 4) {
-                const int rem = 4 - len;
-                const int v0 = (w >> (4 * len)) & 15, v1 = (w >> (4 * len + 4)) & 15, v2 = (w >> (4 * len + 8)) & 15, v3 = (w >> (4 * len + 12)) & 15;
-                int tl, ta;
-                if (v0 == 0)       { if (rem < 2) break; tl = 2; ta = v1 + 1; }                                   // 0h,Xh
-                else if (v0 == 1)  { if (rem < 3) break; tl = 3; ta = ((v1 << 4) | v2) + 33; }                    // 1h,Yh,Xh
-                else if (v0 == 8)  { if (rem < 4) break; tl = 4; ta = ((v1 << 5) | (v2 << 1) | (v3 & 1)) + 16; }  // 8h,Zh,Yh,Xh
-                else if (v0 == 15) {
-                    if (rem < 2) break;
-                    if (v1 < 14) { tl = 2; ta = 0; }                                                              // Fh,0h..Dh
-                    else if (v1 == 14) { if (rem < 3 || v2 == 15) break; tl = 3; ta = 0; }                        // Fh,Eh,Xh (Fh,Eh,Fh: stop)
-                    else break;                                                                                   // Fh,Fh: tail
-                } else { tl = 1; ta = 1; }
-                len += tl; adv += ta;
+        // Token-length automaton of the foreign-stream walk (ulcb_decode_bp.cu: bp_walk_kernel), after FormatSpecs.md:53-131 /
+        // libulc/ulcDecoder.c:113-186.  States: 0 token start, 1 after 0h, 2 after 1h, 3 after 1h,Yh, 4 after 8h, 5 after 8h,Zh,
+        // 6 after 8h,Zh,Yh, 7 after Fh, 8 after Fh,Eh.
+        auto step1 = [](int st, int v, int *adv, int *stop) -> int {
+            *adv = 0; *stop = 0;
+            switch (st) {
+            case 0: if (v == 0) return 1; if (v == 1) return 2; if (v == 8) return 4; if (v == 15) return 7; *adv = 1; return 0;
+            case 1: *adv = v + 1; return 0;                    // 0h,Xh: 1..16 zeros
+            case 2: *adv = 16 * v + 33; return 3;              // 1h,Yh,Xh: 33..288 zeros
+            case 3: *adv = v; return 0;
+            case 4: *adv = 32 * v + 16; return 5;              // 8h,Zh,Yh,Xh: 16..527 noise
+            case 5: *adv = 2 * v; return 6;
+            case 6: *adv = v & 1; return 0;
+            case 7: if (v < 14) return 0; if (v == 14) return 8; *stop = 2; return 0;   // Fh,0h..Dh / Fh,Eh,.. / Fh,Fh,..
+            default: if (v == 15) *stop = 1; return 0;         // Fh,Eh,0h..Eh quantiser / Fh,Eh,Fh stop
             }
-            lut[w] = (uint16_t)((len << 10) | adv);
+        };
+        // u64 MAP[4096]: for three nybbles, the next state of every entry state k as 4 k' in bits 4k+2..4k+5;
+        // u16 ADV[9][4096]: coefficients the three nybbles cover from entry state k | stop flag << 15;
+        // u32 T1[9][16]: one nybble from state k: 4 k' << 16 | Fh,Fh tail << 12 | Fh,Eh,Fh stop << 11 | coefficients
+        std::vector<uint32_t> tab(4096 * 2 + 9 * 4096 / 2 + 9 * 16);
+        uint64_t *mapT = reinterpret_cast<uint64_t *>(tab.data());
+        uint16_t *advT = reinterpret_cast<uint16_t *>(tab.data() + 4096 * 2);
+        uint32_t *t1 = tab.data() + 4096 * 2 + 9 * 4096 / 2;
+        for (int x = 0; x < 4096; x++) {
+            uint64_t mp = 0;
+            for (int st = 0; st < 9; st++) {
+                int cs = st, total = 0, flag = 0;
+                for (int k = 0; k < 3 && !flag; k++) {
+                    int adv, stop;
+                    cs = step1(cs, (x >> (4 * k)) & 15, &adv, &stop);
+                    total += adv;
+                    if (stop) flag = 1;
+                }
+                if (!flag) mp |= (uint64_t)cs << (4 * st + 2);
+                advT[(size_t)st * 4096 + x] = (uint16_t)(flag ? 0x8000 : total);
+            }
+            mapT[x] = mp;
         }
-        if ((rc = upload(ctx, lut, &tb.walkLut))) return rc;
+        for (int st = 0; st < 9; st++)
+            for (int v = 0; v < 16; v++) {
+                int adv, stop;
+                const int ns = step1(st, v, &adv, &stop);
+                t1[st * 16 + v] = stop ? (stop == 2 ? 0x1000u : 0x800u) : ((uint32_t)(4 * ns) << 16) | (uint32_t)adv;
+            }
+        if ((rc = upload(ctx, tab, &tb.walkTab))) return rc;
     }
     return build_sign_table(ctx, (uint64_t)ctx->maxBlocks * ctx->nChan * N + 256);
 }

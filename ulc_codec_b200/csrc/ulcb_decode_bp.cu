@@ -73,7 +73,7 @@ struct ParseOut { uint32_t nyb, wc, draws, nCoef0, nCoefTot, nRun0, nRunTot; };
 // for the rest (sub-block ends and headers, long zero runs, extended quantisers, stop codes, tails).
 template <bool EMIT>
 __device__ __forceinline__ bool parse_block(const uint8_t *p, const uint32_t *wend, uint32_t maxNyb, const uint16_t *lut,
-                                            uint32_t *up, uint4 *down, ParseOut &o, const uint16_t *walkLut = nullptr) {
+                                            uint32_t *up, uint4 *down, ParseOut &o) {
     // Nybble reader.  A lane reads its block front to back, but 32 lanes of a warp read 32 different blocks: a load that
     // misses stalls the whole warp, and with one miss per lane every ~40 tokens that is a stall on nearly every trip.  So the
     // bytes come in 16-byte loads that are issued a full 16 bytes (~20 tokens) before their first word is needed and wait
@@ -173,22 +173,7 @@ __device__ __forceinline__ bool parse_block(const uint8_t *p, const uint32_t *we
         }
     };
     boundary(true);
-    const unsigned walkAddr = EMIT ? 0u : (unsigned)__cvta_generic_to_shared(walkLut);
     while (!done) {
-        if (!EMIT) {
-            // length-only walk: whole 16-bit windows (up to four tokens) through the table while they stay inside the sub-block;
-            // the token that reaches its end, and every token the table does not take (stop codes, tails), goes the long way
-            for (;;) {
-                x = __funnelshift_r(cur, nxt, sh);
-                unsigned short ev;
-                asm("ld.shared.u16 %0, [%1];" : "=h"(ev) : "r"(walkAddr + 2u * (x & 0xffffu)));
-                const uint32_t e = ev, wl = e >> 10;
-                const int np = pos + (int)(e & 1023u);
-                if (wl == 0u || np >= subEnd) break;
-                pos = np;
-                BP_SKIP(wl);
-            }
-        }
         x = __funnelshift_r(cur, nxt, sh);
         const uint32_t v0 = x & 15u, v1 = (x >> 4) & 15u, v2 = (x >> 8) & 15u, v3 = (x >> 12) & 15u;
         const bool isC = !((0x8103u >> v0) & 1u), isZ = v0 == 0u, isN = v0 == 8u, isQ = v0 == 15u && v1 < 14u;
@@ -270,37 +255,248 @@ __global__ void bp_index_kernel(UlcbBpArgs a) {
     if (lane == 0) off[nb] = (uint32_t)(run < slen ? run : slen);
 }
 
-// ------------------------------------------------------------------------------------------------
-// foreign streams (no index): one lane per stream walks the token lengths block after block
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bp_walk_kernel(UlcbBpArgs a) {
-    extern __shared__ __align__(16) uint16_t walkLut[];     // 65536 entries (ulcb_tables.h: walkLut)
-    __shared__ uint16_t lut[24];
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.tb.walkLut);
-        uint4 *dst = reinterpret_cast<uint4 *>(walkLut);
-        for (int i = threadIdx.x; i < 65536 * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+// ---- mbarrier / TMA bulk-copy helpers ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();                 // a copy that never lands is a bug, not a reason to hang the GPU
     }
-    init_lut(lut);
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// foreign streams (no index): one lane per stream walks the token lengths of the whole stream
+// ------------------------------------------------------------------------------------------------
+// A .ulc payload carries no block index (tools/ulc_Helper.h:10-20): where block k+1 starts is only known after the tokens of
+// block k have been walked (what tools/ulcDecodeTool.c:153-164 does by decoding).  The walk is one dependent chain per stream,
+// so its cost is the latency of ONE step times the steps of one stream, however many streams there are.  The step here is a
+// table-driven automaton over the token grammar (ulcDecoder.c:113-186): nine states (token start; inside 0h,X / 1h,Y,X /
+// 8h,Z,Y,X; after Fh; after Fh,Eh), and shared-memory tables that take a state and THREE nybbles to the next state (NEXT) and to
+// the number of coefficients those nybbles cover (ADV; a multi-nybble run is accounted piecewise: 8h,Z,Y,X = (32 Z + 16) + 2 Y +
+// (X & 1)).  Eight steps (24 nybbles = three words) are looked up back to back with no check in between, so the chain per step
+// is one shared-memory load and one address add; the checks come after.  A group that would reach the end of its sub-block (or
+// holds a stop code) commits only its leading steps; the rest is walked one nybble at a time, and a finished sub-block goes
+// through the header / window-control code.  Lanes in those paths hold up their warp, so a call with few streams runs with few
+// active lanes per warp (and more warps) - the SMs are otherwise empty.
+constexpr int WALK_STATES = 9;
+// ulcb_tables.h: walkTab = u64 MAP[4096] (for three nybbles: the next state of every entry state k, as 4 k' in bits 4k+2..4k+5),
+// u16 ADV[9][4096] (coefficients the three nybbles cover from entry state k | stop flag << 15), then u32 T1[9][16] one-nybble
+// steps (4 k' << 16 | TAIL << 12 | ZEROS << 11 | coefficients).  A state is carried as 4 k: the shift that extracts its field.
+constexpr uint32_t WALK_MAP_BYTES = 4096 * 8, WALK_ADV_BYTES = WALK_STATES * 4096 * 2, WALK_T1_BYTES = WALK_STATES * 16 * 4;
+constexpr uint32_t WALK_TAB_BYTES = WALK_MAP_BYTES + WALK_ADV_BYTES + WALK_T1_BYTES;
+constexpr uint32_t WALK_FLAG = 0x800u, WALK_TAIL = 0x1000u;
+
+// Each lane streams its own 1 MB-scale stream, and thousands of lanes doing so with 16-byte loads are bound by address
+// translation and DRAM row misses, not by their arithmetic (measured: 160 ms for 4096 streams whatever the step cost).  So the
+// bytes come in bulk: every lane owns a two-slot ring in shared memory and has the TMA engine (cp.async.bulk + one mbarrier per
+// slot) fetch the next WALK_CHUNK contiguous bytes of its stream while it walks the current ones.
+constexpr int WALK_CHUNK = 512, WALK_SLOTW = WALK_CHUNK / 4;          // bytes / words of stream per ring slot ...
+constexpr int WALK_COPYW = WALK_SLOTW + 4;                             // ... each copied with the first 16 bytes of the next chunk, so that a
+                                                                       // few words read ahead never leave the slot
+constexpr int WALK_RINGW = 2 * WALK_COPYW;                             // words per lane
+constexpr int WALK_MAXLANES = 96;                                      // lanes per CTA
+
+// the last bytes of the whole input do not make a full bulk copy: word by word, zero beyond the readable end
+__device__ __noinline__ void walk_fill_tail(uint32_t *dst, const uint32_t *ws, const uint32_t *wend, unsigned long long *mb) {
+    for (int i = 0; i < WALK_COPYW; i++) dst[i] = (ws + i < wend) ? __ldg(ws + i) : 0u;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mb)) : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1) bp_walk_kernel(UlcbBpArgs a, int lanes) {
+    extern __shared__ __align__(16) uint32_t wtab[];        // ulcb_tables.h: walkTab
+    uint32_t *rings = wtab + WALK_TAB_BYTES / 4;                                                   // [WALK_MAXLANES][WALK_RINGW]
+    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(rings + WALK_MAXLANES * WALK_RINGW);   // [WALK_MAXLANES][2]
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tb.walkTab);
+        uint4 *dst = reinterpret_cast<uint4 *>(wtab);
+        for (int i = threadIdx.x; i < (int)(WALK_TAB_BYTES / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const int lane = threadIdx.x & 31;
+    const int slotIdx = (threadIdx.x >> 5) * lanes + lane;  // this lane's ring
+    const bool active = lane < lanes;
+    if (active) {
+        mbar_init(&mbars[2 * slotIdx], 1); mbar_init(&mbars[2 * slotIdx + 1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (!active) return;
+    const int s = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes + lane;
     if (s >= a.nStreams) return;
     const int gs = a.s0 + s;
     const int nb = a.nBlocks ? (int)a.nBlocks[gs] : a.nBlocksAll;
     uint32_t *off = a.blkOff + (size_t)s * (a.maxBlk + 1);
     const uint64_t sbeg = a.streamOffs[gs], slen = a.streamOffs[gs + 1] - sbeg;
-    uint64_t pos = 0;
+    const uint32_t endNyb = slen > 0x3fffffffull ? 0x7ffffffeu : (uint32_t)(2 * slen);
+
+    // ---- the ring: chunk k of the stream (WALK_CHUNK bytes from the 16-byte aligned start) lives in slot k & 1 ----
+    const uint8_t *p = a.bytes + sbeg;
+    const uintptr_t pa = reinterpret_cast<uintptr_t>(p);
+    const char *vbase = reinterpret_cast<const char *>(pa & ~(uintptr_t)15);
+    const char *bulkEnd = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(a.wend) & ~(uintptr_t)15);   // bulk copies stay below
+    uint32_t *ring = rings + slotIdx * WALK_RINGW;
+    unsigned long long *mb = &mbars[2 * slotIdx];
+    const unsigned ringAddr = smem_u32(ring);
+    auto fill = [&](uint32_t k) {
+        const char *src = vbase + (size_t)k * WALK_CHUNK;
+        uint32_t *dst = ring + (k & 1u) * WALK_COPYW;
+        if (src + 4 * WALK_COPYW <= bulkEnd) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&mb[k & 1u], 4 * WALK_COPYW);
+            tma_load(dst, src, 4 * WALK_COPYW, &mb[k & 1u]);
+        } else walk_fill_tail(dst, reinterpret_cast<const uint32_t *>(src), a.wend, &mb[k & 1u]);
+    };
+    // Reader state: w0..w3 = the word that holds the current nybble (at bit sh) and the three after it; wpos = the word after w3,
+    // rpos = its shared-memory address, inside chunk kc, which ends at word hk.  Reads are sequential: when the reader enters
+    // chunk k, chunk k - 1 is done with and its slot takes chunk k + 1.
+    uint32_t wpos = (uint32_t)((pa & 15) >> 2), kc = 0, hk = WALK_SLOTW, par = 0;
+    fill(0); fill(1);
+    mbar_wait(&mb[0], 0); par = 1u;
+    unsigned rpos = ringAddr + 4u * wpos;
+    auto cross = [&]() {                                    // wpos has reached hk: on to the next chunk
+        kc++;
+        mbar_wait(&mb[kc & 1u], (par >> (kc & 1u)) & 1u); par ^= 1u << (kc & 1u);
+        fill(kc + 1u);
+        rpos = ringAddr + 4u * ((kc & 1u) * WALK_COPYW + (wpos - kc * WALK_SLOTW));
+        hk += WALK_SLOTW;
+    };
+    auto rd = [&](unsigned ofs) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(rpos + ofs));
+        return v;
+    };
+    uint32_t w0 = rd(0), w1 = rd(4), w2 = rd(8), w3 = rd(12);
+    wpos += 4u; rpos += 16u;
+    uint32_t sh = 8u * (uint32_t)(pa & 3), nyb = 0;         // nyb = nybbles consumed since the start of the stream
+#define WK_SKIP(k)                                                                           \
+    do {                                                                                     \
+        const uint32_t k_ = (uint32_t)(k);                                                   \
+        sh += 4u * k_; nyb += k_;                                                            \
+        if (sh >= 32u) { sh -= 32u; if (wpos >= hk) cross(); w0 = w1; w1 = w2; w2 = w3; w3 = rd(0); wpos++; rpos += 4u; } \
+    } while (0)
+
+    // start as if a block had just ended: the first trip takes the boundary path, which opens block 0
+    int b = -1, c = NCH - 1, pos = 0, subEnd = 0;
+    uint32_t pat = 0, layout = 0, st = 0;                   // st = 4 * state
     bool dead = false;
-    for (int b = 0; b < nb; b++) {
-        off[b] = (uint32_t)pos;
-        if (!dead && pos < slen) {
-            ParseOut o;
-            const uint64_t left = slen - pos;
-            const uint32_t maxNyb = left > 0x3fffffffull ? 0x7fffffffu : (uint32_t)(2 * left);
-            if (parse_block<false>(a.bytes + sbeg + pos, a.wend, maxNyb, lut, nullptr, nullptr, o, walkLut)) pos += (o.nyb + 1) >> 1;
-            else dead = true;                                       // the rest of the stream cannot be located (README.md:33: no resync)
-        } else dead = true;
+    const char *tabB = reinterpret_cast<const char *>(wtab);
+    // the group of eight three-nybble steps (24 nybbles = three words) at the reader's position: xs = 2 * (twelve bits of step j),
+    // m = their state maps.  Carried from trip to trip: a trip prepares the following group while its own chain runs.
+    uint32_t xs[8];
+    uint2 m[8];
+    auto window = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t (&x)[8], uint2 (&mm)[8]) {
+        x[0] = (a0 << 1) & 0x1ffeu;  x[1] = (a0 >> 11) & 0x1ffeu;  x[2] = (__funnelshift_r(a0, a1, 24) << 1) & 0x1ffeu;
+        x[3] = (a1 >> 3) & 0x1ffeu;  x[4] = (a1 >> 15) & 0x1ffeu;  x[5] = (__funnelshift_r(a1, a2, 28) << 1) & 0x1ffeu;
+        x[6] = (a2 >> 7) & 0x1ffeu;  x[7] = (a2 >> 19) & 0x1ffeu;
+#pragma unroll
+        for (int j = 0; j < 8; j++) mm[j] = *reinterpret_cast<const uint2 *>(tabB + 4u * x[j]);
+    };
+    window(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), xs, m);
+    for (;;) {
+        if (wpos >= hk) cross();
+        const uint32_t n4 = rd(0), n5 = rd(4), n6 = rd(8);
+        // the chain: two operations per step, no check in between
+        uint32_t sj[9];
+        sj[0] = st;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sj[j + 1] = __funnelshift_rc(m[j].x, m[j].y, sj[j]) & 0x3cu;
+        uint32_t av[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) av[j] = *reinterpret_cast<const uint16_t *>(tabB + WALK_MAP_BYTES + 2048u * sj[j] + xs[j]);
+        // the following group, should this one stand
+        uint32_t xsN[8];
+        uint2 mN[8];
+        window(__funnelshift_r(w3, n4, sh), __funnelshift_r(n4, n5, sh), __funnelshift_r(n5, n6, sh), xsN, mN);
+        const uint32_t sum = ((av[0] + av[1] + av[2]) + (av[3] + av[4] + av[5])) + (av[6] + av[7]);   // stop flags land in bits 15-18
+        if (sum < 0x8000u && pos + (int)sum < subEnd && nyb + 24u <= endNyb) {
+            pos += (int)sum; st = sj[8]; nyb += 24u;
+            w0 = w3; w1 = n4; w2 = n5; w3 = n6; wpos += 3u; rpos += 12u;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { xs[j] = xsN[j]; m[j] = mN[j]; }
+            continue;
+        }
+        // A group that holds a stop code or reaches the end of its sub-block: its leading steps stand ...
+        {
+            int jn = 0;
+            bool go = true;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                go = go && av[j] < 0x8000u && pos + (int)av[j] < subEnd && nyb + 3u * (uint32_t)(j + 1) <= endNyb;
+                if (go) { pos += (int)av[j]; st = sj[j + 1]; jn++; }
+            }
+#pragma unroll 1
+            for (; jn > 0; jn--) WK_SKIP(3);
+        }
+        // ... and the rest goes nybble by nybble up to and through the end of the sub-block
+        bool fin = false;
+        for (;;) {
+            if (st == 0u && pos >= subEnd) {
+                if (pos > subEnd) { dead = true; fin = true; break; }       // run overshoot: corrupt (ulcDecoder.c:127,139,154)
+                for (;;) {
+                    pat >>= 4;
+                    if (!pat) {
+                        if (++c == NCH) {
+                            // block end: it ends inside its last byte (ulcEncoder_Encode.c:357-358); next block's window control
+                            if (nyb & 1u) WK_SKIP(1);
+                            if (nyb > endNyb) { dead = true; fin = true; break; }
+                            b++;
+                            off[b] = nyb >> 1;
+                            if (b == nb) { fin = true; break; }
+                            if (nyb >= endNyb) { dead = true; fin = true; break; }
+                            const uint32_t wx = __funnelshift_r(w0, w1, sh);
+                            uint32_t wc;
+                            if (wx & 8u) { wc = wx & 0xffu; WK_SKIP(2); }            // ulcDecoder.c:211-216
+                            else         { wc = (wx & 15u) | 0x10u; WK_SKIP(1); }
+                            layout = kLayoutBp[wc >> 4];
+                            c = 0;
+                        }
+                        pat = layout; pos = 0;
+                    }
+                    subEnd = pos + (N >> (pat & 7));
+                    const uint32_t hx = __funnelshift_r(w0, w1, sh);               // sub-block header: a bare quantiser (ulcDecoder.c:103-112)
+                    if ((hx & 15u) == 14u) {
+                        WK_SKIP(2);
+                        if (((hx >> 4) & 15u) == 15u) { pos = subEnd; continue; }   // Eh,Fh: silent sub-block
+                    } else WK_SKIP(1);
+                    break;
+                }
+                break;
+            }
+            if (nyb >= endNyb) { dead = true; fin = true; break; }          // ran off the stream
+            const uint32_t x = __funnelshift_r(w0, w1, sh);
+            const uint32_t t = wtab[(WALK_MAP_BYTES + WALK_ADV_BYTES) / 4 + 4u * st + (x & 15u)];
+            WK_SKIP(1);
+            if (t & (WALK_FLAG | WALK_TAIL)) {              // Fh,Eh,Fh: zeros to the end / Fh,Fh,Zh,Yh,Xh: decaying noise to the end
+                if (t & WALK_TAIL) WK_SKIP(3);
+                pos = subEnd; st = 0u;
+            } else { pos += (int)(t & 0x7ffu); st = t >> 16; }
+        }
+        if (fin) break;
+        window(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), xs, m);
     }
-    off[nb] = (uint32_t)pos;
+#undef WK_SKIP
+    // the chunk fetched ahead may still be in flight: it must land before this CTA's shared memory is given away
+    mbar_wait(&mb[(kc + 1u) & 1u], (par >> ((kc + 1u) & 1u)) & 1u);
+    if (dead) {
+        // the rest of the stream cannot be located (README.md:33: no resync): block b, where the walk died, and all after it are empty
+        if (b < 0) { b = 0; off[0] = 0; }
+        const uint32_t o = off[b];
+        for (int k = b + 1; k <= nb; k++) off[k] = o;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -462,29 +658,6 @@ struct CtaSm {
 };
 constexpr int COEF16_OFS = 4224;  // byte offset of the bf16 coefficient array of a window-switched block inside zb (the
                                   // sub-block scratch occupies the first 4 KB)
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
-    unsigned done = 0;
-    for (unsigned spins = 0; !done; spins++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
-        if (spins > (1u << 24)) __trap();                 // a copy that never lands is a bug, not a reason to hang the GPU
-    }
-}
-// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
 
 // what one warp needs to know about one block
 struct BlkInfo {
@@ -1018,19 +1191,20 @@ cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &a, bool haveIndex, int smCo
         const int wpc = 4;
         bp_index_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
     } else {
-        // one lane per stream, latency-bound: spread the lanes over all SMs, one warp per CTA until there are more warps than SMs
-        int warps = (a.nStreams + 32 * smCount - 1) / (32 * smCount);
+        // one lane per stream, latency-bound: few streams run with few active lanes per warp (divergence between the lanes of
+        // a warp is what the walk pays for), up to 8 warps per SM; many streams fill the warps
+        int lanes = 32;
+        while (lanes > 1 && (long long)a.nStreams * 2 <= (long long)lanes * smCount * 8) lanes >>= 1;
+        if (const char *e = getenv("ULCB_WALK_LANES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v; }
+        const long long warpsTotal = ((long long)a.nStreams + lanes - 1) / lanes;
+        int warps = (int)((warpsTotal + smCount - 1) / smCount);
         if (warps < 1) warps = 1;
-        if (warps > 8) warps = 8;
-        const int thr = 32 * warps;
-        const size_t smem = 65536 * sizeof(uint16_t);
-        static bool attr = false;
-        if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(bp_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            attr = true;
-        }
-        bp_walk_kernel<<<(a.nStreams + thr - 1) / thr, thr, smem, stream>>>(a);
+        if (warps > 16) warps = 16;
+        if (warps * lanes > WALK_MAXLANES) warps = WALK_MAXLANES / lanes;     // one ring per lane
+        const size_t smem = (size_t)WALK_TAB_BYTES + (size_t)WALK_MAXLANES * WALK_RINGW * sizeof(uint32_t) + WALK_MAXLANES * 16;
+        cudaError_t e = cudaFuncSetAttribute(bp_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+        if (e != cudaSuccess) return e;
+        bp_walk_kernel<<<(unsigned)((warpsTotal + warps - 1) / warps), 32 * warps, smem, stream>>>(a, lanes);
     }
     if (launches) *launches += 1;
     return cudaGetLastError();
