@@ -178,12 +178,42 @@ def cpu_reference_encode(quality: float = 50.0, seconds: float = 30.0):
             "sample": f"{cores} procs x one {seconds:g} s stream, oracle/_ref/ulcencodetool_avx -{quality:g} (unmodified reference, AVX/FMA build), WAV in /dev/shm"}
 
 
+def verify_encode(torch, ctx, capi, rank, n_streams, ns, nb, out, ostride, bb, n_verify: int = 16, quality: float = 50.0):
+    """Compares a strided sample of the encoded streams (first, last, spread over the launch) with the oracle encoder on the same
+    PCM: block sizes and bytes.  BASELINE.json allows a quantisation-boundary flip in at most 0.1 % of blocks."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    from ulc_codec_b200 import corpus
+    slots = sorted({0, n_streams - 1, *np.linspace(0, n_streams - 1, n_verify).astype(int).tolist()})
+
+    def ref(s):
+        pcm = corpus.generate(rank * n_streams + s, ns, "music")
+        return s, oracle.Encoder(RATE, NCH, N).encode_stream(pcm, "vbr", quality, 0.0)
+    with ThreadPoolExecutor(min(32, os.cpu_count() or 1)) as ex:
+        refs = dict(ex.map(ref, slots))
+    bbh = bb.view(n_streams, nb)
+    diff = tot = 0
+    for s in slots:
+        r = refs[s]
+        sizes = bbh[s].cpu().numpy().astype(np.int64)
+        got = out[s * ostride:s * ostride + int(sizes.sum())].cpu().numpy()
+        rs = r["block_bytes"].astype(np.int64)
+        go = np.concatenate([[0], np.cumsum(sizes)]); ro = np.concatenate([[0], np.cumsum(rs)])
+        for b in range(nb):
+            tot += 1
+            if sizes[b] != rs[b] or not np.array_equal(got[go[b]:go[b + 1]], r["data"][ro[b]:ro[b + 1]]):
+                diff += 1
+    if diff > 1e-3 * tot + 1:
+        raise AssertionError(f"bench verification: {diff} of {tot} encoded blocks differ from the oracle")
+    return {"streams": len(slots), "blocks": tot, "blocks_differing": diff, "against": "oracle.Encoder (byte comparison per block)"}
+
+
 def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, warmup, peaks, with_cpu):
     """configs[2]: batched VBR Quality 50 encode, 60 s stereo streams, BlockSize 2048, PCM16 in, corpus generated on the device."""
     ns = STREAM_SECONDS * RATE
     nb = ctx.blocks_for(ns)
-    stride = ns * NCH
-    pcm = torch.empty(n_streams * stride, dtype=torch.int16, device=dev)
+    stride = nb * N * NCH                                           # whole blocks: the lead-out past the samples is silence
+    pcm = torch.zeros(n_streams * stride, dtype=torch.int16, device=dev)
     ctx.generate_corpus_device("music", rank * n_streams, n_streams, ns, pcm.data_ptr(), stride)
     ostride = nb * 640                                               # VBR Q50 averages ~460 B/block on this corpus
     out = torch.empty(n_streams * ostride, dtype=torch.uint8, device=dev)
@@ -223,6 +253,7 @@ def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, war
                     "avg_bytes_per_block": out_bytes / (n_streams * nb)},
          "roofline": {"bound": "hbm", "kernel": "ulcb_encode_kernel<2,512,false>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                       "algorithmic_bytes_per_launch": algo, "launch_ms": ms, "traffic": measured_traffic("encode", n_streams, nb)},
+         "verified_streams": verify_encode(torch, ctx, capi, rank, n_streams, ns, nb, out, ostride, bb),
          "gpu_launches": steps}
     if with_cpu:
         c = cpu_reference_encode()
@@ -233,16 +264,140 @@ def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, war
 
 # ------------------------------------------------------------------------------------------------
 
+def build_id() -> str:
+    """Hash of the CUDA sources the loaded library was built from (profiles/traffic.json is keyed by it)."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, "ulc_codec_b200", "csrc", "*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:12]
+
+
 def measured_traffic(kernel: str, n_streams: int, n_blocks: int):
-    """DRAM bytes (read + write) of one launch of `kernel`, from the committed `ncu --set full` capture of the same
-    launch shape (profiles/traffic.json, written by scripts/ncu_traffic.py).  None when the shapes differ."""
+    """DRAM bytes (read + write) per step of `kernel`, from the committed `ncu --set full` capture of the same launch shape AND the
+    same build (profiles/traffic.json, written by scripts/ncu_traffic.py).  None when shape or build differ."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
     except Exception:
         return None
-    if t.get("streams") != n_streams or t.get("blocks") != n_blocks:
+    if t.get("streams") != n_streams or t.get("blocks") != n_blocks or t.get("build") != build_id():
         return None
     return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+
+
+def make_streams(pool, n_distinct: int, seed0: int, n_blocks: int = BLOCKS_PER_STREAM):
+    """n_distinct streams of n_blocks pool blocks each.  Returns (streams, block-size index uint32[n_distinct, n_blocks])."""
+    sizes = np.array([len(b) for b in pool], np.uint32)
+    streams, idx = [], np.zeros((n_distinct, n_blocks), np.uint32)
+    for d in range(n_distinct):
+        rng = np.random.default_rng(0x9E3779B9 * (seed0 + d + 1) & 0xFFFFFFFF)
+        sel = rng.integers(0, len(pool), n_blocks)
+        streams.append(np.concatenate([pool[i] for i in sel]))
+        idx[d] = sizes[sel]
+    return streams, idx
+
+
+class DecodeBatch:
+    """A device-resident decode batch: n_streams slots filled from n_distinct distinct streams in an order in which neighbours
+    (and slots one launch wave apart) differ."""
+
+    def __init__(self, torch, dev, distinct, index, n_streams: int):
+        self.torch, self.n_streams, self.n_distinct = torch, n_streams, len(distinct)
+        self.distinct, self.index = distinct, index
+        nd = self.n_distinct
+        self.order = [(s * 7 + s // nd) % nd for s in range(n_streams)]
+        lens = np.array([len(distinct[o]) for o in self.order], np.uint64)
+        self.offs = np.zeros(n_streams + 1, np.uint64)
+        self.offs[1:] = np.cumsum(lens)
+        self.total_in = int(self.offs[-1])
+        d_dist = [torch.from_numpy(d).to(dev) for d in distinct]
+        self.d_bytes = torch.empty(self.total_in + 64, dtype=torch.uint8, device=dev)
+        for s, o in enumerate(self.order):
+            self.d_bytes[int(self.offs[s]):int(self.offs[s + 1])] = d_dist[o]
+        self.d_bytes[self.total_in:] = 0
+        del d_dist
+        self.d_offs = torch.from_numpy(self.offs.view(np.int64)).to(dev)
+        self.d_index = torch.from_numpy(index.view(np.int32)).to(dev)[torch.tensor(self.order, device=dev)].contiguous()
+        self.stride = BLOCKS_PER_STREAM * N * NCH
+        self.d_status = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+
+
+def time_steps(torch, dist, ctx, ext, dev, world, step, steps: int, clock_gpu=None):
+    """Times `steps` calls of step() with CUDA events on the library's stream; returns (ms per step over the whole region as
+    the max over ranks, mean ms of the individual steps, clocks summary or None)."""
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    clk = ClockSampler(clock_gpu) if clock_gpu is not None else None
+    if clk:
+        clk.__enter__()
+    t0.record(ext)
+    for a, b in evs:
+        a.record(ext); step(); b.record(ext)
+    t1.record(ext)
+    ctx.sync()
+    torch.cuda.synchronize()
+    if clk:
+        clk.__exit__()
+    total = t0.elapsed_time(t1)
+    each = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if world > 1:
+        t = torch.tensor([total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+        dist.barrier()
+    return total / steps, each, (clk.summary() if clk else None)
+
+
+def verify_decode(torch, batch: DecodeBatch, d_out, n_verify: int = 64):
+    """Copies back a strided sample of the decoded streams (first, last, and slots spread over every launch wave) and compares each
+    with the oracle decoder: PCM16 within +-1 LSB, whole stream.  Returns the number of streams verified (raises on a mismatch)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    ns = batch.n_streams
+    slots = sorted({0, ns - 1, *np.linspace(0, ns - 1, n_verify).astype(int).tolist()})
+    need = sorted({batch.order[s] for s in slots})
+
+    def ref(o):
+        f, bits = oracle.Decoder(NCH, N).decode_stream(batch.distinct[o], BLOCKS_PER_STREAM)
+        assert (bits != 0).all()
+        return o, oracle.float_to_pcm16(f)
+    with ThreadPoolExecutor(min(32, os.cpu_count() or 1)) as ex:
+        refs = dict(ex.map(ref, need))
+    worst = 0
+    for s in slots:
+        got = d_out[s * batch.stride:(s + 1) * batch.stride].cpu().numpy().reshape(-1, NCH)
+        d = int(np.abs(got.astype(np.int32) - refs[batch.order[s]].astype(np.int32)).max())
+        if d > 1:
+            raise AssertionError(f"bench verification: stream slot {s} differs from the oracle by {d} LSB")
+        worst = max(worst, d)
+    return len(slots), worst
+
+
+def pcie_ceiling(torch, dist, dev, world, gb: float = 2.0):
+    """What the box gives this rank for plain pinned-memory copies while every rank copies at once (cudaMemcpyAsync, GB/s)."""
+    n = int(gb * (1 << 30))
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    res = {}
+    for name, (dst, src) in {"d2h_gbs": (h, d), "h2d_gbs": (d, h)}.items():
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        if world > 1:
+            t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        res[name] = n / dt / 1e9
+    del h, d
+    return res
 
 
 def main():
@@ -252,9 +407,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (default = BASELINE configs[1])")
-    ap.add_argument("--e2e-streams", type=int, default=512)
+    ap.add_argument("--distinct", type=int, default=1024, help="distinct streams behind the batch")
+    ap.add_argument("--e2e-streams", type=int, default=2048, help="streams per GPU of the host-buffer (e2e) measurement")
+    ap.add_argument("--verify", type=int, default=64, help="decoded streams compared with the oracle after the timed loop (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--enc-streams", type=int, default=2048, help="streams per GPU of the secondary encode measurement (0 = skip)")
+    ap.add_argument("--enc-streams", type=int, default=4096, help="streams per GPU of the secondary encode measurement (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary objects (indexed / mixed decode, configs[3], configs[4])")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -262,8 +420,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = {"workload": "configs[1]: batched decode-only, 60 s stereo streams @128 kbps CBR, BlockSize 2048, PCM16 out",
            "streams_per_gpu": args.streams, "blocks_per_stream": BLOCKS_PER_STREAM, "rate_hz": RATE, "n_chan": NCH, "block_size": N,
-           "input": "reference-encoded (oracle/_ref scalar build) CBR-128 blocks of the synthetic music corpus; each stream = 1294 blocks "
-                    "drawn per stream from the 431-block golden pool tests/golden/music_cbr128_bs2048.npz; 256 distinct streams replicated",
+           "input": f"reference-encoded (oracle/_ref scalar build) CBR-128 blocks of the synthetic music corpus; each stream = 1294 blocks "
+                    f"drawn per stream from the 431-block golden pool tests/golden/music_cbr128_bs2048.npz; {min(args.distinct, args.streams)} "
+                    "distinct streams per GPU, replicated; raw .ulc payloads WITHOUT a block index (what the reference decoder reads), "
+                    "so every step includes the token-length walk that locates the blocks",
            "l2": "inputs+outputs per step (>40 GB) far exceed the 126 MB L2; no flush needed"}
     blocks = load_pool()
 
@@ -295,92 +455,88 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-
-    # ---- inputs (untimed): 256 distinct streams, replicated in a rank-dependent order ----
-    n_streams = args.streams
-    n_distinct = min(256, n_streams)
-    distinct = [build_stream(blocks, rank * 100003 + d) for d in range(n_distinct)]
-    order = [(s * 7 + s // n_distinct) % n_distinct for s in range(n_streams)]
-    lens = np.array([len(distinct[o]) for o in order], np.uint64)
-    offs = np.zeros(n_streams + 1, np.uint64)
-    offs[1:] = np.cumsum(lens)
-    total_in = int(offs[-1])
-    d_dist = [torch.from_numpy(d).to(dev) for d in distinct]
-    d_bytes = torch.empty(total_in + 64, dtype=torch.uint8, device=dev)
-    for s, o in enumerate(order):
-        d_bytes[int(offs[s]):int(offs[s + 1])] = d_dist[o]
-    d_bytes[total_in:] = 0
-    del d_dist
-    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
-    stride = BLOCKS_PER_STREAM * N * NCH
-    d_out = torch.empty(n_streams * stride, dtype=torch.int16, device=dev)
-    d_status = torch.zeros(n_streams, dtype=torch.int32, device=dev)
-
-    ctx = capi.Context(RATE, NCH, N, max_blocks=BLOCKS_PER_STREAM, device=local)
-    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
-
-    def step():
-        ctx.decode_streams_device(n_streams, d_bytes.data_ptr(), d_offs.data_ptr(), BLOCKS_PER_STREAM, d_out.data_ptr(), stride,
-                                  "pcm16", d_status=d_status.data_ptr())
-
-    torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        step()
-    ctx.sync()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    l0 = ctx.launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clk:
-        t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
-        t_all0.record(ext)
-        for a, b in evs:
-            a.record(ext); step(); b.record(ext)
-        t_all1.record(ext)
-        ctx.sync()
-        torch.cuda.synchronize()
-    launches = ctx.launches - l0
-    total_ms = t_all0.elapsed_time(t_all1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        dist.barrier()
-    assert int((d_status != -1).sum().item()) == 0, "decode reported corrupt streams"
-    ms_per_step = total_ms / args.steps
-    audio_per_step = world * n_streams * BLOCKS_PER_STREAM * N / RATE
-    value = audio_per_step / (ms_per_step / 1e3)
-
-    # ---- roofline of the dominant (only) kernel: algorithmic bytes / launch duration ----
-    algo_bytes = total_in + n_streams * stride * 2                 # bytes_in + PCM16 out  
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = algo_bytes / (kern_ms / 1e3) / 1e9
-    roof = {"bound": "hbm", "kernel": "ulcb_decode_ws_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)",
-            "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kern_ms,
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+    # ---- inputs (untimed) ----
+    n_streams = args.streams
+    distinct, index = make_streams(blocks, min(args.distinct, n_streams), rank * 100003)
+    batch = DecodeBatch(torch, dev, distinct, index, n_streams)
+    stride = batch.stride
+    d_out = torch.empty(n_streams * stride, dtype=torch.int16, device=dev)
+
+    ctx = capi.Context(RATE, NCH, N, max_blocks=BLOCKS_PER_STREAM, device=local)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+
+    def step(indexed=False, b=batch):
+        kw = dict(d_block_bytes=b.d_index.data_ptr(), block_bytes_stride=BLOCKS_PER_STREAM) if indexed else {}
+        ctx.decode_streams_device(b.n_streams, b.d_bytes.data_ptr(), b.d_offs.data_ptr(), BLOCKS_PER_STREAM, d_out.data_ptr(), stride,
+                                  "pcm16", d_status=b.d_status.data_ptr(), **kw)
+
+    # ---- headline: foreign streams, inputs resident ----
+    for _ in range(args.warmup):
+        step()
+    ctx.set_kernel_timing(True)
+    ctx.kernel_times(reset=True)
+    l0 = ctx.launches
+    ms_per_step, kern_ms, clocks = time_steps(torch, dist, ctx, ext, dev, world, step, args.steps, clock_gpu=local)
+    launches = ctx.launches - l0
+    ktimes = ctx.kernel_times(reset=True)
+    ctx.set_kernel_timing(False)
+    assert int((batch.d_status != -1).sum().item()) == 0, "decode reported corrupt streams"
+    audio_per_step = world * n_streams * BLOCKS_PER_STREAM * N / RATE
+    value = audio_per_step / (ms_per_step / 1e3)
+    verified = None
+    if args.verify > 0:
+        nv, worst = verify_decode(torch, batch, d_out, args.verify)
+        verified = {"streams": nv, "max_abs_diff_lsb": worst, "against": "oracle.Decoder (pinned to the reference's scalar build), whole 60 s streams, PCM16"}
+
+    # ---- roofline of the dominant kernel (the transform: ~3/4 of the step): algorithmic bytes / its time per step ----
+    algo_bytes = batch.total_in + n_streams * stride * 2            # bytes in + PCM16 out (8934 B per block)
+    per_kernel = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in ktimes.items() if v[1]}
+    tr_ms = per_kernel.get("bp_transform", {}).get("ms_per_step") or kern_ms
+    achieved = algo_bytes / (tr_ms / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": "bp_transform_kernel<true,false>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_source, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": tr_ms,
+            "launch_note": "one step = the pipeline walk -> (parse -> scan -> transform) per wave of streams; launch_ms is the transform "
+                           "kernel's summed time per step (CUDA events on the library's stream around every launch), algorithmic bytes are "
+                           "the whole step's (bytes in + PCM16 out)",
+            "kernels_ms_per_step": per_kernel,
+            "step": {"ms": kern_ms, "achieved": algo_bytes / (kern_ms / 1e3) / 1e9, "frac": algo_bytes / (kern_ms / 1e3) / 1e9 / peak},
             "traffic": measured_traffic("decode", n_streams, BLOCKS_PER_STREAM)}
+
+    extra = {}
+    if not args.no_extra:
+        # the same batch with the caller-supplied block-size index (this library's encoder and container.py emit one): no walk
+        for _ in range(2):
+            step(True)
+        ms_i, _, _ = time_steps(torch, dist, ctx, ext, dev, world, lambda: step(True), max(2, args.steps // 2))
+        extra["decode_indexed"] = {"value": audio_per_step / (ms_i / 1e3), "unit": "xrealtime", "ms_per_step": ms_i,
+                                   "roofline_step_frac": algo_bytes / (ms_i / 1e3) / 1e9 / peak,
+                                   "note": "ULCB_DecodeStreamsIndexedDevice: block sizes supplied, no token-length walk"}
+        assert int((batch.d_status != -1).sum().item()) == 0
 
     # ---- e2e: through the host-pointer C-ABI call, pinned host buffers, copies inside the timed region ----
     e2e = None
+    pcie = None
     if rank == 0 or world > 1:
+        pcie = pcie_ceiling(torch, dist, dev, world)
         ne = min(args.e2e_streams, n_streams)
-        h_streams = [distinct[o] for o in order[:ne]]
+        h_streams = [distinct[o] for o in batch.order[:ne]]
         h_data, h_offs = capi.pack_streams(h_streams)
         pin_in = torch.empty(len(h_data), dtype=torch.uint8).pin_memory()
         pin_in.numpy()[:] = h_data
         pin_out = torch.empty(ne * stride, dtype=torch.int16).pin_memory()
         h_status = np.zeros(ne, np.int32)
 
-        def e2e_step():
-            rc = ctx.L.ULCB_DecodeStreams(ctx.h, ne, pin_in.data_ptr(), h_offs.ctypes.data, None, BLOCKS_PER_STREAM,
-                                          pin_out.data_ptr(), stride, capi.FMT_PCM16, h_status.ctypes.data, None, 0)
+        def e2e_step(n=ne, out=pin_out):
+            rc = ctx.L.ULCB_DecodeStreams(ctx.h, n, pin_in.data_ptr(), h_offs.ctypes.data, None, BLOCKS_PER_STREAM,
+                                          out.data_ptr(), stride, capi.FMT_PCM16, h_status.ctypes.data, None, 0)
             assert rc == 0, rc
         e2e_step()
         if world > 1:
@@ -395,15 +551,50 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         assert (h_status == -1).all()
+        if args.verify > 0:                                            # the host buffer holds what the device path produced
+            s_chk = ne - 1
+            ref = d_out[s_chk * stride:(s_chk + 1) * stride].cpu().numpy()
+            assert np.array_equal(pin_out.numpy()[s_chk * stride:(s_chk + 1) * stride], ref), "e2e output differs from the device-resident run"
+        d2h = int(ne * stride * 2)
         e2e = {"value": world * ne * BLOCKS_PER_STREAM * N / RATE / dt, "unit": "xrealtime", "h2d_bytes_per_step": int(len(h_data)),
-               "d2h_bytes_per_step": int(ne * stride * 2), "streams_per_gpu": ne, "ms_per_step": dt * 1e3,
-               "api": "ULCB_DecodeStreams (host pointers, pinned; bytes in by H2D copy, PCM out stored by the kernel straight into the pinned buffer over PCIe), bounded to e2e_streams streams per GPU"}
+               "d2h_bytes_per_step": d2h, "streams_per_gpu": ne, "ms_per_step": dt * 1e3,
+               "pcie_gbs": (len(h_data) + d2h) / dt / 1e9, "pcie_ceiling": pcie,
+               "api": "ULCB_DecodeStreams (host pointers, pinned; bytes in by H2D copy, PCM out stored by the kernel straight into the pinned "
+                      "buffer over PCIe); e2e_streams streams per GPU = the pinned output that is reasonable to page-lock (stated in streams_per_gpu)"}
+        if not args.no_extra and rank == 0 and world == 1:
+            # pageable caller buffers: staged through device memory and one D2H copy
+            npg = min(256, ne)
+            pg_out = torch.empty(npg * stride, dtype=torch.int16)
+            e2e_step(npg, pg_out)
+            t0 = time.perf_counter()
+            e2e_step(npg, pg_out)
+            dtp = time.perf_counter() - t0
+            e2e["pageable"] = {"value": npg * BLOCKS_PER_STREAM * N / RATE / dtp, "unit": "xrealtime", "streams": npg, "ms_per_step": dtp * 1e3}
+            del pg_out
+        del pin_in, pin_out
+
+    if not args.no_extra:
+        # window-switched blocks priced in: the same launch shape on a pool that mixes the music stream with the transient-heavy ones
+        from tests import wavecheck
+        mixed_pool = wavecheck.block_pool()
+        nm = min(1024, n_streams)
+        md, mi = make_streams(mixed_pool, min(256, nm), 7000 + rank * 100003)
+        mb = DecodeBatch(torch, dev, md, mi, nm)
+        for _ in range(2):
+            step(False, mb)
+        ms_m, _, _ = time_steps(torch, dist, ctx, ext, dev, world, lambda: step(False, mb), max(2, args.steps // 2))
+        assert int((mb.d_status != -1).sum().item()) == 0
+        extra["decode_mixed"] = {"value": world * nm * BLOCKS_PER_STREAM * N / RATE / (ms_m / 1e3), "unit": "xrealtime", "ms_per_step": ms_m,
+                                 "streams_per_gpu": nm, "avg_bytes_per_block": mb.total_in / (nm * BLOCKS_PER_STREAM),
+                                 "note": "pool = music_cbr128 + transient_vbr50 + music_vbr75 goldens (about a third of the blocks window-switched "
+                                         "or transient-flagged), no block index"}
+        del mb
 
     # ---- secondary measurement: batched VBR encode (configs[2]); the headline stays the decode line above ----
     enc = None
+    del batch.d_bytes, d_out
+    torch.cuda.empty_cache()
     if args.enc_streams > 0:
-        del d_bytes, d_out
-        torch.cuda.empty_cache()
         enc = bench_encode(ctx, capi, torch, dist, dev, rank, world, args.enc_streams, max(1, args.steps // 2), 1, peaks,
                            with_cpu=(rank == 0 and world == 1 and not args.no_cpu))
 
@@ -417,8 +608,9 @@ def main():
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": METRIC, "value": value, "unit": "xrealtime", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": cfg, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "encode": enc}
+            "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "verified_streams": verified["streams"] if verified else 0, "verification": verified,
+            "roofline": roof, "cpu_baseline": cpu, "encode": enc, "build": build_id(), **extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

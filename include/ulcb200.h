@@ -246,6 +246,18 @@ void *ULCB_Stream(ULCB_Context *ctx);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t ULCB_LaunchCount(const ULCB_Context *ctx);
 
+/* Per-kernel device time of the block-parallel decode pipeline (measurement aid for bench.py's roofline object; the reference has
+ * no counterpart).  While enabled, CUDA events are recorded on the context's stream around every launch; ULCB_KernelTimes
+ * synchronises the stream and returns, per kernel kind, the accumulated milliseconds and launch counts since the last reset. */
+#define ULCB_KERNEL_BP_WALK       0   /* token-length walk of streams without a block-size index */
+#define ULCB_KERNEL_BP_INDEX      1   /* block offsets from a caller-supplied index */
+#define ULCB_KERNEL_BP_PARSE      2
+#define ULCB_KERNEL_BP_SCAN       3
+#define ULCB_KERNEL_BP_TRANSFORM  4
+#define ULCB_KERNEL_KINDS         5
+int ULCB_SetKernelTiming(ULCB_Context *ctx, int enable);
+int ULCB_KernelTimes(ULCB_Context *ctx, double *ms, uint64_t *count, int reset);
+
 /* Stage-level test hooks (host pointers; synchronous).  Used by tests/ only. */
 int ULCB_TestDCT4(ULCB_Context *ctx, float *data, int size, int count);
 /* parse + dequantise + noise-fill only: coefs[nBlocks][nChan*blockSize], blockBits[nBlocks] for ONE stream */

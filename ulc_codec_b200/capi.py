@@ -24,7 +24,7 @@ EXPORTS = (
     "ULCB_ContextCreate", "ULCB_ContextDestroy", "ULCB_LastCudaError", "ULCB_ErrorString",
     "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_DecodeStreamsIndexedDevice",
     "ULCB_DecodeStreamsIndexed", "ULCB_Sync", "ULCB_Stream",
-    "ULCB_LaunchCount", "ULCB_TestDCT4", "ULCB_TestParse",
+    "ULCB_LaunchCount", "ULCB_SetKernelTiming", "ULCB_KernelTimes", "ULCB_TestDCT4", "ULCB_TestParse",
     "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
     "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
     "ULCB_GenerateCorpusDevice", "ULCB_ConvertSamplesDevice", "ULCB_GetAvgComplexity",
@@ -90,6 +90,8 @@ def load():
     L.ULCB_Stream.restype = vp
     L.ULCB_LaunchCount.argtypes = [vp]
     L.ULCB_LaunchCount.restype = u64
+    L.ULCB_SetKernelTiming.argtypes = [vp, i32]
+    L.ULCB_KernelTimes.argtypes = [vp, vp, vp, i32]
     L.ULCB_TestDCT4.argtypes = [vp, vp, i32, i32]
     L.ULCB_TestParse.argtypes = [vp, vp, u64, u32, vp, vp]
     L.ULC_DecoderState_Init.argtypes = [C.POINTER(ULC_DecoderState_t)]
@@ -171,6 +173,18 @@ class Context:
 
     def sync(self):
         _check(self.L, self.h, self.L.ULCB_Sync(self.h), "ULCB_Sync")
+
+    KERNEL_KINDS = ("bp_walk", "bp_index", "bp_parse", "bp_scan", "bp_transform")
+
+    def set_kernel_timing(self, enable: bool = True):
+        _check(self.L, self.h, self.L.ULCB_SetKernelTiming(self.h, int(enable)), "ULCB_SetKernelTiming")
+
+    def kernel_times(self, reset: bool = True) -> dict:
+        """{kind: (milliseconds, launches)} accumulated since the last reset (ULCB_KernelTimes; synchronises the stream)."""
+        ms = np.zeros(len(self.KERNEL_KINDS), np.float64)
+        cnt = np.zeros(len(self.KERNEL_KINDS), np.uint64)
+        _check(self.L, self.h, self.L.ULCB_KernelTimes(self.h, ms.ctypes.data, cnt.ctypes.data, int(reset)), "ULCB_KernelTimes")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_KINDS)}
 
     # ---- host-pointer batched decode (ULCB_DecodeStreams) ----
     def decode_streams(self, streams, n_blocks, fmt: str = "pcm16", want_bits: bool = False, block_bytes=None):

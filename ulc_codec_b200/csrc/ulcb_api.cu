@@ -44,9 +44,22 @@ struct ULCB_Context {
     void *bpBad = nullptr;   size_t bpBadCap = 0;
     void *bpArena = nullptr; size_t bpArenaCap = 0;
     void *hPlan = nullptr;   size_t hPlanCap = 0;   // pinned: stream offsets / block counts read back to plan the waves
+    // per-kernel timing (ULCB_SetKernelTiming): event pairs recorded around the launches, resolved by ULCB_KernelTimes
+    bool timing = false;
+    struct TimedSpan { cudaEvent_t a, b; int kind; };
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> evPool;
+    double kernMs[ULCB_KERNEL_KINDS] = {}; uint64_t kernCount[ULCB_KERNEL_KINDS] = {};
 };
 
 namespace {
+
+cudaEvent_t timing_event(ULCB_Context *ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->evPool.empty()) { e = ctx->evPool.back(); ctx->evPool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
 
 #define CK(ctx, expr)                                                        \
     do {                                                                     \
@@ -376,6 +389,8 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->corpusLut) cudaFree(ctx->corpusLut);
     if (ctx->dAvgCx) cudaFree(ctx->dAvgCx);
     if (ctx->dCxScratch) cudaFree(ctx->dCxScratch);
+    for (auto &sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.kind == ULCB_KERNEL_BP_WALK || sp.kind == ULCB_KERNEL_BP_INDEX) cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -440,7 +455,10 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
         if ((rc0 = grow(ctx, &ctx->bpOff, &ctx->bpOffCap, sizeof(uint32_t) * (size_t)nStreams * (maxBlk + 1)))) return rc0;
         a.s0 = 0; a.nStreams = nStreams; a.base0 = hOffs[0]; a.blkOff = (uint32_t *)ctx->bpOff;
         int nl = 0;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->timing) { e0 = timing_event(ctx); e1 = timing_event(ctx); cudaEventRecord(e0, ctx->stream); }
         CK(ctx, ulcb_decode_bp_offsets(a, dBlockBytes != nullptr, ctx->smCount, ctx->stream, &nl));
+        if (ctx->timing) { cudaEventRecord(e1, ctx->stream); ctx->spans.push_back({e0, e1, dBlockBytes ? ULCB_KERNEL_BP_INDEX : ULCB_KERNEL_BP_WALK}); }
         ctx->launches += (uint64_t)nl;
     }
     for (int s0 = 0; s0 < nStreams;) {
@@ -453,7 +471,16 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
         a.s0 = s0; a.nStreams = n; a.base0 = hOffs[s0];
         a.blkOff = (uint32_t *)ctx->bpOff + (size_t)s0 * (maxBlk + 1); a.desc = (UlcbBpDesc *)ctx->bpDesc; a.firstBad = (int32_t *)ctx->bpBad; a.arena = (uint8_t *)ctx->bpArena;
         int nl = 0;
-        CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, ctx->stream, &nl));
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (ctx->timing) for (auto &e : ev) e = timing_event(ctx);
+        CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, ctx->stream, &nl, ctx->timing ? ev : nullptr));
+        if (ctx->timing) {
+            // an event can close one span and open the next only once: the pool gets it back from the span that opened with it
+            ctx->spans.push_back({ev[0], ev[1], ULCB_KERNEL_BP_PARSE});
+            ctx->spans.push_back({ev[1], ev[2], ULCB_KERNEL_BP_SCAN});
+            ctx->spans.push_back({ev[2], ev[3], ULCB_KERNEL_BP_TRANSFORM});
+            ctx->spans.push_back({ev[3], nullptr, -1});
+        }
         ctx->launches += (uint64_t)nl;
         s0 = s1;
     }
@@ -572,6 +599,35 @@ int ULCB_DecodeStreamsIndexed(ULCB_Context *ctx, int nStreams, const uint8_t *by
     if (!blockBytes) return ULCB_E_PARAM;
     return decode_host(ctx, nStreams, bytes, streamOffs, nBlocks, nBlocksAll, blockBytes, blockBytesStride, out, outStrideElems, format,
                        status, blockBits, bitsStride);
+}
+
+int ULCB_SetKernelTiming(ULCB_Context *ctx, int enable) {
+    if (!ctx) return ULCB_E_PARAM;
+    ctx->timing = enable != 0;
+    return ULCB_OK;
+}
+
+int ULCB_KernelTimes(ULCB_Context *ctx, double *ms, uint64_t *count, int reset) {
+    if (!ctx) return ULCB_E_PARAM;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &sp : ctx->spans) {
+        if (sp.kind >= 0 && sp.b) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { ctx->kernMs[sp.kind] += t; ctx->kernCount[sp.kind]++; }
+            else (void)cudaGetLastError();
+        }
+    }
+    // every event opens exactly one span entry (the last of a chain opens an entry without an end): back to the pool
+    for (auto &sp : ctx->spans) ctx->evPool.push_back(sp.a);
+    for (auto &sp : ctx->spans) if (sp.kind == ULCB_KERNEL_BP_WALK || sp.kind == ULCB_KERNEL_BP_INDEX) ctx->evPool.push_back(sp.b);
+    ctx->spans.clear();
+    for (int k = 0; k < ULCB_KERNEL_KINDS; k++) {
+        if (ms) ms[k] = ctx->kernMs[k];
+        if (count) count[k] = ctx->kernCount[k];
+        if (reset) { ctx->kernMs[k] = 0; ctx->kernCount[k] = 0; }
+    }
+    return ULCB_OK;
 }
 
 int ULCB_TestParse(ULCB_Context *ctx, const uint8_t *bytes, uint64_t nBytes, uint32_t nBlocks, float *coefs, uint32_t *blockBits) {

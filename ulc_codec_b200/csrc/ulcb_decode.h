@@ -73,4 +73,5 @@ struct UlcbBpArgs {
 bool        ulcb_decode_bp_supported(const UlcbTables &tb, int nChan);
 size_t      ulcb_decode_bp_arena_bytes(uint64_t payloadBytes, int nStreams, int maxBlk);
 cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &args, bool haveIndex, int smCount, cudaStream_t stream, int *launches);
-cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, cudaStream_t stream, int *launches);
+// ev (nullable): four events recorded before parse, after parse, after scan and after transform
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, cudaStream_t stream, int *launches, cudaEvent_t *ev = nullptr);

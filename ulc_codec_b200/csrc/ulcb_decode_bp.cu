@@ -1211,12 +1211,15 @@ cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &a, bool haveIndex, int smCo
 }
 
 // One wave: parse -> scan -> transform (a.blkOff points at the wave's first stream).
-cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, cudaStream_t stream, int *launches) {
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, cudaStream_t stream, int *launches, cudaEvent_t *ev) {
     if (a.nStreams <= 0 || a.maxBlk <= 0) return cudaSuccess;
     const int wpc = 4;                                            // warps per CTA of the per-stream kernels
     const long long nThr = (long long)a.nStreams * a.maxBlk;
+    if (ev) cudaEventRecord(ev[0], stream);
     bp_parse_kernel<<<(unsigned)((nThr + 127) / 128), 128, 0, stream>>>(a);
+    if (ev) cudaEventRecord(ev[1], stream);
     bp_scan_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
+    if (ev) cudaEventRecord(ev[2], stream);
     const int runsPerStream = (a.maxBlk + a.runLen - 1) / a.runLen;
     const long long grid = (long long)a.nStreams * runsPerStream;
     if (a.dbgCoefs) {
@@ -1226,6 +1229,7 @@ cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, cudaStream_t s
         if (pcm16) bp_transform_kernel<true, false><<<(unsigned)grid, 64, 0, stream>>>(a);
         else       bp_transform_kernel<false, false><<<(unsigned)grid, 64, 0, stream>>>(a);
     }
+    if (ev) cudaEventRecord(ev[3], stream);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }
