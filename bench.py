@@ -262,6 +262,135 @@ def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, war
     return r
 
 
+def _event_ms(torch, ctx, ext, fn):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    ctx.sync(); torch.cuda.synchronize()
+    e0.record(ext); fn(); e1.record(ext)
+    ctx.sync(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def _snr_db(torch, ref_i16, got_i16):
+    """Per-stream SNR (dB) of the decoded PCM16 against the original, on the device."""
+    r = ref_i16.to(torch.float32); e = got_i16.to(torch.float32) - r
+    return 10.0 * torch.log10((r * r).sum(dim=1) / (e * e).sum(dim=1).clamp_min(1e-9))
+
+
+def encode_decode_case(capi, torch, dev, rank, local, peak, *, block_size, n_streams, seconds, kind, mode, rate, first_id, verify=2, waves=1):
+    """Encode n_streams x seconds of the `kind` corpus and decode the result again, the bitstream never leaving the device
+    (the decoder is handed the encoder's block-size index); `waves` batches back to back reuse the same buffers.  Returns
+    encode / decode / round-trip throughput, roofline fractions against the algorithmic bytes, a reconstruction SNR and a parity
+    check of `verify` streams against the oracle (bytes identical, PCM16 within 1 LSB)."""
+    from oracle import oracle
+    from ulc_codec_b200 import corpus
+    bs = block_size
+    ns = seconds * RATE
+    with capi.Context(RATE, NCH, bs, max_blocks=(ns + bs - 1) // bs + 2, device=local) as ctx:
+        ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+        nb = ctx.blocks_for(ns)
+        istride = nb * bs * NCH
+        pcm = torch.zeros(n_streams * istride, dtype=torch.int16, device=dev)
+        ostride = (nb * (3 * int(rate * 1000 / 8 * bs / RATE) + 64) if mode != "vbr" else nb * bs) + 64
+        out = torch.zeros(n_streams * ostride + 64, dtype=torch.uint8, device=dev)
+        bb = torch.zeros(n_streams * nb, dtype=torch.int32, device=dev)
+        est = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+        offs = (torch.arange(n_streams + 1, dtype=torch.int64, device=dev) * ostride)
+        dec = torch.empty(n_streams * istride, dtype=torch.int16, device=dev)
+        dst = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+
+        def enc():
+            ctx.encode_streams_device(n_streams, pcm.data_ptr(), "pcm16", istride, nb, mode, rate, out.data_ptr(), ostride,
+                                      d_block_bytes=bb.data_ptr(), meta_stride=nb, d_status=est.data_ptr())
+
+        def dcd():
+            ctx.decode_streams_device(n_streams, out.data_ptr(), offs.data_ptr(), nb, dec.data_ptr(), istride, "pcm16",
+                                      d_status=dst.data_ptr(), d_block_bytes=bb.data_ptr(), block_bytes_stride=nb)
+        t_enc = t_dec = 0.0
+        out_bytes = 0
+        snr_min = float("inf")
+        for w in range(waves + 1):                                   # wave 0 is the warm-up
+            ctx.generate_corpus_device(kind, first_id + w * n_streams, n_streams, ns, pcm.data_ptr(), istride)
+            te = _event_ms(torch, ctx, ext, enc)
+            td = _event_ms(torch, ctx, ext, dcd)
+            assert int((est != 0).sum().item()) == 0, "encode arena overflow"
+            assert int((dst != -1).sum().item()) == 0, "decoder rejected an encoded stream"
+            if w:
+                t_enc += te; t_dec += td
+                out_bytes += int(bb.sum().item())
+                # the decoder's output lags the input by two blocks (encoder lap + decoder lap): compare the aligned parts
+                k = min(32, n_streams)                               # a sample of streams: the float copies are 4x the PCM16
+                a = pcm.view(n_streams, nb, bs * NCH)[:k, :-2].reshape(k, -1)
+                b = dec.view(n_streams, nb, bs * NCH)[:k, 2:].reshape(k, -1)
+                snr_min = min(snr_min, float(_snr_db(torch, a, b).min().item()))
+        blocks = waves * n_streams * nb
+        audio = waves * n_streams * nb * bs / RATE
+        in_bytes = blocks * bs * NCH * 2
+        ver = None
+        if verify:
+            bbh = bb.view(n_streams, nb)
+            ok = 0
+            for s in sorted({0, n_streams - 1, *np.linspace(0, n_streams - 1, verify).astype(int).tolist()}):
+                p = corpus.generate(first_id + waves * n_streams + s, ns, kind)
+                if mode == "abr2":
+                    avg = float(ctx.avg_complexity(n_streams)[s])
+                    ref = oracle.Encoder(RATE, NCH, bs).encode_stream(p, "abr", rate, avg)
+                else:
+                    ref = oracle.Encoder(RATE, NCH, bs).encode_stream(p, mode, rate, 0.0)
+                sizes = bbh[s].cpu().numpy().astype(np.int64)
+                got = out[s * ostride:s * ostride + int(sizes.sum())].cpu().numpy()
+                nd = int((sizes != ref["block_bytes"].astype(np.int64)).sum())
+                same = nd == 0 and np.array_equal(got, ref["data"])
+                f, bits = oracle.Decoder(NCH, bs).decode_stream(got, nb)
+                d = int(np.abs(dec[s * istride:(s + 1) * istride].cpu().numpy().reshape(-1, NCH).astype(np.int32) - oracle.float_to_pcm16(f).astype(np.int32)).max())
+                if d > 1 or nd > max(1, nb // 500):
+                    raise AssertionError(f"bench verification (bs {bs} {mode}): stream {s}: {nd} block sizes differ from the oracle, decode differs by {d} LSB")
+                ok += 1 if same else 0
+            ver = {"streams": verify, "byte_identical_to_oracle": ok, "decode_max_abs_diff_lsb": "<=1"}
+        del pcm, out, dec
+        torch.cuda.empty_cache()
+    r = {"streams_per_gpu": n_streams, "waves": waves, "seconds_per_stream": seconds, "block_size": bs, "blocks_per_stream": nb,
+         "avg_bytes_per_block": out_bytes / blocks,
+         "encode": {"value": audio / (t_enc / 1e3), "unit": "xrealtime", "ms": t_enc,
+                    "roofline_frac": (in_bytes + out_bytes) / (t_enc / 1e3) / 1e9 / peak},
+         "decode": {"value": audio / (t_dec / 1e3), "unit": "xrealtime", "ms": t_dec,
+                    "roofline_frac": (in_bytes + out_bytes) / (t_dec / 1e3) / 1e9 / peak},
+         "round_trip": {"value": audio / ((t_enc + t_dec) / 1e3), "unit": "xrealtime"},
+         "min_snr_db": snr_min, "verification": ver}
+    return r
+
+
+def cpu_reference_tool(kind, args, seconds=20.0, decode=False):
+    """The reference tool (AVX build) on all host cores, one process per core, for an arbitrary tool command line."""
+    from ulc_codec_b200 import corpus
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    enc_tool = os.path.join(ROOT, "oracle", "_ref", "ulcencodetool_avx")
+    dec_tool = os.path.join(ROOT, "oracle", "_ref", "ulcdecodetool_avx")
+    if not (os.access(enc_tool, os.X_OK) and os.access(dec_tool, os.X_OK)):
+        return None
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    ns = int(seconds * RATE)
+    with tempfile.TemporaryDirectory(dir=shm) as td:
+        base = [corpus.generate(300000 + i, ns, kind) for i in range(min(cores, 4))]
+        files = []
+        for c in range(cores):
+            path = os.path.join(td, f"s{c}.wav")
+            with open(path, "wb") as f:
+                f.write(wav_bytes(base[c % len(base)]))
+            files.append(path)
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([enc_tool, p, p + ".ulc", *args], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for p in files]
+        rcs = [p.wait() for p in procs]
+        t_enc = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([dec_tool, p + ".ulc", "/dev/null"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for p in files]
+        rcs += [p.wait() for p in procs]
+        t_dec = time.perf_counter() - t0
+    if any(rcs):
+        return None
+    return {"encode": cores * seconds / t_enc, "decode": cores * seconds / t_dec, "unit": "xrealtime", "cores": cores, "kind": "reference",
+            "sample": f"{cores} procs x one {seconds:g} s {kind} stream, oracle/_ref/ulc{{en,de}}codetool_avx {' '.join(args)}"}
+
+
 # ------------------------------------------------------------------------------------------------
 
 def build_id() -> str:
@@ -597,6 +726,31 @@ def main():
     if args.enc_streams > 0:
         enc = bench_encode(ctx, capi, torch, dist, dev, rank, world, args.enc_streams, max(1, args.steps // 2), 1, peaks,
                            with_cpu=(rank == 0 and world == 1 and not args.no_cpu))
+
+    # ---- configs[3] (transient-heavy, BlockSize 256 / 8192, ABR-64 with the quality search on the device) and a bounded sample of
+    #      configs[4] (VBR Q75 encode -> decode round trip, bitstream resident, in waves) ----
+    if not args.no_extra:
+        torch.cuda.empty_cache()
+        c3 = {}
+        for bs, nst in ((256, 1024), (8192, 512)):
+            c3[f"bs{bs}"] = encode_decode_case(capi, torch, dev, rank, local, peak, block_size=bs, n_streams=nst, seconds=60, kind="transient",
+                                               mode="abr2", rate=64.0, first_id=500000 + rank * 10000)
+            if rank == 0 and world == 1 and not args.no_cpu:
+                c3[f"bs{bs}"]["cpu_baseline"] = cpu_reference_tool("transient", ["64,0.5", f"-blocksize:{bs}"])
+        extra["configs3_transient_abr64"] = {"workload": "configs[3]: transient-heavy corpus (impulse trains + noise bursts), ABR 64 kbps, two passes on the "
+                                                         "device (analysis pass for AvgComplexity, then the size search per block), then decode of the result",
+                                             **c3}
+        rt = encode_decode_case(capi, torch, dev, rank, local, peak, block_size=N, n_streams=1024, seconds=180, kind="music", mode="vbr", rate=75.0,
+                                first_id=700000 + rank * 100000, waves=2, verify=2)
+        if world > 1:
+            t = torch.tensor([rt["encode"]["ms"] + rt["decode"]["ms"]], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rt["round_trip"]["value"] = world * 2 * 1024 * rt["blocks_per_stream"] * N / RATE / (float(t.item()) / 1e3)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            rt["cpu_baseline"] = cpu_reference_tool("music", ["-75"])
+        extra["configs4_roundtrip_q75"] = {"workload": "configs[4]: VBR Quality=75 encode + decode round trip of 180 s stereo streams, stream-sharded; the full "
+                                                       "corpus is 65536 streams = 8192 per GPU at 8 GPUs, processed in resident waves; this is a bounded sample "
+                                                       "of 2 waves x 1024 streams per GPU (a wave of 2048 streams is 65 GB of PCM16 and fits as well)", **rt}
 
     if rank != 0:
         if world > 1:

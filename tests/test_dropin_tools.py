@@ -34,7 +34,23 @@ def test_reference_tools_on_the_gpu_library(tmp_path, kind, args, seconds):
     t_ref, _ = _run("ulcencodetool_scalar", src, ulc_ref, *args)
     t_gpu, out = _run("ulcencodetool_b200", src, ulc_gpu, *args)
     a, b = open(ulc_ref, "rb").read(), open(ulc_gpu, "rb").read()
-    assert a == b, f"encoded files differ ({len(a)} vs {len(b)} bytes)\n{out}"
+    if seconds <= 30:
+        assert a == b, f"encoded files differ ({len(a)} vs {len(b)} bytes)\n{out}"
+    else:
+        # long streams: BASELINE.json allows a quantisation-boundary flip in at most 0.1 % of blocks (device log vs glibc logf
+        # in the last ulp; the reference's own two builds differ in 0.4-1 %)
+        from oracle import oracle
+        from ulc_codec_b200 import container
+        fa, fb = container.parse(a), container.parse(b)
+        assert fa.header.n_blocks == fb.header.n_blocks and fa.header.block_size == fb.header.block_size
+        nb, bsz = fa.header.n_blocks, fa.header.block_size
+        pa, pb = fa.payload, fb.payload
+        _, bits_a = oracle.Decoder(2, bsz).decode_stream(pa, nb)
+        _, bits_b = oracle.Decoder(2, bsz).decode_stream(pb, nb)
+        assert (bits_a != 0).all() and (bits_b != 0).all()
+        oa = np.concatenate([[0], np.cumsum((bits_a.astype(np.int64) + 7) // 8)]); ob = np.concatenate([[0], np.cumsum((bits_b.astype(np.int64) + 7) // 8)])
+        differing = sum(1 for k in range(nb) if not np.array_equal(pa[oa[k]:oa[k + 1]], pb[ob[k]:ob[k + 1]]))
+        assert differing <= max(1, nb // 1000), f"{differing} of {nb} blocks differ"
     wav_ref, wav_gpu = str(tmp_path / "ref.wav"), str(tmp_path / "gpu.wav")
     d_ref, _ = _run("ulcdecodetool_scalar", ulc_ref, wav_ref)
     d_gpu, _ = _run("ulcdecodetool_b200", ulc_ref, wav_gpu)
