@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from ulc_codec_b200 import capi
+if os.environ.get("ULCB_LIB"): capi.LIB_PATH = os.path.abspath(os.environ["ULCB_LIB"])      # experiment builds (scripts/build_variant.sh)
 ap = argparse.ArgumentParser(); ap.add_argument("--streams", type=int, default=1024); ap.add_argument("--blocks", type=int, default=1294)
 ap.add_argument("--reps", type=int, default=3); ap.add_argument("--mode", default="index"); ap.add_argument("--distinct", type=int, default=64)
 a = ap.parse_args()

@@ -198,3 +198,26 @@ def test_shard_of_a_batch_equals_the_batch(capi):
                     assert np.array_equal(part["streams"][i - a], full["streams"][i])
                 dpart, spart, _ = ctx.decode_streams(full["streams"][a:b], nb, fmt="pcm16")
                 assert np.array_equal(dpart, dfull[a:b]) and np.array_equal(spart, sfull[a:b])
+
+
+@pytest.mark.parametrize("rate_hz,block_size,mode,param", [(32000, 1024, "vbr", 60.0), (48000, 2048, "cbr", 112.0), (22050, 512, "vbr", 45.0),
+                                                           (96000, 4096, "vbr", 70.0)])
+def test_other_sample_rates(capi, rate_hz, block_size, mode, param):
+    """RateHz only enters through host-built tables - the Bark band edges (ulcEncoder_Psyopt.c:83-92), the detector's
+    filter coefficients (ulcEncoder_WindowControl.c:73-88) and the kbps -> bits conversion (ulcEncoder.c:93-116).  Bytes, block sizes
+    and window decisions must equal the oracle's at any rate; the decoder does not depend on the rate at all."""
+    from ulc_codec_b200 import corpus
+    pcms = [corpus.generate(900 + i, 7 * block_size + 123 * i, "transient" if i & 1 else "music") for i in range(4)]
+    refs = [oracle.Encoder(rate_hz, 2, block_size).encode_stream(p, mode, param, 0.0) for p in pcms]
+    with capi.Context(rate_hz, 2, block_size) as ctx:
+        r = ctx.encode_streams(pcms, mode, param)
+        nbs = [len(x["block_bytes"]) for x in refs]
+        pcm_out, status, _ = ctx.decode_streams([x["data"] for x in refs], nbs, fmt="pcm16")
+    for i, ref in enumerate(refs):
+        nb = nbs[i]
+        assert np.array_equal(r["block_bytes"][i][:nb], ref["block_bytes"]), i
+        assert np.array_equal(r["window_ctrl"][i][:nb], ref["window_ctrl"]), i
+        assert np.array_equal(r["streams"][i][:len(ref["data"])], ref["data"]), i
+        f, bits = oracle.Decoder(2, block_size).decode_stream(ref["data"], nb)
+        assert status[i] == -1
+        assert np.abs(pcm_out[i, :nb * block_size].astype(np.int32) - oracle.float_to_pcm16(f).astype(np.int32)).max() <= 1
