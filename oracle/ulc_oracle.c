@@ -227,7 +227,8 @@ ORACLE_API void ulco_mdct_mdst(float *mdct, float *mdst, const float *fresh, flo
 /* ------------------------------------------------------------------------------------------ */
 /* Sub-block layout of a window-control code (ulcHelper.h:24-46, FormatSpecs.md:35-51):
  * fills shift[] (size = N >> shift) and returns the count; *transient = index of the
- * sub-block that carries the overlap scaling.                                             */
+ * sub-block that carries the overlap scaling, -1 when none does (layout 0: "unused",
+ * ulcHelper.h:29, but the decoder takes it - found by tests/grammar.py, not by any golden). */
 ORACLE_API int ulco_subblocks(int window_ctrl, int shift[4], int *transient) {
 	static const uint16_t layout[16] = {
 		0x0000, 0x0008, 0x0019, 0x0091, 0x012A, 0x01A2, 0x02A1, 0x0A21,
@@ -235,7 +236,7 @@ ORACLE_API int ulco_subblocks(int window_ctrl, int shift[4], int *transient) {
 	};
 	unsigned pat = layout[(window_ctrl >> 4) & 15];
 	int n = 0;
-	*transient = 0;
+	*transient = -1;
 	do {
 		shift[n] = pat & 7;
 		if(pat & 8) *transient = n;

@@ -51,5 +51,26 @@ for i, (ref, rbits) in enumerate(refs):
             fb = int(np.flatnonzero(per > 1e-4 * max(1e-9, np.abs(ref).max()))[0]) if (per > 1e-4 * max(1e-9, np.abs(ref).max())).any() else -1
             print("stream", i, "kind", i % 4, "mismatch before the bad block", e, "first differing block", fb, "of", ok_upto, "dead", dead, "oracle bad", first_bad,
                   "bits equal", np.array_equal(bits[i, :ok_upto], rbits[:ok_upto]), "peak", float(np.abs(ref).max()), "gpu peak", float(np.abs(pcm[i, :ok_upto*2048]).max()))
-print("fuzz done:", len(streams), "streams,", bad, "disagreements;", int((status >= 0).sum()), "flagged")
+# Beyond the contract's letter: a damaged block that still parses is decoded by the reference too, and a decoder is a pure function
+# of the bytes - so every block both sides accept is compared as well (output block k mixes blocks k-1 and k; the reference's
+# RNG position after a damaged block is part of that function).  Mismatching streams are dumped for minimisation.
+garbage = 0
+for i, (ref, rbits) in enumerate(refs):
+    dead = int(status[i]); good = dead if dead >= 0 else nb
+    first_bad = int(np.flatnonzero(rbits == 0)[0]) if (rbits == 0).any() else nb
+    upto = min(good, first_bad)
+    ends = np.cumsum((rbits[:upto].astype(np.int64) + 7) // 8)
+    upto = int((ends <= len(streams[i])).sum())
+    if upto <= 0: continue
+    peak = max(1e-9, float(np.abs(ref[:upto * 2048]).max()))
+    per = np.abs(pcm[i, :upto * 2048] - ref[:upto * 2048]).reshape(upto, -1).max(axis=1) / peak
+    if not np.array_equal(bits[i, :upto], rbits[:upto]) or (per > 2e-5).any():
+        garbage += 1
+        fb = int(np.flatnonzero(per > 2e-5)[0]) if (per > 2e-5).any() else -1
+        print("stream", i, "kind", i % 4, "parseable-but-damaged block differs: first differing block", fb, "of", upto, "first hit block", first_hit[i],
+              "err", float(per.max()), "peak", peak)
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez(f"gpurun_out/fuzz_case_{sys.argv[1] if len(sys.argv) > 1 else 7}_{i}.npz", data=streams[i], nb=nb, first=fb)
+print("fuzz done:", len(streams), "streams,", bad, "disagreements;", garbage, "streams with a differing damaged-but-parseable block;", int((status >= 0).sum()), "flagged")
+bad += garbage
 sys.exit(1 if bad else 0)

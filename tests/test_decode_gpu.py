@@ -185,3 +185,46 @@ def test_fast_and_generic_kernels_agree(tmp_path):
             assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= 1, k
         else:
             assert peak_rel_err(a, b) < 2e-6, (k, peak_rel_err(a, b))
+
+
+@pytest.mark.parametrize("block_size,n_chan,seed", [(2048, 2, 3), (256, 1, 4), (1024, 2, 5), (8192, 2, 6), (512, 1, 7), (4096, 1, 8)])
+@pytest.mark.parametrize("with_index", [False, True])
+def test_grammar_vectors(capi, block_size, n_chan, seed, with_index):
+    """Every token of the grammar, every decimation layout including the "unused" layout 0 (tests/grammar.py), through the batched
+    decoder: bit counts exact, float PCM within 1e-5 of the stream peak.  At BlockSize 2048 stereo this is the block-parallel
+    pipeline (token automaton of the walk when no index is given); the other shapes run the generic kernel.
+    These spectra are dense and white (random nybbles in every line), the worst case for the reference's own f32 twiddle recurrences:
+    at N = 8192 its DCT-IV is 4.6e-5 of the peak away from the closed form on white input (tests/test_oracle_vs_ref.py::
+    test_dct_bit_identical), so there the bound is the reference's self-noise, 6e-5; the encoder-made goldens hold 1e-5 at every size."""
+    from tests import grammar
+    nb = 24
+    st, sz = grammar.streams(40, nb, block_size, n_chan, seed=seed)
+    refs = [oracle.Decoder(n_chan, block_size).decode_stream(np.concatenate([s, np.zeros(64, np.uint8)]), nb) for s in st]
+    with capi.Context(44100, n_chan, block_size, max_blocks=nb) as ctx:
+        pcm, status, bits = ctx.decode_streams(st, nb, fmt="f32", want_bits=True, block_bytes=sz if with_index else None)
+    assert (status == -1).all(), status
+    for i, (ref, rbits) in enumerate(refs):
+        assert np.array_equal(bits[i].astype(np.int64), rbits.astype(np.int64)), i
+        per = np.abs(pcm[i].reshape(nb, -1) - ref.reshape(nb, -1)).max(axis=1) / max(1e-30, float(np.abs(ref).max()))
+        assert per.max() < (6e-5 if block_size == 8192 else 1e-5), (i, int(per.argmax()), float(per.max()))
+
+
+@pytest.mark.parametrize("env", [{"ULCB_DECODE_GENERIC": "1"}, {"ULCB_DECODE_WS": "1"}])
+def test_grammar_vectors_other_kernels(env):
+    """The same vectors through the kernels the launcher does not pick by default at BlockSize 2048 stereo."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import numpy as np\nfrom oracle import oracle\nfrom tests import grammar\nfrom ulc_codec_b200 import capi\n"
+            "st, sz = grammar.streams(40, 24, 2048, 2, seed=3)\n"
+            "with capi.Context(44100, 2, 2048, max_blocks=24) as ctx:\n"
+            "    pcm, status, bits = ctx.decode_streams(st, 24, fmt='f32', want_bits=True)\n"
+            "assert (status == -1).all()\n"
+            "for i, s in enumerate(st):\n"
+            "    ref, rbits = oracle.Decoder(2, 2048).decode_stream(np.concatenate([s, np.zeros(64, np.uint8)]), 24)\n"
+            "    assert np.array_equal(bits[i].astype(np.int64), rbits.astype(np.int64)), i\n"
+            "    assert np.abs(pcm[i] - ref).max() < 1e-5 * np.abs(ref).max(), i\n"
+            "print('grammar ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True, text=True)
+    assert r.returncode == 0 and "grammar ok" in r.stdout, r.stdout + r.stderr

@@ -49,3 +49,23 @@ def test_oracle_encoder_matches_reference_golden(name):
     assert np.array_equal(enc["coefs"][:6], g["coefs_head"])
     assert sha(enc["coefs"]) == g["coefs_sha256"]
     assert sha(enc["ranks"]) == g["ranks_sha256"]
+
+
+def test_oracle_on_grammar_vectors():
+    """Hand-built streams with every token of the grammar (tests/grammar.py): the oracle's output must hash to what the compiled
+    reference produced (tests/golden/grammar_vectors.json, written by tests/golden/make_grammar_golden.py).  This is what caught the
+    oracle applying overlap scaling to decimation layout 0, which no encoder-made golden contains."""
+    import hashlib
+    import json
+    import os
+    from tests import grammar
+    from tests.fixtures import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "grammar_vectors.json")))
+    for case in g["cases"]:
+        N, C = case["block_size"], case["n_chan"]
+        st, sz = grammar.streams(g["n_streams"], g["n_blocks"], N, C, seed=case["seed"])
+        for i, s in enumerate(st):
+            pcm, bits = oracle.Decoder(C, N).decode_stream(np.concatenate([s, np.zeros(64, np.uint8)]), g["n_blocks"])
+            assert bits.astype(int).tolist() == case["bits"][i], (N, C, i)
+            assert np.array_equal((bits.astype(np.int64) + 7) // 8, sz[i].astype(np.int64))
+            assert hashlib.sha256(np.ascontiguousarray(pcm, np.float32).tobytes()).hexdigest() == case["pcm_sha256"][i], (N, C, i)

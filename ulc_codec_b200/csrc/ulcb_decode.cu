@@ -503,13 +503,21 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                     int start = nr.start_n & 0xffff, n = nr.start_n >> 16;
                     uint32_t g = nr.draw;
                     uint32_t p0 = (__ldg(&par[g >> 5]) >> (g & 31)) & 1u;
-                    float l2 = (nr.decay != 1.0f) ? log2f(nr.decay) : 0.0f;
+                    // A decaying tail's level is the reference's own running product p *= r in f32 (ulcDecoder.c:178-184), not
+                    // amp * r^i: with r = 1 - n^2 2^-19 close to 1 the rounding of p * r has the same sign for thousands of steps
+                    // and the sequence drifts 1e-4 away from the closed form.  Every lane runs the chain (lockstep: the cost
+                    // of one chain), 32 steps between its samples.
+                    const bool decays = nr.decay != 1.0f;
+                    float a = nr.amp;
+                    if (decays) for (int k = 0; k < lane; k++) a = __fmul_rn(a, nr.decay);
                     for (int i = lane; i < n; i += 32) {
                         uint32_t m = g + (uint32_t)i + 1u;
                         uint32_t sgn = ((__ldg(&par[m >> 5]) >> (m & 31)) & 1u) ^ p0;
-                        float a = nr.amp;
-                        if (nr.decay != 1.0f) a *= exp2f((float)i * l2);
                         sm.buf[start + i] = sgn ? -a : a;
+                        if (decays) {
+#pragma unroll 8
+                            for (int k = 0; k < 32; k++) a = __fmul_rn(a, nr.decay);
+                        }
                     }
                 }
             }

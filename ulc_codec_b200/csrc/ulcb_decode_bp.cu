@@ -642,7 +642,7 @@ __device__ __forceinline__ void store_pairs<true>(void *outBlk, int slotIdx, flo
     __stcs(reinterpret_cast<uint2 *>(outBlk) + slotIdx, make_uint2(pcm16_pair(l0, r0), pcm16_pair(l1, r1)));
 }
 
-struct Tail { int start, end; float amp, l2; };     // decaying noise to the end of a sub-block (ulcDecoder.c:172-186)
+struct Tail { int start, end; float amp, r; };      // decaying noise to the end of a sub-block (ulcDecoder.c:172-186): level amp, decay factor r
 
 struct WarpSm {
     float2   zb[32 * ZROW];       // FFT tile / coefficient words / short-block scratch / output swap
@@ -728,8 +728,7 @@ __device__ __noinline__ void noise_fill(WarpSm &w, const BlkInfo &bi, const uint
                 const int q = (int)((rr.w >> 12) & 31u);
                 Tail t; t.start = s; t.end = e;
                 t.amp = (float)(lv * lv) * quant_scale(q) * (1.0f / 16);
-                const float decay = 1.0f + (float)(nn * nn) * -0x1.0p-19f;
-                t.l2 = decay != 1.0f ? log2f(decay) : 0.0f;
+                t.r = 1.0f + (float)(nn * nn) * -0x1.0p-19f;
                 const int slot = atomicAdd(&w.nTails, 1);
                 if (slot < 8) w.tail[slot] = t;
             }
@@ -782,13 +781,54 @@ __device__ __noinline__ void noise_fill(WarpSm &w, const BlkInfo &bi, const uint
     __syncwarp();
 }
 
-__device__ __forceinline__ float tail_gain(const WarpSm &w, int nT, int idx) {
-    float g = 1.0f;
-    for (int t = 0; t < nT; t++) {
-        const Tail &tl = w.tail[t];
-        if (idx >= tl.start && idx < tl.end) g = tl.amp * exp2f((float)(idx - tl.start) * tl.l2);
+// A decaying tail's level at offset k is the reference's own running product p *= r in f32 (ulcDecoder.c:178-184), not amp * r^k:
+// with r = 1 - n^2 2^-19 close to 1 the rounding of p * r keeps its sign for thousands of steps and the sequence drifts up to 1e-4
+// away from the closed form.  A lane walks its coefficients in ascending order and advances the chain between them (all lanes in
+// lockstep: the cost of one chain per tail, and tails are rare).
+struct TailChain {
+    int start, end, k;
+    float p, r;
+    __device__ __forceinline__ void open(const Tail &t) { start = t.start; end = t.end; k = t.start; p = t.amp; r = t.r; }
+    __device__ __forceinline__ void none() { start = end = k = 0; p = 1.0f; r = 1.0f; }
+    __device__ __forceinline__ float gain(int idx) {         // idx ascending from call to call
+        if (idx < start || idx >= end) return 1.0f;
+        for (; k < idx; k++) p = __fmul_rn(p, r);
+        return p;
     }
-    return g;
+};
+
+// The rare way into a long block's first FFT pass: a decaying noise tail (one per channel in a long block; its gains applied here) or
+// the coefficient tap.  The words are expanded to float pairs in the tile in ascending order (the tail's running product), then
+// pre-twiddled through the tile.  Out of line: it must not cost the common path registers or instruction-cache footprint.
+template <bool DBG>
+__device__ __noinline__ void expand_rare(WarpSm &w, int nT, float *dbg, int lane) {
+    float2 *zb = w.zb;
+    {
+        TailChain tc;
+        if (nT) tc.open(w.tail[0]); else tc.none();
+#pragma unroll 1
+        for (int j = 0; j < 32; j++) {
+            const int n = lane + 32 * j;
+            const uint32_t wa = __float_as_uint(zb[j * ZROW + lane].x);
+            float ev = __uint_as_float(wa << 16), od = __uint_as_float(wa & 0xffff0000u);
+            if (nT) { ev *= tc.gain(2 * n); od *= tc.gain(2 * n + 1); }
+            if (DBG) reinterpret_cast<float2 *>(dbg)[n] = make_float2(ev, od);
+            zb[j * ZROW + lane] = make_float2(ev, od);
+        }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int j = 0; j < 16; j++) {
+        const int ja = j, jb = 31 - j;
+        const float2 va = zb[ja * ZROW + lane], vb = zb[jb * ZROW + lane];
+        const float ea = va.x, oa = va.y, eb = vb.x, ob = vb.y;
+        const float ia = __shfl_xor_sync(FULLM, ob, 31);      // v[N-1-2na]
+        const float ib = __shfl_xor_sync(FULLM, oa, 31);      // v[N-1-2nb]
+        const float ca = cosf(0.049087385212340517f * (float)ja), sa = sinf(0.049087385212340517f * (float)ja);   // pi / 64
+        const float cb = cosf(0.049087385212340517f * (float)jb), sb = sinf(0.049087385212340517f * (float)jb);
+        zb[ja * ZROW + lane] = make_float2(ea * ca + ia * sa, ia * ca - ea * sa);
+        zb[jb * ZROW + lane] = make_float2(eb * cb + ib * sb, ib * cb - eb * sb);
+    }
 }
 
 // ---- the pending tail lives in Tensor Memory ----
@@ -902,7 +942,9 @@ bp_transform_kernel(UlcbBpArgs a) {
             continue;
         }
         const int wc = (int)cur.wc;
-        const bool longBlk = (wc >> 4) == 1;
+        // one sub-block of the whole block size: layout 1 (N/1*, what encoders write) and layout 0 (N/1 without the transient flag:
+        // "unused", ulcHelper.h:29, but a decoder must take what parses)
+        const bool longBlk = (wc >> 4) <= 1;
         float *dbg = DBG ? a.dbgCoefs + (((size_t)gs * a.nBlocksAll + blk) * 2 + c) * N : nullptr;
 
         // ---- clear the coefficient words, then scatter this channel's words into them ----
@@ -956,29 +998,7 @@ bp_transform_kernel(UlcbBpArgs a) {
                 }
                 __syncwarp();
             } else {
-                // rare: decaying noise tails (gain applied here) / coefficient tap.  Rolled: z goes through the tile.
-#pragma unroll 1
-                for (int j = 0; j < 16; j++) {
-                    const int ja = j, jb = 31 - j;
-                    const int na = lane + 32 * ja, nb2 = lane + 32 * jb;
-                    const uint32_t wa = __float_as_uint(zb[ja * ZROW + lane].x), wb = __float_as_uint(zb[jb * ZROW + lane].x);
-                    float ea = __uint_as_float(wa << 16), oa = __uint_as_float(wa & 0xffff0000u);
-                    float eb = __uint_as_float(wb << 16), ob = __uint_as_float(wb & 0xffff0000u);
-                    if (nT) {
-                        ea *= tail_gain(w, nT, 2 * na); oa *= tail_gain(w, nT, 2 * na + 1);
-                        eb *= tail_gain(w, nT, 2 * nb2); ob *= tail_gain(w, nT, 2 * nb2 + 1);
-                    }
-                    if (DBG) {
-                        reinterpret_cast<float2 *>(dbg)[na] = make_float2(ea, oa);
-                        reinterpret_cast<float2 *>(dbg)[nb2] = make_float2(eb, ob);
-                    }
-                    const float ia = __shfl_xor_sync(FULLM, ob, 31);      // v[N-1-2na]
-                    const float ib = __shfl_xor_sync(FULLM, oa, 31);      // v[N-1-2nb]
-                    const float ca = cosf(0.049087385212340517f * (float)ja), sa = sinf(0.049087385212340517f * (float)ja);   // pi / 64
-                    const float cb = cosf(0.049087385212340517f * (float)jb), sb = sinf(0.049087385212340517f * (float)jb);
-                    zb[ja * ZROW + lane] = make_float2(ea * ca + ia * sa, ia * ca - ea * sa);
-                    zb[jb * ZROW + lane] = make_float2(eb * cb + ib * sb, ib * cb - eb * sb);
-                }
+                expand_rare<DBG>(w, nT, dbg, lane);
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 32; j++) { const float2 v = zb[j * ZROW + lane]; xr[j] = v.x; xi[j] = v.y; }
@@ -1036,7 +1056,7 @@ bp_transform_kernel(UlcbBpArgs a) {
             }
             // un-fold (Fourier_IMDCT_Template.h:66-93) against the pending tail, all at the same k = lane + 32 k2; the tail comes
             // from / goes back to TMEM eight columns at a time
-            int ov = N >> (wc & 7);                       // the long block is its own transient sub-block (layout 0x8)
+            int ov = (wc >> 4) ? N >> (wc & 7) : N;       // layout 1: the long block is its own transient sub-block; layout 0: no overlap scaling
             if (ov > lastSub) ov = lastSub;
             lastSub = N;
             if (ov == N) {
@@ -1106,9 +1126,12 @@ bp_transform_kernel(UlcbBpArgs a) {
             int offc = 0;
             for (unsigned pat = kLayoutBp[wc >> 4];;) {
                 const int sh = pat & 7, S = N >> sh, hS = S >> 1;
+                TailChain tc;
+                tc.none();
+                for (int t = 0; t < nT; t++) if (w.tail[t].start >= offc && w.tail[t].start < offc + S) tc.open(w.tail[t]);   // at most one per sub-block
                 for (int i = lane; i < S; i += 32) {
                     float x = __uint_as_float((uint32_t)coef16[offc + i] << 16);
-                    if (nT) x *= tail_gain(w, nT, offc + i);
+                    if (nT) x *= tc.gain(offc + i);
                     if (DBG) dbg[offc + i] = x;
                     scr[i] = x;
                 }

@@ -66,7 +66,7 @@ __constant__ uint16_t kLayoutWs[16] = {
 };
 
 struct Run  { uint32_t a, b; };                     // a: start | n << 12; b: draw offset in block | bf16 amplitude << 16
-struct Tail { int start, end; float amp, l2; };     // decaying noise to the end of a sub-block (ulcDecoder.c:172-186)
+struct Tail { int start, end; float amp, l2; };     // decaying noise to the end of a sub-block (ulcDecoder.c:172-186); l2 = decay factor r
 struct Meta { int live, wc, nRuns[2], nTails[2]; uint32_t drawBase; int pad; Tail tail[2][8]; };
 
 struct Smem {
@@ -443,7 +443,7 @@ __device__ void parse_warp(Smem &sm, const UlcbDecodeArgs &args, int stream, con
                                             Tail t; t.start = start; t.end = start + left;
                                             t.amp = (float)(lv * lv) * quant_scale(co.q) * (1.0f / 16);
                                             const float decay = 1.0f + (float)(nn * nn) * -0x1.0p-19f;
-                                            t.l2 = decay != 1.0f ? log2f(decay) : 0.0f;
+                                            t.l2 = decay;
                                             mt.tail[c][nTails] = t;
                                         }
                                         nRuns++; nTails++;
@@ -594,7 +594,14 @@ __device__ __forceinline__ float tail_gain(const Meta &mt, int c, int nT, int id
     float g = 1.0f;
     for (int t = 0; t < nT; t++) {
         const Tail &tl = mt.tail[c][t];
-        if (idx >= tl.start && idx < tl.end) g = tl.amp * exp2f((float)(idx - tl.start) * tl.l2);
+        if (idx >= tl.start && idx < tl.end) {
+            // the reference's running product p *= r, step by step (ulcDecoder.c:178-184): in f32 it drifts up to 1e-4 away from
+            // amp * r^k for slow decays, so the closed form is not an option; tails are rare and this kernel is not the default
+            // path, so each value simply re-runs the chain from the start of the tail
+            g = tl.amp;
+            const float r = tl.l2;                           // the decay factor itself
+            for (int k = idx - tl.start; k > 0; k--) g = __fmul_rn(g, r);
+        }
     }
     return g;
 }
@@ -638,7 +645,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
         WTK(2);
         float *dbg = args.dbgCoefs ? args.dbgCoefs + (((size_t)stream * args.nBlocksAll + blk) * 2 + c) * N : nullptr;
 
-        if ((wc >> 4) == 1) {
+        if ((wc >> 4) <= 1) {                             // layouts 1 (N/1*) and 0 (N/1, "unused" but parseable, ulcHelper.h:29)
             // ======================= long block: register path =======================
             if (!kLayout) {
                 float v[32];
@@ -716,7 +723,7 @@ __device__ void transform_warp(Smem &sm, const UlcbDecodeArgs &args, int stream,
             }
             WTK(6);
             // un-fold (Fourier_IMDCT_Template.h:66-93) against the pending tail, all at the same k = lane + 32 k2
-            int ov = N >> (wc & 7);                       // the long block is its own transient sub-block (layout 0x8)
+            int ov = (wc >> 4) ? N >> (wc & 7) : N;       // layout 1: the long block is its own transient sub-block; layout 0: no overlap scaling
             if (ov > lastSub) ov = lastSub;
             lastSub = N;
             const int flat = (N - ov) >> 1;
