@@ -110,7 +110,7 @@ typedef struct ULCB_Context ULCB_Context;
 enum {
 	ULCB_OK            =  0,
 	ULCB_E_PARAM       = -1,   /* bad argument */
-	ULCB_E_UNSUPPORTED = -2,   /* valid for the reference, not built here yet (nChan > 2, BlockSize > 8192) */
+	ULCB_E_UNSUPPORTED = -2,   /* valid for the reference, not built here: BlockSize > 8192, nChan > 8, or nChan > 2 with nChan * BlockSize > 16384 */
 	ULCB_E_NOMEM       = -3,
 	ULCB_E_CUDA        = -4,   /* CUDA runtime error; ULCB_LastCudaError() has the code */
 	ULCB_E_NODEVICE    = -5,   /* no sm_100 GPU / kernel image: there is no CPU fallback */

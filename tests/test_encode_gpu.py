@@ -221,3 +221,34 @@ def test_other_sample_rates(capi, rate_hz, block_size, mode, param):
         f, bits = oracle.Decoder(2, block_size).decode_stream(ref["data"], nb)
         assert status[i] == -1
         assert np.abs(pcm_out[i, :nb * block_size].astype(np.int32) - oracle.float_to_pcm16(f).astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("n_chan,block_size,mode,param", [(3, 1024, "vbr", 60.0), (4, 2048, "vbr", 50.0), (5, 512, "cbr", 160.0), (6, 2048, "vbr", 70.0),
+                                                          (8, 1024, "abr", 256.0)])
+def test_more_than_two_channels(capi, n_chan, block_size, mode, param):
+    """channels are M/S-paired (0,1), (2,3), ..., an odd last channel stays unpaired (ulcEncoder_BlockTransform.c:102,
+    ulcDecoder.c:281-289).  Encoder bytes / block sizes / window decisions and decoder PCM against the oracle (pinned for 3-5 channels
+    against the compiled reference in tests/test_oracle_vs_ref.py)."""
+    from ulc_codec_b200 import corpus
+    ns = 6 * block_size + 777
+    pcms = []
+    for s in range(3):
+        planes = [corpus.generate(1200 + 10 * s + i, ns, "transient" if (i + s) & 1 else "music") for i in range((n_chan + 1) // 2)]
+        pcms.append(np.concatenate(planes, axis=1)[:, :n_chan].copy())
+    avg = 0.8 if mode == "abr" else 0.0
+    refs = [oracle.Encoder(44100, n_chan, block_size).encode_stream(p, mode, param, avg) for p in pcms]
+    with capi.Context(44100, n_chan, block_size) as ctx:
+        r = ctx.encode_streams(pcms, mode, param, avg)
+        nbs = [len(x["block_bytes"]) for x in refs]
+        pcm_f, status, bits = ctx.decode_streams([x["data"] for x in refs], nbs, fmt="f32", want_bits=True)
+        pcm_i, status_i, _ = ctx.decode_streams([x["data"] for x in refs], nbs, fmt="pcm16")
+    assert (r["status"] == 0).all() and (status == -1).all() and (status_i == -1).all()
+    for i, ref in enumerate(refs):
+        nb = nbs[i]
+        assert np.array_equal(r["block_bytes"][i][:nb], ref["block_bytes"]), i
+        assert np.array_equal(r["window_ctrl"][i][:nb], ref["window_ctrl"]), i
+        assert np.array_equal(r["streams"][i][:len(ref["data"])], ref["data"]), i
+        f, rbits = oracle.Decoder(n_chan, block_size).decode_stream(ref["data"], nb)
+        assert np.array_equal(bits[i][:nb].astype(np.int64), rbits.astype(np.int64))
+        assert np.abs(pcm_f[i, :nb * block_size] - f).max() < 1e-5 * np.abs(f).max()
+        assert np.abs(pcm_i[i, :nb * block_size].astype(np.int32) - oracle.float_to_pcm16(f).astype(np.int32)).max() <= 1

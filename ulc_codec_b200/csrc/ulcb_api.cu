@@ -317,7 +317,9 @@ int grow(ULCB_Context *ctx, void **p, size_t *cap, size_t need) {
     return ULCB_OK;
 }
 
-bool supported(int nChan, int N) { return nChan >= 1 && nChan <= 2 && N >= 256 && N <= 8192; }
+// Built: BlockSize 256..8192; mono and stereo at every block size, 3..8 channels while nChan * BlockSize <= 16384 (the generic
+// decoder keeps a whole block of every channel in shared memory and gives each thread at most 16 coefficients).
+bool supported(int nChan, int N) { return N >= 256 && N <= 8192 && nChan >= 1 && (nChan <= 2 || (nChan <= 8 && nChan * N <= 16384)); }
 bool valid(int nChan, int N) {
     return nChan >= 1 && nChan <= 255 && N >= 256 && N <= 32768 && (N & (N - 1)) == 0;
 }
@@ -509,6 +511,7 @@ static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes,
                          format, dStatus, dBlockBits, bitsStride, dbgCoefs, hOffs, hNBlocks);
     UlcbDecodeArgs a{};
     a.tb = ctx->tb;
+    a.nChan = ctx->nChan;
     a.nStreams = nStreams; a.nBlocksAll = (int)nBlocksAll;
     a.bytes = dBytes; a.streamOffs = dStreamOffs; a.nBlocks = dNBlocks;
     a.out = dOut; a.outStride = outStrideElems;
@@ -810,6 +813,7 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
     CK(ctx, cudaSetDevice(ctx->device));
     UlcbEncodeArgs a{};
     a.tb = ctx->etb;
+    a.nChan = ctx->nChan;
     a.nStreams = nStreams; a.nBlocksAll = (int)nBlocksAll; a.nBlocks = dNBlocks;
     a.pcm = dPcm; a.pcmFloat = format == ULCB_FMT_FLOAT32; a.inStride = inStrideElems; a.nSamples = dNSamples;
     a.mode = prm->mode;

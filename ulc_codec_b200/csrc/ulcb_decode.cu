@@ -324,17 +324,20 @@ __device__ void emit_chain(const Smem<NCH> &sm, int tp, int endSeg, int endPos, 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NCH, bool PCM16, int NTHR>
+// NCHT = channels per stream, fixed at compile time for mono and stereo; 0 = taken from the arguments (3 and more channels:
+// M/S pairs (0,1), (2,3), ..., an odd last channel stays unpaired - ulcDecoder.c:281-289).
+template <int NCHT, bool PCM16, int NTHR>
 __global__ void __launch_bounds__(NTHR, (NTHR <= 256 ? 3 : 1))
 ulcb_decode_kernel(UlcbDecodeArgs args) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const UlcbTables &tb = args.tb;
+    const int NCH = NCHT ? NCHT : args.nChan;
     const int N = tb.N, H = N >> 1;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int maxRuns = NCH * N / 16 + 8 * NCH;
     constexpr int MAXPAIRS = 4;                  // host picks NTHR >= NCH*N/16, so NCH*N/4 pairs fit 4 per thread
 
-    Smem<NCH> sm;
+    Smem<NCHT> sm;
     {
         unsigned char *p = smraw;
         sm.buf  = reinterpret_cast<float *>(p);     p += sizeof(float) * NCH * N;
@@ -393,9 +396,9 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                 if (tid == 0) sm.ctl[C_NRUNS] = 0;
                 auto ensure = [&](long long q) {           // make q's page current (uniform across the CTA)
                     long long pg = q / PAGE_NYB;
-                    if (pg != curPage) { curPage = pg; load_page<NCH>(sm, abase, pg, nWordsValid); }
+                    if (pg != curPage) { curPage = pg; load_page<NCHT>(sm, abase, pg, nWordsValid); }
                 };
-                auto read_nyb = [&](long long q) -> int { ensure(q); return page_nyb<NCH>(sm, (int)(q - curPage * PAGE_NYB)); };
+                auto read_nyb = [&](long long q) -> int { ensure(q); return page_nyb<NCHT>(sm, (int)(q - curPage * PAGE_NYB)); };
                 __syncthreads();
                 int h0 = read_nyb(pos++);
                 if (h0 & 8) wc = h0 | (read_nyb(pos++) << 4); else wc = h0 | 0x10;
@@ -419,7 +422,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                                 int tp = (int)(pos - curPage * PAGE_NYB);
                                 __syncthreads();
                                 DTK(5);
-                                resolve_chain<NCH>(sm, tp, remain, q, sub0 + (S - remain), (int)blkDraws);
+                                resolve_chain<NCHT>(sm, tp, remain, q, sub0 + (S - remain), (int)blkDraws);
                                 __syncthreads();
                                 DTK(6);
                                 int sEnd = sm.ctl[C_SEND];
@@ -430,7 +433,7 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                                            sm.ctl[C_ENDCOEFS], sm.ctl[C_ENDDRAWS], sm.ctl[C_OK], sm.ctl[C_EXITPH], sm.ctl[C_SUMCOEFS]);
 #endif
                                 if (!sm.ctl[C_OK]) { ok = false; break; }
-                                emit_chain<NCH>(sm, tp, sEnd < 0 ? PAGE_WORDS : sEnd, sm.ctl[C_ENDPOS], maxRuns, drawBase);
+                                emit_chain<NCHT>(sm, tp, sEnd < 0 ? PAGE_WORDS : sEnd, sm.ctl[C_ENDPOS], maxRuns, drawBase);
                                 DTK(7);
                                 if (sEnd >= 0) {
                                     const int kind = sm.ctl[C_ENDKIND];
@@ -621,8 +624,14 @@ ulcb_decode_kernel(UlcbDecodeArgs args) {
                     }
                 }
             } else {
-                for (int i = tid; i < N; i += nthr) {
-                    float v = sm.buf[i];
+                // any channel count: output sample i = n * NCH + c
+                for (int i = tid; i < N * NCH; i += nthr) {
+                    const int n = i / NCH, c = i - n * NCH;
+                    float v = sm.buf[c * N + n];
+                    if ((c | 1) < NCH) {                                 // paired channel: undo M/S
+                        const float m = sm.buf[(c & ~1) * N + n], sd = sm.buf[(c | 1) * N + n];
+                        v = (c & 1) ? m - sd : m + sd;
+                    }
                     if (PCM16) {
                         v = fminf(fmaxf(v * 32768.0f, -32768.0f), 32767.0f);
                         reinterpret_cast<int16_t *>(outBlk)[i] = (int16_t)__float2int_rn(v);
@@ -670,8 +679,9 @@ static cudaError_t launch_t(const UlcbDecodeArgs &args, int pcm16, int gridBlock
 }
 
 int ulcb_decode_threads(int N, int nChan) {
-    int t = nChan * N / 16;
-    return t < 256 ? 256 : t;
+    int t = 256;
+    while (t < nChan * N / 16) t <<= 1;          // >= nChan*N/16 (4 pairs per thread in the DCT), one of 256 / 512 / 1024 / (too many)
+    return t;
 }
 
 cudaError_t ulcb_decode_launch(const UlcbDecodeArgs &args, int nChan, int pcm16, int gridBlocks, cudaStream_t stream) {
@@ -694,6 +704,10 @@ cudaError_t ulcb_decode_launch(const UlcbDecodeArgs &args, int nChan, int pcm16,
         if (nthr == 256)  return launch_t<1, 256>(args, pcm16, gridBlocks, smem, stream);
         if (nthr == 512)  return launch_t<1, 512>(args, pcm16, gridBlocks, smem, stream);
         if (nthr == 1024) return launch_t<1, 1024>(args, pcm16, gridBlocks, smem, stream);
+    } else if (nChan == args.nChan) {
+        if (nthr == 256)  return launch_t<0, 256>(args, pcm16, gridBlocks, smem, stream);
+        if (nthr == 512)  return launch_t<0, 512>(args, pcm16, gridBlocks, smem, stream);
+        if (nthr == 1024) return launch_t<0, 1024>(args, pcm16, gridBlocks, smem, stream);
     }
     return cudaErrorInvalidValue;
 }

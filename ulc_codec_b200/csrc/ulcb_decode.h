@@ -15,6 +15,7 @@ struct UlcbStreamState {
 
 struct UlcbDecodeArgs {
     UlcbTables      tb;
+    int             nChan;             // channels per stream (the kernels specialised for 1 / 2 ignore it)
     int             nStreams;
     int             nBlocksAll;        // used when nBlocks == nullptr
     const uint8_t  *bytes;             // all streams, device

@@ -52,9 +52,12 @@ __constant__ uint16_t kLayoutE[16] = {
 
 struct SubInfo { int off, S, lgS, sh, ovL, ovR; };
 
-enum { MAXU = 8, MAXBU = 12 };
+constexpr int ULCB_ENC_MAXCH = 8;      // most channels the run-time-channel-count instantiation takes
 
-struct EncSmall {
+// MAXU = channels x sub-blocks (4 at most) = units of the coder and of the Bark analysis; + one amplitude unit per sub-block
+template <int MAXU>
+struct EncSmallT {
+    static constexpr int MAXBU = MAXU + 4;
     float   env[3];
     float   seg[32];                 // {sum,cnt} x 16: [0..7] previous block, [8..15] current
     SubInfo sub[4];
@@ -276,7 +279,8 @@ __device__ __forceinline__ void dct2_leaf8(float *x) {
     x[1] = (a1 + e1) * R; x[5] = b1; x[3] = c1; x[7] = (a1 - e1) * R;
 }
 
-__device__ __forceinline__ int find_sub(const EncSmall &sm, int n) {     // sub-block holding in-channel index n
+template <class SM>
+__device__ __forceinline__ int find_sub(const SM &sm, int n) {     // sub-block holding in-channel index n
     int j = 0;
     const int ns = sm.nsub;
     if (ns > 1) {
@@ -394,42 +398,49 @@ __device__ __forceinline__ void put_quant(Sink &w, int inf) {            // ulcE
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int NTHR>
+template <int NCHT, int NTHR>            // NCHT = channels, 0 = taken from the arguments (3 .. ULCB_ENC_MAXCH)
 struct Encoder {
+    static constexpr int MAXCH = NCHT ? NCHT : ULCB_ENC_MAXCH;
+    using EncSmall = EncSmallT<4 * MAXCH>;
+    static constexpr int MAXU = 4 * MAXCH;
     const UlcbEncodeArgs &args;
     const UlcbEncTables &tb;
     EncSmall &sm;
     Work w;
-    const int N, CN, H, tid;
-
+    const int nchRt, N, CN, H, tid;
+    __device__ __forceinline__ int nch() const { return NCHT ? NCHT : nchRt; }
     __device__ Encoder(const UlcbEncodeArgs &a, EncSmall &s, const Work &wk)
-        : args(a), tb(a.tb), sm(s), w(wk), N(a.tb.N), CN(NCH * a.tb.N), H(a.tb.N >> 1), tid(threadIdx.x) {}
+        : args(a), tb(a.tb), sm(s), w(wk), nchRt(a.nChan), N(a.tb.N), CN((NCHT ? NCHT : a.nChan) * a.tb.N), H(a.tb.N >> 1), tid(threadIdx.x) {}
 
+    // Coefficients per thread in the rank and coder phases: thread t owns [t*E, (t+1)*E).  E is a power of two, so it divides every
+    // sub-block size (N/8 >= 32 >= E) and a thread's slots never straddle a sub-block or a channel; with a channel count that is
+    // not a power of two the last threads own nothing.
+    __device__ __forceinline__ int slot_items() const { const int e = CN / NTHR; return (e & (e - 1)) ? 1 << (32 - __clz(e)) : e; }
     __device__ __forceinline__ float *blk(int k) const { return w.R + ((k + 3) % 3) * CN; }
 
     // ---------------- ingest ----------------
     __device__ void ingest(int k, const void *pcm, long long validSamples) {
         float *R0 = blk(k);
         for (int n = tid; n < N; n += NTHR) {
-            float v[NCH];
+            float v[MAXCH];
             bool ok = n < validSamples;
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
+            for (int c = 0; c < nch(); c++) {
                 float x = 0.0f;
                 if (ok) {
-                    if (args.pcmFloat) x = reinterpret_cast<const float *>(pcm)[(size_t)n * NCH + c];
-                    else x = (float)reinterpret_cast<const int16_t *>(pcm)[(size_t)n * NCH + c] * 0x1.0p-15f;   // tools/WavIO_Helper.c:49-55
+                    if (args.pcmFloat) x = reinterpret_cast<const float *>(pcm)[(size_t)n * nch() + c];
+                    else x = (float)reinterpret_cast<const int16_t *>(pcm)[(size_t)n * nch() + c] * 0x1.0p-15f;   // tools/WavIO_Helper.c:49-55
                 }
                 v[c] = x;
             }
 #pragma unroll
-            for (int c = 1; c < NCH; c += 2) {                       // M/S (ulcEncoder_BlockTransform.c:102-111)
+            for (int c = 1; c < nch(); c += 2) {                       // M/S (ulcEncoder_BlockTransform.c:102-111)
                 float a = v[c - 1], b = v[c];
                 v[c - 1] = (a + b) * 0.5f;
                 v[c]     = (a - b) * 0.5f;
             }
 #pragma unroll
-            for (int c = 0; c < NCH; c++) R0[c * N + n] = v[c];
+            for (int c = 0; c < nch(); c++) R0[c * N + n] = v[c];
         }
     }
 
@@ -477,7 +488,7 @@ struct Encoder {
     }
     __device__ void fold(int k) {
         const float *R1 = blk(k - 1), *R2 = blk(k - 2);
-        for (int P = tid; P < NCH * H; P += NTHR) {
+        for (int P = tid; P < nch() * H; P += NTHR) {
             const int c = P >> (tb.log2N - 1), r = P & (H - 1);
             const int j = find_sub(sm, 2 * r);
             const SubInfo s = sm.sub[j];
@@ -509,8 +520,8 @@ struct Encoder {
     __device__ __forceinline__ void locate(int P, int &hb, int &cbase, int &j, int &lp) const {
         // pair index P in [0, CN) -> buffer half, channel base, sub-block, local pair index
         const int lgH = tb.log2N - 1;
-        const int cc = P >> lgH, r = P & (H - 1);                     // cc = hb*NCH + c
-        hb = cc >= NCH; const int c = hb ? cc - NCH : cc;
+        const int cc = P >> lgH, r = P & (H - 1);                     // cc = hb*nch() + c
+        hb = cc >= nch(); const int c = hb ? cc - nch() : cc;
         j = find_sub(sm, 2 * r);
         lp = r - (sm.sub[j].off >> 1);
         cbase = c * N + sm.sub[j].off;
@@ -585,9 +596,9 @@ struct Encoder {
 #pragma unroll 4
         for (int P = tid; P < CN; P += NTHR) {
             const int cc = P >> lgH, r = P & (H - 1);
-            const bool hb = cc >= NCH;
+            const bool hb = cc >= nch();
             const int node = r >> (lgm - 1), i = r & (hm - 1);
-            const int off = (hb ? cc - NCH : cc) * N + (node << lgm);
+            const int off = (hb ? cc - nch() : cc) * N + (node << lgm);
             const float *src = (hb ? S1 : S0) + off;
             float *dst = (hb ? D1 : D0) + off;
             float a = src[i], b = src[m - 1 - i];
@@ -620,9 +631,9 @@ struct Encoder {
 #pragma unroll 2
         for (int Q = tid; Q < (CN >> 1); Q += NTHR) {
             const int cc = Q >> (lgH - 1), r = Q & ((H >> 1) - 1);
-            const bool hb = cc >= NCH;
+            const bool hb = cc >= nch();
             const int node = r >> (lgm - 2), i = r & (qm - 1), i2 = hm - 1 - i;
-            const int off = (hb ? cc - NCH : cc) * N + (node << lgm);
+            const int off = (hb ? cc - nch() : cc) * N + (node << lgm);
             const float *src = (hb ? S1 : S0) + off;
             float *dst = (hb ? D1 : D0) + off;
             const float a0 = src[i], b0 = src[m - 1 - i], a1 = src[i2], b1 = src[hm + i];
@@ -643,9 +654,9 @@ struct Encoder {
 #pragma unroll 4
         for (int P = tid; P < CN; P += NTHR) {
             const int cc = P >> lgH, r = P & (H - 1);
-            const bool hb = cc >= NCH;
+            const bool hb = cc >= nch();
             const int node = r >> (lgm - 1), i = r & (hm - 1);
-            const int off = (hb ? cc - NCH : cc) * N + (node << lgm);
+            const int off = (hb ? cc - nch() : cc) * N + (node << lgm);
             const float *src = (hb ? S1 : S0) + off;
             float *dst = (hb ? D1 : D0) + off;
             if (node_is_dct4(d, node)) {                              // Fourier_DCT4_Template.h:100-114
@@ -691,7 +702,7 @@ struct Encoder {
             const int n0 = 2 * p - s.off;                             // even local index
             float amp = 0.0f;
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
+            for (int c = 0; c < nch(); c++) {
                 const int base = c * N + s.off;
                 float re0 = w.XA[base + n0] * norm, re1 = w.XA[base + n0 + 1] * norm;
                 float im0 = w.XB[base + s.S - 1 - n0] * norm, im1 = w.XB[base + s.S - 2 - n0] * norm;   // MDST is stored reversed (:184-186)
@@ -799,7 +810,7 @@ struct Encoder {
     }
     __device__ void serial_sums(int k) {
         const float *lgN = blk(k - 2);
-        const int U = NCH * sm.nsub, nTasks = U + sm.nsub + 1;
+        const int U = nch() * sm.nsub, nTasks = U + sm.nsub + 1;
         constexpr int NW = NTHR / 32;
         const int warp = tid >> 5, lane = tid & 31;
         for (int task = warp; task < nTasks; task += NW) {
@@ -844,13 +855,13 @@ struct Encoder {
         return l * (1.0f - fr) + r * fr;
     }
     __device__ void spread() {
-        const int U = NCH * sm.nsub;
+        const int U = nch() * sm.nsub;
         for (int p = tid; p < H; p += NTHR) {
             const int j = find_sub(sm, 2 * p);
             const SubInfo &s = sm.sub[j];
             const int line = p - (s.off >> 1);
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
+            for (int c = 0; c < nch(); c++) {
                 float v = bark_interp(sm.band[c * sm.nsub + j], s.sh, line);
                 float wgt = expf_ref(0.5f * v);
                 float *dst = w.TB + c * N + s.off + 2 * line;
@@ -880,11 +891,11 @@ struct Encoder {
         // LSD radix sort, 4 bits per pass, stable: equal keys stay in index order
         const uint32_t *uk = reinterpret_cast<const uint32_t *>(w.TA);
         uint16_t *src = reinterpret_cast<uint16_t *>(w.XB), *dst = src + CN;
-        const int E = CN / NTHR;
+        const int E = slot_items(), Ev = tid * E < CN ? E : 0;
         for (int shift = 0; shift < 32; shift += 4) {
 #pragma unroll
             for (int d = 0; d < 16; d++) w.cnt[d * NTHR + tid] = 0;
-            for (int e = 0; e < E; e++) {
+            for (int e = 0; e < Ev; e++) {
                 int dg = (uk[src[tid * E + e]] >> shift) & 15;
                 w.cnt[dg * NTHR + tid]++;
             }
@@ -896,7 +907,7 @@ struct Encoder {
 #pragma unroll
             for (int q = 0; q < 16; q++) { int t = w.cnt[tid * 16 + q]; w.cnt[tid * 16 + q] = (uint16_t)base; base += t; }
             wsync<NTHR>();
-            for (int e = 0; e < E; e++) {
+            for (int e = 0; e < Ev; e++) {
                 uint16_t ix = src[tid * E + e];
                 int dg = (uk[ix] >> shift) & 15;
                 int pos = w.cnt[dg * NTHR + tid]++;
@@ -920,10 +931,10 @@ struct Encoder {
     // key (4 histogram passes of 8 bits, no scatter) replaces the 8-pass sort.  Keys equal to the threshold are taken in
     // index order, which is the order the stable sort gives them.  Writes rank = 0 (kept) / 0xFFFF (dropped).
     static constexpr int MAXE = 16;
-    __device__ bool can_select() const { return CN / NTHR <= MAXE; }
+    __device__ bool can_select() const { return slot_items() <= MAXE; }
     __device__ void rank_select(int nOut) {
         const uint32_t *uk = reinterpret_cast<const uint32_t *>(w.TA);
-        const int E = CN / NTHR, i0 = tid * E;
+        const int i0 = tid * slot_items(), E = i0 < CN ? slot_items() : 0;      // E = this thread's keys (all or none)
         uint32_t key[MAXE];
 #pragma unroll
         for (int e = 0; e < MAXE; e++) key[e] = e < E ? uk[i0 + e] : 0xffffffffu;
@@ -990,7 +1001,7 @@ struct Encoder {
         uint16_t *jump = reinterpret_cast<uint16_t *>(w.encScratch);             // [CN] next zone start if a zone starts here
         uint8_t  *qcand = w.encScratch + 2 * CN;                                  // [CN] quantiser of that zone
         const float *coef = w.XA, *pairs = w.TB;
-        const int E = CN / NTHR, U = NCH * sm.nsub, i0 = tid * E;
+        const int Eall = slot_items(), U = nch() * sm.nsub, i0 = tid * Eall, E = i0 < CN ? Eall : 0;   // E = this thread's slots (all or none)
         const int capNyb = 8 * ((CN >> 1) + 4);                                   // 2*CN + 16 bytes
 
 #ifdef ULCB_PHASE_TIMING
@@ -1102,7 +1113,7 @@ struct Encoder {
         // unit of this thread's slots (a thread's slots never straddle a sub-block: E divides every sub-block size)
         const int c = i0 >> tb.log2N, nloc = i0 & (N - 1), j = find_sub(sm, nloc), u = c * sm.nsub + j;
         const int uOff = c * N + sm.sub[j].off, uEnd = uOff + sm.sub[j].S;
-        const bool ownsTail = (i0 + E == uEnd);
+        const bool ownsTail = E && (i0 + E == uEnd);
 
         auto walk = [&](auto &sink, bool cacheTail) {
             int nc = prevKeptP1 > uOff ? prevKeptP1 : uOff;
@@ -1171,11 +1182,12 @@ struct Encoder {
 // b-1, first half of block b, one sample either side) straight from the PCM input, so it shares nothing with
 // the workers but the published decision.  The tap energies are computed by the 32 lanes; the three one-pole
 // envelope recurrences are serial by definition and run on lane 0 in the reference's operation order.
-template <int NCH>
+template <int NCHT>
 struct Detector {
+    static constexpr int MAXCH = NCHT ? NCHT : ULCB_ENC_MAXCH;
     const UlcbEncodeArgs &args;
     float2 *E;                    // [3][N] private scratch: the block buffers of the three pipelined passes
-    float *stg;                   // [NCH][N+2] analysis window, M/S
+    float *stg;                   // [nch()][N+2] analysis window, M/S
     float *seg;                   // [32] {sum,cnt} x 16 (shared memory)
     float env[3];
     const unsigned char *pcm; long long nSamples; const float *prevBlk;   // prevBlk: block before this call (M/S planar) or nullptr
@@ -1187,6 +1199,8 @@ struct Detector {
     // the reference's operation order, so the decisions are unchanged.  E holds three block buffers that rotate through
     // the roles post (in place) -> pre (in place) -> blk (read).  Returns the decision for block it-2 (it >= 2).
     float preHp = 0.0f, preBp = 0.0f;          // post-mask end values of the block whose pre-mask pass comes next
+    int nchRt = NCHT;
+    __device__ __forceinline__ int nch() const { return NCHT ? NCHT : nchRt; }
     __device__ int iterate(int it, int nBlocks) {
         const int N = args.tb.N, H = N >> 1, lane = threadIdx.x & 31, W = N + 2;
         const UlcbEncTables &tb = args.tb;
@@ -1204,7 +1218,7 @@ struct Detector {
             const size_t elem = args.pcmFloat ? 4 : 2;
             const long long s0 = (long long)b * N + H - 1;
             const long long lo = s0 < 0 ? 0 : s0, hi = (s0 + W < nSamples ? s0 + W : nSamples);
-            for (long long o = lo * NCH * (long long)elem + 128ll * lane; o < hi * NCH * (long long)elem; o += 128 * 32)
+            for (long long o = lo * nch() * (long long)elem + 128ll * lane; o < hi * nch() * (long long)elem; o += 128 * 32)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pcm + o));
         }
         if (doPost) {
@@ -1215,9 +1229,9 @@ struct Detector {
                 i0 = (-sBeg < (long long)W) ? (int)(-sBeg) : W;
                 for (int i = lane; i < i0; i += 32)
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) stg[c * W + i] = prevBlk ? prevBlk[c * N + (int)(N + sBeg + i)] : 0.0f;
+                    for (int c = 0; c < nch(); c++) stg[c * W + i] = prevBlk ? prevBlk[c * N + (int)(N + sBeg + i)] : 0.0f;
             }
-            if (nSamples > 0 && NCH == 2 && !args.pcmFloat) {
+            if (nSamples > 0 && nch() == 2 && !args.pcmFloat) {
                 // stereo PCM16: one 32-bit load per sample pair, 16 of them in flight per lane
                 const uint32_t *p32 = reinterpret_cast<const uint32_t *>(pcm);
                 for (int ib = i0 + lane; ib < W; ib += 512) {
@@ -1241,7 +1255,7 @@ struct Detector {
                 }
             } else if (nSamples > 0) {
                 for (int ib = i0 + lane; ib < W; ib += 256) {             // 8 independent loads in flight per lane
-                    float v[8][NCH]; bool ok[8];
+                    float v[8][MAXCH]; bool ok[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const int i = ib + 32 * u;
@@ -1249,24 +1263,24 @@ struct Detector {
                         ok[u] = i < W && sv < nSamples;
                         const size_t sc = ok[u] ? (size_t)sv : 0;
 #pragma unroll
-                        for (int q = 0; q < NCH; q++)
-                            v[u][q] = args.pcmFloat ? reinterpret_cast<const float *>(pcm)[sc * NCH + q]
-                                                    : (float)reinterpret_cast<const int16_t *>(pcm)[sc * NCH + q] * 0x1.0p-15f;
+                        for (int q = 0; q < nch(); q++)
+                            v[u][q] = args.pcmFloat ? reinterpret_cast<const float *>(pcm)[sc * nch() + q]
+                                                    : (float)reinterpret_cast<const int16_t *>(pcm)[sc * nch() + q] * 0x1.0p-15f;
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const int i = ib + 32 * u;
 #pragma unroll
-                        for (int c = 1; c < NCH; c += 2) { float a = v[u][c - 1], bb = v[u][c]; v[u][c - 1] = (a + bb) * 0.5f; v[u][c] = (a - bb) * 0.5f; }
+                        for (int c = 1; c < nch(); c += 2) { float a = v[u][c - 1], bb = v[u][c]; v[u][c - 1] = (a + bb) * 0.5f; v[u][c] = (a - bb) * 0.5f; }
                         if (i < W)
 #pragma unroll
-                            for (int c = 0; c < NCH; c++) stg[c * W + i] = ok[u] ? v[u][c] : 0.0f;
+                            for (int c = 0; c < nch(); c++) stg[c * W + i] = ok[u] ? v[u][c] : 0.0f;
                     }
                 }
             } else {
                 for (int i = i0 + lane; i < W; i += 32)
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) stg[c * W + i] = 0.0f;
+                    for (int c = 0; c < nch(); c++) stg[c * W + i] = 0.0f;
             }
             __syncwarp();
             DTICK(16);
@@ -1274,7 +1288,7 @@ struct Detector {
             for (int n = lane; n < N; n += 32) {
                 float ehp = 0.0f, ebp = 0.0f;
 #pragma unroll
-                for (int c = 0; c < NCH; c++) {
+                for (int c = 0; c < nch(); c++) {
                     float t0 = stg[c * W + n], t1 = stg[c * W + n + 1], t2 = stg[c * W + n + 2];
                     float hp = (-t0 + 2.0f * t1) - t2, bp = -t0 + t2;
                     ehp += hp * hp; ebp += bp * bp;
@@ -1346,9 +1360,11 @@ struct Detector {
     }
 };
 
-template <int NCH, int NTHR, bool GWS>
+template <int NCHT, int NTHR, bool GWS>
 __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArgs args) {
     extern __shared__ __align__(16) unsigned char smraw[];
+    const int NCH = NCHT ? NCHT : args.nChan;
+    using EncSmall = typename Encoder<NCHT, NTHR>::EncSmall;
     const int N = args.tb.N, CN = NCH * N, H = N >> 1;
     const int tid = threadIdx.x;
     const bool isDetector = tid >= NTHR;                              // the extra warp
@@ -1367,7 +1383,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
         wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
         wk.encScratch = GWS ? reinterpret_cast<uint8_t *>(big + 7 * CN) : reinterpret_cast<uint8_t *>(wk.cnt);
     }
-    Encoder<NCH, NTHR> enc(args, sm, wk);
+    Encoder<NCHT, NTHR> enc(args, sm, wk);
 
     for (int stream = blockIdx.x; stream < args.nStreams; stream += gridDim.x) {
         const int nBlocks = args.nBlocks ? (int)args.nBlocks[stream] : args.nBlocksAll;
@@ -1381,8 +1397,9 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
         if (isDetector) {
             // ================= transient detector warp: decisions for blocks 0..nBlocks-1, one block ahead =================
             const int lane = tid & 31;
-            Detector<NCH> det{args, detE, detStage, sm.seg, {0.0f, 0.0f, 0.0f}, pcm, nSamples,
+            Detector<NCHT> det{args, detE, detStage, sm.seg, {0.0f, 0.0f, 0.0f}, pcm, nSamples,
                               resume ? args.stateSamples + (size_t)stream * 2 * CN + CN : nullptr};
+            det.nchRt = NCH;
             if (lane == 0)
                 for (int i = 0; i < 16; i++) { sm.seg[i] = 0.0f; sm.seg[16 + i] = resume ? st->seg[i] : 0.0f; }
             if (resume) for (int i = 0; i < 3; i++) det.env[i] = st->env[i];      // every lane: the chains run SIMD across lanes
@@ -1579,11 +1596,12 @@ cudaError_t ulcb_avg_complexity_launch(const float *dComplexity, uint64_t metaSt
     return cudaGetLastError();
 }
 
-bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4096; }
+bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4096 || nChan > 2; }
 int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }
 size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)8 * nChan * N + 64 + (size_t)6 * N; }   // + the detector's 3 block buffers
 size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs) {
-    size_t s = ((sizeof(EncSmall) + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * (nChan < 2 ? 2 : nChan) * (N + 4);
+    const size_t small = nChan == 1 ? sizeof(EncSmallT<4>) : nChan == 2 ? sizeof(EncSmallT<8>) : sizeof(EncSmallT<4 * ULCB_ENC_MAXCH>);
+    size_t s = ((small + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * (nChan < 2 ? 2 : nChan) * (N + 4);
     if (!globalWs) s += sizeof(float) * ((size_t)7 * nChan * N + 64);
     return s + 16;
 }
@@ -1592,7 +1610,7 @@ template <int NCH, int NTHR>
 static cudaError_t launch_e(const UlcbEncodeArgs &args, int gridBlocks, cudaStream_t stream) {
     const bool gws = args.workspace != nullptr;
     void (*k)(UlcbEncodeArgs) = gws ? ulcb_encode_kernel<NCH, NTHR, true> : ulcb_encode_kernel<NCH, NTHR, false>;
-    size_t smem = ulcb_encode_smem_bytes(args.tb.N, NCH, NTHR, gws);
+    size_t smem = ulcb_encode_smem_bytes(args.tb.N, NCH ? NCH : args.nChan, NTHR, gws);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<gridBlocks, NTHR + 32, smem, stream>>>(args);
@@ -1603,5 +1621,8 @@ cudaError_t ulcb_encode_launch(const UlcbEncodeArgs &args, int nChan, int gridBl
     const int nthr = ulcb_encode_threads(args.tb.N, nChan);
     if (nChan == 2) return nthr == 512 ? launch_e<2, 512>(args, gridBlocks, stream) : launch_e<2, 256>(args, gridBlocks, stream);
     if (nChan == 1) return nthr == 512 ? launch_e<1, 512>(args, gridBlocks, stream) : launch_e<1, 256>(args, gridBlocks, stream);
+    // 3 .. ULCB_ENC_MAXCH channels: one instantiation with the channel count at run time, work buffers in the global workspace
+    if (nChan <= ULCB_ENC_MAXCH && nChan == args.nChan && args.workspace)
+        return nthr == 512 ? launch_e<0, 512>(args, gridBlocks, stream) : launch_e<0, 256>(args, gridBlocks, stream);
     return cudaErrorInvalidValue;
 }

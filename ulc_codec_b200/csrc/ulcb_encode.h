@@ -48,6 +48,7 @@ enum { ULCB_ENC_VBR = 0, ULCB_ENC_CBR = 1, ULCB_ENC_ABR = 2,
 
 struct UlcbEncodeArgs {
     UlcbEncTables   tb;
+    int             nChan;             // channels per stream (the kernels specialised for 1 / 2 ignore it)
     int             nStreams;
     int             nBlocksAll;        // blocks per stream when nBlocks == nullptr
     const uint32_t *nBlocks;           // [nStreams] or nullptr
