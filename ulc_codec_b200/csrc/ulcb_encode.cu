@@ -767,13 +767,15 @@ struct Encoder {
             __syncwarp();
             stage[0][lane] = L; stage[1][lane] = L * X; stage[2][lane] = X;
             __syncwarp();
+            if (lane < 3) {                                               // the other lanes have no chain (and must not touch the stage)
 #pragma unroll
-            for (int t0 = 0; t0 < 32; t0 += 8) {
-                double a[8];
+                for (int t0 = 0; t0 < 32; t0 += 8) {
+                    double a[8];
 #pragma unroll
-                for (int t = 0; t < 8; t++) a[t] = stage[src][t0 + t];
+                    for (int t = 0; t < 8; t++) a[t] = stage[src][t0 + t];
 #pragma unroll
-                for (int t = 0; t < 8; t++) { if (lane < 3) stage[src][t0 + t] = acc; acc += a[t]; }
+                    for (int t = 0; t < 8; t++) { stage[src][t0 + t] = acc; acc += a[t]; }
+                }
             }
             __syncwarp();
             events_in(base);
