@@ -26,11 +26,12 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
     auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     const int M = S >> 1;                       // complex FFT size
     const float2 *__restrict__ E = tb.dctE[sh];
+    const int lgM = 31 - __clz(M);              // every size is a power of two: index splits are shifts and masks, not divisions
 
     // ---- pre-twiddle: pairs (n, M-1-n), n < M/2 ----
     const int halfM = M >> 1;
     for (int idx = tid; idx < nT * halfM; idx += nthr) {
-        int t = idx / halfM, n = idx - t * halfM, m = M - 1 - n;
+        int t = idx >> (lgM - 1), n = idx & (halfM - 1), m = M - 1 - n;
         float2 *z = reinterpret_cast<float2 *>(base + t * stride);
         float2 a = z[n], b = z[m];              // a = (v[2n], v[2n+1]); b = (v[2m], v[2m+1])
         float2 zn = cmul(make_float2(a.x, b.y), __ldg(&E[n]));
@@ -43,13 +44,14 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
     // ---- radix-4 DIF stages ----
     const int Mmax = tb.N >> 1;
     const float2 *__restrict__ W = tb.fftW;
-    int L = M;
-    for (; L >= 4; L >>= 2) {
+    int L = M, lgL = lgM;
+    const int lgMmax = 31 - __clz(Mmax);
+    for (; L >= 4; L >>= 2, lgL -= 2) {
         const int q = L >> 2;                   // quarter length
-        const int wstep = Mmax / L;
+        const int wstep = 1 << (lgMmax - lgL);
         for (int idx = tid; idx < nT * (M >> 2); idx += nthr) {
-            int t = idx / (M >> 2), w = idx - t * (M >> 2);
-            int g = w / q, j = w - g * q;
+            int t = idx >> (lgM - 2), w = idx & ((M >> 2) - 1);
+            int g = w >> (lgL - 2), j = w & (q - 1);
             float2 *x = reinterpret_cast<float2 *>(base + t * stride) + g * L + j;
             float2 a0 = x[0], a1 = x[q], a2 = x[2 * q], a3 = x[3 * q];
             float2 b0 = make_float2(a0.x + a2.x, a0.y + a2.y);
@@ -72,7 +74,7 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
     }
     if (L == 2) {                               // odd log2(M): one radix-2 stage on adjacent pairs
         for (int idx = tid; idx < nT * (M >> 1); idx += nthr) {
-            int t = idx / (M >> 1), g = idx - t * (M >> 1);
+            int t = idx >> (lgM - 1), g = idx & ((M >> 1) - 1);
             float2 *x = reinterpret_cast<float2 *>(base + t * stride) + 2 * g;
             float2 a0 = x[0], a1 = x[1];
             x[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
@@ -88,7 +90,7 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
     for (int r = 0; r < MAXPAIRS; r++) {
         int idx = tid + r * nthr;
         if (idx < nT * halfM) {
-            int t = idx / halfM, k = idx - t * halfM, m = M - 1 - k;
+            int t = idx >> (lgM - 1), k = idx & (halfM - 1), m = M - 1 - k;
             const float2 *z = reinterpret_cast<const float2 *>(base + t * stride);
             float2 yk = cmul(z[__ldg(&P[k])], __ldg(&E[k]));
             float2 ym = cmul(z[__ldg(&P[m])], __ldg(&E[m]));
@@ -101,7 +103,7 @@ __device__ void dct4_inplace(float *base, int stride, int nT, int S, int sh, con
     for (int r = 0; r < MAXPAIRS; r++) {
         int idx = tid + r * nthr;
         if (idx < nT * halfM) {
-            int t = idx / halfM, k = idx - t * halfM, m = M - 1 - k;
+            int t = idx >> (lgM - 1), k = idx & (halfM - 1), m = M - 1 - k;
             float2 *z = reinterpret_cast<float2 *>(base + t * stride);
             z[k] = o0[r];
             z[m] = o1[r];
