@@ -43,6 +43,7 @@ struct ULCB_Context {
     void *bpDesc = nullptr;  size_t bpDescCap = 0;
     void *bpBad = nullptr;   size_t bpBadCap = 0;
     void *bpArena = nullptr; size_t bpArenaCap = 0;
+    size_t bpPlanCap = 0;               // bytes of arena a wave may plan for
     void *hPlan = nullptr;   size_t hPlanCap = 0;   // pinned: stream offsets / block counts read back to plan the waves
     // per-kernel timing (ULCB_SetKernelTiming): event pairs recorded around the launches, resolved by ULCB_KernelTimes
     bool timing = false;
@@ -436,11 +437,15 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
 
     // waves: as many streams as the arena cap holds
     static const size_t capEnv = getenv("ULCB_BP_ARENA_MB") ? (size_t)atoll(getenv("ULCB_BP_ARENA_MB")) << 20 : (size_t)8192 << 20;
-    size_t cap = capEnv;
-    {
-        size_t fr = 0, tot = 0;
-        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) { const size_t lim = (fr + ctx->bpArenaCap) / 2; if (cap > lim) cap = lim; }
+    // waves never plan for more than half of what was free when the context first decoded (asked once: cudaMemGetInfo is a slow,
+    // serialising driver call, and a step that starts with a tiny kernel has nothing queued to hide it behind - it showed as
+    // 50 ms gaps in some steps)
+    if (ctx->bpPlanCap == 0) {
+        size_t fr = 0, tot = 0, cap0 = capEnv;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) { const size_t lim = (fr + ctx->bpArenaCap) / 2; if (cap0 > lim) cap0 = lim; }
+        ctx->bpPlanCap = cap0 ? cap0 : 1;
     }
+    const size_t cap = ctx->bpPlanCap;
     static const int runLen = getenv("ULCB_BP_RUNLEN") ? atoi(getenv("ULCB_BP_RUNLEN")) : 64;
     UlcbBpArgs a{};
     a.tb = ctx->tb; a.nSignBits = ctx->tb.nSignBits;
