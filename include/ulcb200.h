@@ -181,6 +181,16 @@ int ULCB_DecodeStreamsIndexed(ULCB_Context *ctx, int nStreams,
 
 int ULCB_Sync(ULCB_Context *ctx);
 
+/* The block index a .ulc file does not carry (tools/ulc_Helper.h:10-20): the size in bytes of every block of every stream, found
+ * by walking the token lengths only - no dequantisation, no transform.  The reference has no counterpart short of decoding the
+ * file (tools/ulcDecodeTool.c:153-164 learns each block's size from ULC_DecodeBlock's return value).  HOST pointers, synchronous;
+ * any block size and channel count the context supports.
+ *   blockBytes    [nStreams][blockBytesStride] out: bytes of each block; 0 from the first block that cannot be located
+ *                 (corrupt or truncated stream) on
+ *   status        [nStreams] out, nullable: -1 = every block located, else the index of the first that was not */
+int ULCB_IndexStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, const uint64_t *streamOffs, const uint32_t *nBlocks,
+                      uint32_t nBlocksAll, uint32_t *blockBytes, uint64_t blockBytesStride, int32_t *status);
+
 /* ---- batched encode ---- */
 enum { ULCB_MODE_VBR = 0, ULCB_MODE_CBR = 1, ULCB_MODE_ABR = 2,
        /* ABR whose AvgComplexity the library measures itself, per stream, in a first analysis pass on the device (window

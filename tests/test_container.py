@@ -124,3 +124,59 @@ def test_gpu_decodes_a_batch_of_ulc_files_and_indexes_them():
         assert status[i] == -1
         assert np.abs(pcm[i, :nb * 2048].astype(np.int32) - ref.astype(np.int32)).max() <= 1
         assert np.array_equal(container.block_index(bits[i, :nb]), offs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block_size,n_chan,seed", [(2048, 2, 3), (256, 1, 4), (1024, 2, 5), (8192, 2, 6), (512, 3, 7), (4096, 1, 8)])
+def test_index_prepass_grammar_vectors(block_size, n_chan, seed):
+    """ULCB_IndexStreams (the token-length walk alone) against the oracle decoder's bit counts on the hand-built grammar vectors: every
+    block size, 1-3 channels, every token and layout; then with damaged and truncated streams (first unlocatable block = the oracle's)."""
+    from oracle import oracle
+    from tests import grammar
+    from ulc_codec_b200 import capi
+    nb = 24
+    st, sz = grammar.streams(48, nb, block_size, n_chan, seed=seed)
+    with capi.Context(44100, n_chan, block_size, max_blocks=nb) as ctx:
+        bb, status = ctx.index_streams(st, nb)
+        assert (status == -1).all()
+        for i in range(len(st)):
+            assert np.array_equal(bb[i], sz[i]), i
+        # damage: overshooting runs, truncation
+        rng = np.random.default_rng(seed)
+        bad = []
+        for i, s in enumerate(st):
+            s = s.copy()
+            if i % 3 == 0:
+                s = s[:int(rng.integers(1, len(s)))]
+            elif i % 3 == 1:
+                a = int(rng.integers(0, len(s) - 8)); s[a:a + 8] = 0xF8          # 8h,Fh,... noise runs that overshoot their sub-block sooner or later
+            else:
+                s[int(rng.integers(0, len(s)))] ^= 0x5A
+            bad.append(s)
+        bb, status = ctx.index_streams(bad, nb)
+    for i, s in enumerate(bad):
+        _, bits = oracle.Decoder(n_chan, block_size).decode_stream(np.concatenate([s, np.zeros(64, np.uint8)]), nb)
+        want = (bits.astype(np.int64) + 7) // 8
+        ends = np.cumsum(want)
+        good = int(np.flatnonzero(bits == 0)[0]) if (bits == 0).any() else nb
+        good = min(good, int((ends[:good] <= len(s)).sum()))                     # blocks that lie wholly inside a truncated stream
+        got_good = nb if status[i] < 0 else int(status[i])
+        assert got_good == good, (i, got_good, good)
+        assert np.array_equal(bb[i, :good], want[:good]), i
+        assert not bb[i, good:].any(), i
+
+
+@pytest.mark.gpu
+def test_index_prepass_on_ulc_files():
+    """container.index_batch: golden .ulc files of one shape get their block offsets without being decoded."""
+    from ulc_codec_b200 import capi
+    files = []
+    for name in ("music_cbr128_bs2048", "transient_vbr50_bs2048", "music_vbr75_bs2048"):
+        g = load_golden_stream(name)
+        files.append(container.parse(container.build(2048, 44100, 2, g["data"], g["block_bytes"])))
+    with capi.Context(44100, 2, 2048, max_blocks=max(f.header.n_blocks for f in files)) as ctx:
+        status = container.index_batch(ctx, files)
+    assert (status == -1).all()
+    for f, name in zip(files, ("music_cbr128_bs2048", "transient_vbr50_bs2048", "music_vbr75_bs2048")):
+        g = load_golden_stream(name)
+        assert np.array_equal(np.diff(f.offsets), g["block_bytes"].astype(np.int64))

@@ -23,7 +23,7 @@ EXPORTS = (
     "ULC_DecoderState_Init", "ULC_DecoderState_Destroy", "ULC_DecodeBlock",
     "ULCB_ContextCreate", "ULCB_ContextDestroy", "ULCB_LastCudaError", "ULCB_ErrorString",
     "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_DecodeStreamsIndexedDevice",
-    "ULCB_DecodeStreamsIndexed", "ULCB_Sync", "ULCB_Stream",
+    "ULCB_DecodeStreamsIndexed", "ULCB_IndexStreams", "ULCB_Sync", "ULCB_Stream",
     "ULCB_LaunchCount", "ULCB_SetKernelTiming", "ULCB_KernelTimes", "ULCB_TestDCT4", "ULCB_TestParse",
     "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
     "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
@@ -85,6 +85,7 @@ def load():
     L.ULCB_DecodeStreams.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, i32, vp, vp, u64]
     L.ULCB_DecodeStreamsIndexedDevice.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, vp, u64, i32, vp, vp, u64]
     L.ULCB_DecodeStreamsIndexed.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, vp, u64, i32, vp, vp, u64]
+    L.ULCB_IndexStreams.argtypes = [vp, i32, vp, vp, vp, u32, vp, u64, vp]
     L.ULCB_Sync.argtypes = [vp]
     L.ULCB_Stream.argtypes = [vp]
     L.ULCB_Stream.restype = vp
@@ -218,6 +219,23 @@ class Context:
                 idx.ctypes.data, idx.shape[1], *common)
             _check(self.L, self.h, rc, "ULCB_DecodeStreamsIndexed")
         return out, status, bits
+
+    def index_streams(self, streams, n_blocks):
+        """Block sizes of foreign streams (ULCB_IndexStreams: token-length walk only).  Returns (block_bytes uint32[nStreams, maxBlocks],
+        status int32[nStreams]); a row is zero from the first block that could not be located."""
+        data, offs = pack_streams(streams)
+        ns = len(streams)
+        if np.isscalar(n_blocks):
+            nb_arr, nb_all, max_blk = None, int(n_blocks), int(n_blocks)
+        else:
+            nb_arr = np.ascontiguousarray(n_blocks, np.uint32)
+            nb_all, max_blk = 0, int(nb_arr.max()) if ns else 0
+        bb = np.zeros((ns, max(1, max_blk)), np.uint32)
+        status = np.zeros(ns, np.int32)
+        rc = self.L.ULCB_IndexStreams(self.h, ns, data.ctypes.data, offs.ctypes.data, nb_arr.ctypes.data if nb_arr is not None else None, nb_all,
+                                      bb.ctypes.data, bb.shape[1], status.ctypes.data)
+        _check(self.L, self.h, rc, "ULCB_IndexStreams")
+        return bb, status
 
     # ---- device-pointer batched decode (ULCB_DecodeStreamsDevice); pointers are plain ints ----
     def decode_streams_device(self, n_streams: int, d_bytes: int, d_offs: int, n_blocks_all: int, d_out: int,

@@ -136,3 +136,18 @@ def pack_batch(files: Iterable[UlcFile]):
     offs[1:] = np.cumsum([len(f.payload) for f in files])
     data = np.concatenate([f.payload for f in files]) if offs[-1] else np.zeros(0, np.uint8)
     return data, offs, np.array([f.header.n_blocks for f in files], dtype=np.uint32)
+
+
+def index_batch(ctx, files: Iterable[UlcFile]) -> np.ndarray:
+    """The light pre-pass for foreign files: block sizes of every file of a batch from `ULCB_IndexStreams` (the
+    token-length walk alone, no decode), stored as `offsets` on each file.  Returns status int32[n]: -1 = every block located, else
+    the index of the first block that was not (the reference tool stops there with "Corrupted stream", tools/ulcDecodeTool.c:153-157).
+    The sizes feed `ULCB_DecodeStreamsIndexed` and random access into the stream."""
+    files = list(files)
+    data, offs, nblk = pack_batch(files)
+    streams = [data[int(offs[i]):int(offs[i + 1])] for i in range(len(files))]
+    bb, status = ctx.index_streams(streams, nblk)
+    for f, row, st in zip(files, bb, status):
+        n = f.header.n_blocks if st < 0 else int(st)
+        f.offsets = np.concatenate([[0], np.cumsum(row[:n].astype(np.int64))]).astype(np.int64)
+    return status

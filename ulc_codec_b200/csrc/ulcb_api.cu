@@ -448,7 +448,7 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
     const size_t cap = ctx->bpPlanCap;
     static const int runLen = getenv("ULCB_BP_RUNLEN") ? atoi(getenv("ULCB_BP_RUNLEN")) : 64;
     UlcbBpArgs a{};
-    a.tb = ctx->tb; a.nSignBits = ctx->tb.nSignBits;
+    a.tb = ctx->tb; a.nSignBits = ctx->tb.nSignBits; a.nChan = ctx->nChan;
     a.nBlocksAll = (int)nBlocksAll; a.maxBlk = (int)maxBlk; a.runLen = runLen < 1 ? 1 : runLen;
     a.bytes = dBytes; a.streamOffs = dStreamOffs; a.nBlocks = dNBlocks;
     a.wend = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(dBytes) + hOffs[nStreams] + 8) & ~(uintptr_t)3);
@@ -607,6 +607,57 @@ int ULCB_DecodeStreamsIndexed(ULCB_Context *ctx, int nStreams, const uint8_t *by
     if (!blockBytes) return ULCB_E_PARAM;
     return decode_host(ctx, nStreams, bytes, streamOffs, nBlocks, nBlocksAll, blockBytes, blockBytesStride, out, outStrideElems, format,
                        status, blockBits, bitsStride);
+}
+
+// The block index a .ulc file lacks: the token-length walk alone (no parse, no transform), any block size and channel count.
+static int index_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs, const uint64_t *hOffs,
+                        const uint32_t *dNBlocks, uint32_t maxBlk, uint32_t nBlocksAll, uint32_t *dBlockBytes, uint64_t stride, int32_t *dStatus) {
+    int rc;
+    if ((rc = grow(ctx, &ctx->bpOff, &ctx->bpOffCap, sizeof(uint32_t) * (size_t)nStreams * (maxBlk + 1)))) return rc;
+    UlcbBpArgs a{};
+    a.tb = ctx->tb; a.nChan = ctx->nChan;
+    a.nBlocksAll = (int)nBlocksAll; a.maxBlk = (int)maxBlk; a.runLen = 1;
+    a.bytes = dBytes; a.streamOffs = dStreamOffs; a.nBlocks = dNBlocks;
+    a.wend = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(dBytes) + hOffs[nStreams] + 8) & ~(uintptr_t)3);
+    a.s0 = 0; a.nStreams = nStreams; a.base0 = hOffs[0]; a.blkOff = (uint32_t *)ctx->bpOff;
+    int nl = 0;
+    CK(ctx, ulcb_decode_bp_offsets(a, false, ctx->smCount, ctx->stream, &nl));
+    CK(ctx, ulcb_decode_bp_sizes(a, dBlockBytes, stride, dStatus, ctx->stream));
+    ctx->launches += (uint64_t)nl + 1;
+    return ULCB_OK;
+}
+
+int ULCB_IndexStreams(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, const uint64_t *streamOffs, const uint32_t *nBlocks,
+                      uint32_t nBlocksAll, uint32_t *blockBytes, uint64_t blockBytesStride, int32_t *status) {
+    if (!ctx || nStreams < 0 || !bytes || !streamOffs || !blockBytes) return ULCB_E_PARAM;
+    if (nStreams == 0) return ULCB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint32_t maxBlk = nBlocksAll;
+    if (nBlocks) { maxBlk = 0; for (int s = 0; s < nStreams; s++) if (nBlocks[s] > maxBlk) maxBlk = nBlocks[s]; }
+    if (maxBlk == 0) return ULCB_OK;
+    if (blockBytesStride < maxBlk) return ULCB_E_PARAM;
+    for (int s = 0; s < nStreams; s++) if (streamOffs[s + 1] < streamOffs[s]) return ULCB_E_PARAM;
+    const size_t nBytes = streamOffs[nStreams];
+    const size_t offOffs = 0, offNb = offOffs + sizeof(uint64_t) * (nStreams + 1), offSt = offNb + sizeof(uint32_t) * nStreams;
+    const size_t offIdx = (offSt + sizeof(int32_t) * nStreams + 15) & ~(size_t)15;
+    const size_t auxBytes = offIdx + sizeof(uint32_t) * (size_t)nStreams * blockBytesStride;
+    int rc;
+    if ((rc = grow(ctx, &ctx->dIn, &ctx->dInCap, nBytes + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->dAux, &ctx->dAuxCap, auxBytes))) return rc;
+    char *aux = (char *)ctx->dAux;
+    CK(ctx, cudaMemcpyAsync(ctx->dIn, bytes, nBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemsetAsync((char *)ctx->dIn + nBytes, 0, 64, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(aux + offOffs, streamOffs, sizeof(uint64_t) * (nStreams + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nBlocks) CK(ctx, cudaMemcpyAsync(aux + offNb, nBlocks, sizeof(uint32_t) * nStreams, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemsetAsync(aux + offIdx, 0, sizeof(uint32_t) * (size_t)nStreams * blockBytesStride, ctx->stream));
+    rc = index_device(ctx, nStreams, (const uint8_t *)ctx->dIn, (const uint64_t *)(aux + offOffs), streamOffs,
+                      nBlocks ? (const uint32_t *)(aux + offNb) : nullptr, maxBlk, nBlocksAll, (uint32_t *)(aux + offIdx), blockBytesStride,
+                      (int32_t *)(aux + offSt));
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(blockBytes, aux + offIdx, sizeof(uint32_t) * (size_t)nStreams * blockBytesStride, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(ctx, cudaMemcpyAsync(status, aux + offSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ULCB_OK;
 }
 
 int ULCB_SetKernelTiming(ULCB_Context *ctx, int enable) {

@@ -52,6 +52,7 @@ struct UlcbBpDesc {                   // one per block, written by the parse ker
 struct UlcbBpArgs {
     UlcbTables      tb;
     uint64_t        nSignBits;
+    int             nChan;            // channels (the walk takes any count; parse and transform are built for stereo)
     int             s0, nStreams;     // this wave: streams [s0, s0 + nStreams) of the call
     int             nBlocksAll, maxBlk, runLen;
     const uint8_t  *bytes;            // all streams of the call
@@ -74,5 +75,7 @@ struct UlcbBpArgs {
 bool        ulcb_decode_bp_supported(const UlcbTables &tb, int nChan);
 size_t      ulcb_decode_bp_arena_bytes(uint64_t payloadBytes, int nStreams, int maxBlk);
 cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &args, bool haveIndex, int smCount, cudaStream_t stream, int *launches);
+// block sizes from the offsets table: sizes[stream][block] = bytes of the block, 0 from the first block that could not be located
+cudaError_t ulcb_decode_bp_sizes(const UlcbBpArgs &args, uint32_t *dSizes, uint64_t sizesStride, int32_t *dStatus, cudaStream_t stream);
 // ev (nullable): four events recorded before parse, after parse, after scan and after transform
 cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, cudaStream_t stream, int *launches, cudaEvent_t *ev = nullptr);

@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(512, 1) bp_walk_kernel(UlcbBpArgs a, int lanes
     } while (0)
 
     // start as if a block had just ended: the first trip takes the boundary path, which opens block 0
-    int b = -1, c = NCH - 1, pos = 0, subEnd = 0;
+    const int WN = a.tb.N, WCH = a.nChan;                    // the walk is not tied to the pipeline's block size and channel count
+    int b = -1, c = WCH - 1, pos = 0, subEnd = 0;
     uint32_t pat = 0, layout = 0, st = 0;                   // st = 4 * state
     bool dead = false;
     const char *tabB = reinterpret_cast<const char *>(wtab);
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(512, 1) bp_walk_kernel(UlcbBpArgs a, int lanes
                 for (;;) {
                     pat >>= 4;
                     if (!pat) {
-                        if (++c == NCH) {
+                        if (++c == WCH) {
                             // block end: it ends inside its last byte (ulcEncoder_Encode.c:357-358); next block's window control
                             if (nyb & 1u) WK_SKIP(1);
                             if (nyb > endNyb) { dead = true; fin = true; break; }
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(512, 1) bp_walk_kernel(UlcbBpArgs a, int lanes
                         }
                         pat = layout; pos = 0;
                     }
-                    subEnd = pos + (N >> (pat & 7));
+                    subEnd = pos + (WN >> (pat & 7));
                     const uint32_t hx = __funnelshift_r(w0, w1, sh);               // sub-block header: a bare quantiser (ulcDecoder.c:103-112)
                     if ((hx & 15u) == 14u) {
                         WK_SKIP(2);
@@ -699,19 +700,16 @@ __device__ __forceinline__ int issue_words(WarpSm &w, unsigned long long *mb, co
 // parity[g+i+1] ^ parity[g].  The runs of a channel (a few dozen, 16..527 coefficients each, ~25 typical) are cut into items
 // of 16 coefficient words; the warp works through the flat item list eight items at a time, four lanes per item, four
 // words per lane, so that long and short runs cost the same per coefficient.  The item list lives in the (idle) TMA slot.
-// LONGBLK: coefficient word n lives in the .x of tile slot [n / 32][n % 32]; otherwise in the dense bf16 array.
+// `dense` = the block's bf16 coefficient array as 32-bit words (two coefficients per word): at the start of the tile for a long block
+// (read back column-wise by the pre-twiddle, conflict-free), behind the sub-block scratch for a window-switched one.
 struct RunRec { int s, e; uint32_t g0, amp2, flip, pad; };
 constexpr int MAXITEMS = 2 * (RECSLOT - 32 * 6) ;   // u16 items behind 32 run records
 
-template <bool LONGBLK>
-__device__ __noinline__ void noise_fill(WarpSm &w, const BlkInfo &bi, const uint32_t *__restrict__ par, int lane) {
+__device__ __noinline__ void noise_fill(WarpSm &w, uint32_t *dense, const BlkInfo &bi, const uint32_t *__restrict__ par, int lane) {
     const int grp = lane >> 2, j = lane & 3;
-    uint32_t *dense = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(w.zb) + COEF16_OFS);
     RunRec *rt = reinterpret_cast<RunRec *>(w.rec);
     uint16_t *items = reinterpret_cast<uint16_t *>(w.rec + 32 * 6);
-    auto word = [&](int n) -> uint32_t * {
-        return LONGBLK ? reinterpret_cast<uint32_t *>(&w.zb[(n >> 5) * ZROW + (n & 31)].x) : dense + n;
-    };
+    auto word = [&](int n) -> uint32_t * { return dense + n; };
     for (int r0 = 0; r0 < bi.nRuns; r0 += 32) {
         // ---- one run per lane: record, item count, item list ----
         const int r = r0 + lane;
@@ -804,12 +802,17 @@ template <bool DBG>
 __device__ __noinline__ void expand_rare(WarpSm &w, int nT, float *dbg, int lane) {
     float2 *zb = w.zb;
     {
+        // the words sit densely at the start of the tile they are expanded into: all of them into registers first
+        uint32_t wds[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) wds[j] = reinterpret_cast<const uint32_t *>(w.zb)[lane + 32 * j];
+        __syncwarp();
         TailChain tc;
         if (nT) tc.open(w.tail[0]); else tc.none();
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 32; j++) {
             const int n = lane + 32 * j;
-            const uint32_t wa = __float_as_uint(zb[j * ZROW + lane].x);
+            const uint32_t wa = wds[j];
             float ev = __uint_as_float(wa << 16), od = __uint_as_float(wa & 0xffff0000u);
             if (nT) { ev *= tc.gain(2 * n); od *= tc.gain(2 * n + 1); }
             if (DBG) reinterpret_cast<float2 *>(dbg)[n] = make_float2(ev, od);
@@ -947,12 +950,13 @@ bp_transform_kernel(UlcbBpArgs a) {
         const bool longBlk = (wc >> 4) <= 1;
         float *dbg = DBG ? a.dbgCoefs + (((size_t)gs * a.nBlocksAll + blk) * 2 + c) * N : nullptr;
 
-        // ---- clear the coefficient words, then scatter this channel's words into them ----
+        // ---- clear the coefficient words (bf16, 4 KB: at the start of the tile for a long block, behind the sub-block scratch for a
+        //      window-switched one), then scatter this channel's words into them ----
+        uint16_t *cdst = longBlk ? reinterpret_cast<uint16_t *>(w.zb) : coef16;
         {
-            uint4 *z = reinterpret_cast<uint4 *>(w.zb);
+            uint4 *z = reinterpret_cast<uint4 *>(cdst);
 #pragma unroll 4
-            for (int i = 0; i < (32 * ZROW * 8) / 16 / 32; i++) z[lane + 32 * i] = make_uint4(0, 0, 0, 0);
-            if (lane < ((32 * ZROW * 8) / 16) % 32) z[lane + 32 * ((32 * ZROW * 8) / 16 / 32)] = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < (N * 2) / 16 / 32; i++) z[lane + 32 * i] = make_uint4(0, 0, 0, 0);
             if (lane == 0) w.nTails = 0;
         }
         __syncwarp();
@@ -962,19 +966,14 @@ bp_transform_kernel(UlcbBpArgs a) {
 #pragma unroll 4
             for (int i = lane; i < inflight; i += 32) {
                 const uint32_t rw = w.rec[skew + i];
-                const int pos = (int)(rw >> 16);
-                uint16_t *dst = longBlk
-                    ? reinterpret_cast<uint16_t *>(&zb[(pos >> 6) * ZROW + ((pos >> 1) & 31)].x) + (pos & 1)
-                    : coef16 + pos;
-                *dst = (uint16_t)rw;
+                cdst[rw >> 16] = (uint16_t)rw;
             }
             __syncwarp();
             done += inflight; inflight = 0;
         }
         // noise runs (the landing slot holds their work list), then - long block - start the next block's copy behind this
         // block's transform; a window-switched block keeps the slot for its time-ordered pending tail until it is done
-        if (longBlk) noise_fill<true>(w, cur, par, lane);
-        else         noise_fill<false>(w, cur, par, lane);
+        noise_fill(w, reinterpret_cast<uint32_t *>(cdst), cur, par, lane);
         const int nT = min(w.nTails, 8);
         const bool haveNext = blk + 1 < bLast && blk + 1 < firstBad;
         BlkInfo nxt{};
@@ -989,10 +988,10 @@ bp_transform_kernel(UlcbBpArgs a) {
                 // z[n] = (v[2n] + i v[N-1-2n]) E[n], n = lane + 32 j: v[2n] is the even half of word n (own column of the tile),
                 // v[N-1-2n] the odd half of word 1023-n = column 31-lane, row 31-j.  Straight into the registers of pass 0.
                 // The lane-dependent factor E[lane] of the twiddle moves behind pass 0 (it is common to the whole column).
-                const float *own = &zb[lane].x, *mir = &zb[31 * ZROW + 31 - lane].x;
+                const uint32_t *own = reinterpret_cast<const uint32_t *>(w.zb) + lane, *mir = reinterpret_cast<const uint32_t *>(w.zb) + 1023 - lane;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const uint32_t wa = __float_as_uint(own[j * ZROW * 2]), wm = __float_as_uint(mir[-j * ZROW * 2]);
+                    const uint32_t wa = own[32 * j], wm = mir[-32 * j];
                     const float ev = __uint_as_float(wa << 16), od = __uint_as_float(wm & 0xffff0000u);
                     xr[j] = ev * rotC(j) + od * rotS(j); xi[j] = od * rotC(j) - ev * rotS(j);
                 }
@@ -1230,6 +1229,31 @@ cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &a, bool haveIndex, int smCo
         bp_walk_kernel<<<(unsigned)((warpsTotal + warps - 1) / warps), 32 * warps, smem, stream>>>(a, lanes);
     }
     if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// Block sizes of every stream of the call from the offsets table (the index a .ulc file lacks: ULCB_IndexStreams).
+namespace {
+__global__ void bp_sizes_kernel(UlcbBpArgs a, uint32_t *sizes, uint64_t sizesStride, int32_t *status) {
+    const int s = blockIdx.x, gs = a.s0 + s;
+    const int nb = a.nBlocks ? (int)a.nBlocks[gs] : a.nBlocksAll;
+    const uint32_t *off = a.blkOff + (size_t)s * (a.maxBlk + 1);
+    __shared__ int firstBad;
+    if (threadIdx.x == 0) firstBad = nb;
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        const uint32_t len = off[b + 1] - off[b];
+        sizes[(size_t)gs * sizesStride + b] = len;
+        if (len == 0) atomicMin(&firstBad, b);                     // a located block is never empty (window control + headers)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && status) status[gs] = firstBad < nb ? firstBad : -1;
+}
+}  // namespace
+
+cudaError_t ulcb_decode_bp_sizes(const UlcbBpArgs &a, uint32_t *dSizes, uint64_t sizesStride, int32_t *dStatus, cudaStream_t stream) {
+    if (a.nStreams <= 0 || a.maxBlk <= 0) return cudaSuccess;
+    bp_sizes_kernel<<<a.nStreams, 128, 0, stream>>>(a, dSizes, sizesStride, dStatus);
     return cudaGetLastError();
 }
 
