@@ -722,7 +722,9 @@ def main():
     # ---- secondary measurement: batched VBR encode (configs[2]); the headline stays the decode line above ----
     enc = None
     del batch.d_bytes, d_out
+    ctx.close()                                                      # gives the decode scratch (sparse-content arena) back
     torch.cuda.empty_cache()
+    ctx = capi.Context(RATE, NCH, N, max_blocks=BLOCKS_PER_STREAM, device=local)
     if args.enc_streams > 0:
         enc = bench_encode(ctx, capi, torch, dist, dev, rank, world, args.enc_streams, max(1, args.steps // 2), 1, peaks,
                            with_cpu=(rank == 0 and world == 1 and not args.no_cpu))

@@ -436,7 +436,7 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
     for (int s = 0; s < nStreams; s++) if (hOffs[s + 1] < hOffs[s]) return ULCB_E_PARAM;
 
     // waves: as many streams as the arena cap holds
-    static const size_t capEnv = getenv("ULCB_BP_ARENA_MB") ? (size_t)atoll(getenv("ULCB_BP_ARENA_MB")) << 20 : (size_t)8192 << 20;
+    static const size_t capEnv = getenv("ULCB_BP_ARENA_MB") ? (size_t)atoll(getenv("ULCB_BP_ARENA_MB")) << 20 : (size_t)32768 << 20;
     // waves never plan for more than half of what was free when the context first decoded (asked once: cudaMemGetInfo is a slow,
     // serialising driver call, and a step that starts with a tiny kernel has nothing queued to hide it behind - it showed as
     // 50 ms gaps in some steps)
