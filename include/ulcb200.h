@@ -264,7 +264,9 @@ uint64_t ULCB_LaunchCount(const ULCB_Context *ctx);
 #define ULCB_KERNEL_BP_PARSE      2
 #define ULCB_KERNEL_BP_SCAN       3
 #define ULCB_KERNEL_BP_TRANSFORM  4
-#define ULCB_KERNEL_KINDS         5
+#define ULCB_KERNEL_ENC_DETECT    5   /* encoder: transient-detector pre-pass */
+#define ULCB_KERNEL_ENC_ENCODE    6   /* encoder: the encode kernel (each pass of a two-pass ABR call) */
+#define ULCB_KERNEL_KINDS         7
 int ULCB_SetKernelTiming(ULCB_Context *ctx, int enable);
 int ULCB_KernelTimes(ULCB_Context *ctx, double *ms, uint64_t *count, int reset);
 

@@ -4,6 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ulc_codec_b200 import capi, corpus
+if os.environ.get("ULCB_LIB"): capi.LIB_PATH = os.path.abspath(os.environ["ULCB_LIB"])      # experiment builds (scripts/build_variant.sh)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--streams", type=int, default=296)
@@ -36,6 +37,7 @@ with capi.Context(44100, C, N) as ctx:
                                   avg_complexity=0.8, d_nsamples=nsamp.data_ptr(), d_block_bytes=bb.data_ptr(), meta_stride=nb, d_status=st.data_ptr())
     torch.cuda.synchronize()
     step(); ctx.sync()
+    ctx.set_kernel_timing(True)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     for _ in range(a.reps): step()
@@ -46,6 +48,8 @@ with capi.Context(44100, C, N) as ctx:
     print(f"encode {a.mode} {a.rate} N={N} streams={a.streams} blocks/stream={nb}: {ms:.1f} ms/launch, {audio / (ms / 1e3):.0f} x realtime, "
           f"{ms * 1e3 / (nb * a.streams) * min(a.streams, 148):.1f} us per block per SM-slot, avg {byts / (a.streams * nb):.1f} B/block, status bad {int((st != 0).sum())}")
 
+    kt = ctx.kernel_times()
+    print("per launch: " + ", ".join(f"{k} {v[0] / max(1, a.reps):.2f} ms" for k, v in kt.items() if v[1]))
     import ctypes as C
     if hasattr(ctx.L, "ULCB_DebugPhaseTimes"):
         buf = (C.c_ulonglong * 32)()

@@ -175,7 +175,7 @@ class Context:
     def sync(self):
         _check(self.L, self.h, self.L.ULCB_Sync(self.h), "ULCB_Sync")
 
-    KERNEL_KINDS = ("bp_walk", "bp_index", "bp_parse", "bp_scan", "bp_transform")
+    KERNEL_KINDS = ("bp_walk", "bp_index", "bp_parse", "bp_scan", "bp_transform", "enc_detect", "enc_encode")
 
     def set_kernel_timing(self, enable: bool = True):
         _check(self.L, self.h, self.L.ULCB_SetKernelTiming(self.h, int(enable)), "ULCB_SetKernelTiming")

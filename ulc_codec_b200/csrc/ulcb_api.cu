@@ -19,6 +19,11 @@
 cudaError_t ulcb_corpus_launch(int16_t *dOut, uint64_t strideElems, int kind, uint32_t firstId, int nStreams, uint64_t nSamples,
                                uint64_t t0, const int16_t *dSine, const int16_t *dBurst, cudaStream_t stream);
 
+// kinds whose spans own both of their events (the decode pipeline's parse / scan / transform spans share a chain of events)
+static inline bool own_end_event(int kind) {
+    return kind == ULCB_KERNEL_BP_WALK || kind == ULCB_KERNEL_BP_INDEX || kind == ULCB_KERNEL_ENC_DETECT || kind == ULCB_KERNEL_ENC_ENCODE;
+}
+
 struct ULCB_Context {
     int device = 0, rateHz = 0, nChan = 0, N = 0;
     uint32_t maxBlocks = 0;
@@ -30,6 +35,8 @@ struct ULCB_Context {
     int smCount = 148;
     int16_t *corpusLut = nullptr;       // sine[1024] + burst[882]
     float *dAvgCx = nullptr; int avgCap = 0, avgCount = 0;              // two-pass ABR: per-stream AvgComplexity
+    void *detScratch = nullptr; size_t detScratchCap = 0;              // detector pre-pass: per-CTA envelope buffers ...
+    int32_t *dWcAll = nullptr; size_t wcAllCap = 0;                     // ... and its decisions [stream][nBlocksAll]
     float *dCxScratch = nullptr; size_t cxScratchCap = 0;               // ... and the first pass's block complexities when the caller keeps none
     float *encWs = nullptr; size_t encWsFloats = 0; int encGrid = 0;   // global workspace for large block sizes
     std::vector<void *> owned;          // device allocations freed with the context
@@ -392,7 +399,9 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->corpusLut) cudaFree(ctx->corpusLut);
     if (ctx->dAvgCx) cudaFree(ctx->dAvgCx);
     if (ctx->dCxScratch) cudaFree(ctx->dCxScratch);
-    for (auto &sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.kind == ULCB_KERNEL_BP_WALK || sp.kind == ULCB_KERNEL_BP_INDEX) cudaEventDestroy(sp.b); }
+    if (ctx->detScratch) cudaFree(ctx->detScratch);
+    if (ctx->dWcAll) cudaFree(ctx->dWcAll);
+    for (auto &sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (own_end_event(sp.kind)) cudaEventDestroy(sp.b); }
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
     delete ctx;
 }
@@ -679,7 +688,7 @@ int ULCB_KernelTimes(ULCB_Context *ctx, double *ms, uint64_t *count, int reset) 
     }
     // every event opens exactly one span entry (the last of a chain opens an entry without an end): back to the pool
     for (auto &sp : ctx->spans) ctx->evPool.push_back(sp.a);
-    for (auto &sp : ctx->spans) if (sp.kind == ULCB_KERNEL_BP_WALK || sp.kind == ULCB_KERNEL_BP_INDEX) ctx->evPool.push_back(sp.b);
+    for (auto &sp : ctx->spans) if (own_end_event(sp.kind)) ctx->evPool.push_back(sp.b);
     ctx->spans.clear();
     for (int k = 0; k < ULCB_KERNEL_KINDS; k++) {
         if (ms) ms[k] = ctx->kernMs[k];
@@ -898,6 +907,30 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
         }
         a.workspace = ctx->encWs; a.wsFloats = per;
     }
+    // Whole streams from their start (no carried state), every stream nBlocksAll blocks, stereo / mono at a shared-memory
+    // block size: the transient detector runs as a pre-pass over all streams and the encode kernel takes its decisions
+    // (ULCB_ENC_PRE=0 keeps the detector inside the encode kernel, as calls with carried state do).
+    static const bool preOff = getenv("ULCB_ENC_PRE") && atoi(getenv("ULCB_ENC_PRE")) == 0;
+    if (!preOff && !state && !dNBlocks && nBlocksAll > 0 && !a.workspace && ulcb_detect_supported(ctx->N, ctx->nChan)) {
+        const size_t needScr = ulcb_detect_scratch_bytes(ctx->N, nStreams), needWc = (size_t)nStreams * nBlocksAll;
+        if (ctx->detScratchCap < needScr) {
+            if (ctx->detScratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->detScratch); ctx->detScratch = nullptr; ctx->detScratchCap = 0; }
+            CK(ctx, cudaMalloc(&ctx->detScratch, needScr));
+            ctx->detScratchCap = needScr;
+        }
+        if (ctx->wcAllCap < needWc) {
+            if (ctx->dWcAll) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->dWcAll); ctx->dWcAll = nullptr; ctx->wcAllCap = 0; }
+            CK(ctx, cudaMalloc(&ctx->dWcAll, sizeof(int32_t) * needWc));
+            ctx->wcAllCap = needWc;
+        }
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (ctx->timing) { t0 = timing_event(ctx); t1 = timing_event(ctx); cudaEventRecord(t0, ctx->stream); }
+        CK(ctx, ulcb_detect_launch(a, ctx->nChan, ctx->detScratch, ctx->dWcAll, nBlocksAll, ctx->stream));
+        if (ctx->timing) { cudaEventRecord(t1, ctx->stream); ctx->spans.push_back({t0, t1, ULCB_KERNEL_ENC_DETECT}); }
+        ctx->launches++;
+        a.wcAll = ctx->dWcAll; a.wcStride = nBlocksAll;
+        if (getenv("ULCB_ENC_THREADS")) a.encThreads = atoi(getenv("ULCB_ENC_THREADS"));
+    }
     if (prm->mode == ULCB_MODE_ABR_2PASS) {
         // pass 1: analysis only -> block complexities; mean per stream on the device; pass 2: ABR with the per-stream means
         if (ctx->avgCap < nStreams) {
@@ -918,12 +951,18 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
         UlcbEncodeArgs p1 = a;
         p1.mode = ULCB_ENC_ANALYSE; p1.complexity = cxBuf; p1.metaStride = cxStride;
         p1.blockBytes = nullptr; p1.windowCtrl = nullptr; p1.totalBytes = nullptr; p1.status = nullptr;
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (ctx->timing) { t0 = timing_event(ctx); t1 = timing_event(ctx); cudaEventRecord(t0, ctx->stream); }
         CK(ctx, ulcb_encode_launch(p1, ctx->nChan, grid, ctx->stream));
+        if (ctx->timing) { cudaEventRecord(t1, ctx->stream); ctx->spans.push_back({t0, t1, ULCB_KERNEL_ENC_ENCODE}); }
         CK(ctx, ulcb_avg_complexity_launch(cxBuf, cxStride, dNBlocks, nBlocksAll, nStreams, ctx->dAvgCx, ctx->stream));
         ctx->launches += 2; ctx->avgCount = nStreams;
         a.mode = ULCB_ENC_ABR; a.avgPerStream = ctx->dAvgCx;
     }
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->timing) { t0 = timing_event(ctx); t1 = timing_event(ctx); cudaEventRecord(t0, ctx->stream); }
     CK(ctx, ulcb_encode_launch(a, ctx->nChan, grid, ctx->stream));
+    if (ctx->timing) { cudaEventRecord(t1, ctx->stream); ctx->spans.push_back({t0, t1, ULCB_KERNEL_ENC_ENCODE}); }
     ctx->launches++;
     return ULCB_OK;
 }

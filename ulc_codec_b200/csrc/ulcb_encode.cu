@@ -75,9 +75,9 @@ struct EncSmallT {
     int     selBin, selBelow;        // radix-select hand-off
     int     scan[40];
     float   band[MAXBU][ULCB_NBARK];
-    double  lo[MAXBU][ULCB_NBARK][3];
-    double  stage[MAXBU][3][32];
 };
+// f64 scratch of the Bark analysis per unit: lo[MAXBU][NBARK][3] then stage[MAXBU][3][32]
+__host__ __device__ constexpr size_t band_scratch_bytes(int maxbu) { return sizeof(double) * (size_t)maxbu * (ULCB_NBARK * 3 + 3 * 32); }
 
 // ---- small exact helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float logf_ref(float x) { return (float)log((double)x); }   // libm logf to the last ulp (nearly always)
@@ -153,6 +153,7 @@ __device__ __forceinline__ bool node_is_dct4(int d, int node) {   // root = DCT-
 // reconverged explicitly first - single-lane serial sections precede several of these barriers.)
 template <int NTHR> __device__ __forceinline__ void wsync() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory"); }
 template <int NTHR> __device__ __forceinline__ void fsync() { __syncwarp(); asm volatile("bar.sync 0, %0;" ::"n"(NTHR + 32) : "memory"); }
+template <int NTHR, bool PRE> __device__ __forceinline__ void csync() { if (PRE) wsync<NTHR>(); else fsync<NTHR>(); }
 
 // Worker-wide exclusive scans of one int per thread.  `scr` = smem int[NTHR/32 + 2].
 template <int NTHR>
@@ -208,6 +209,8 @@ struct Work {
     float *amp2, *mask;  // [N/2]
     uint16_t *cnt;       // radix counters [16][NTHR]
     uint8_t *encScratch; // 3*CN bytes for the coder (aliases cnt, which is dead after the sort; global for large blocks)
+    double (*lo)[ULCB_NBARK][3];   // Bark analysis: per-unit band sums ...
+    double (*stage)[3][32];        // ... and the 32-line staging of the three f64 chains
 };
 
 // ---- transient detector (ulcEncoder_WindowControl.c:140-239) decision on the 16 segment sums ----------
@@ -398,7 +401,9 @@ __device__ __forceinline__ void put_quant(Sink &w, int inf) {            // ulcE
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NCHT, int NTHR>            // NCHT = channels, 0 = taken from the arguments (3 .. ULCB_ENC_MAXCH)
+// PRE = the window controls come from the detector pre-pass (ulcb_detect_kernel): no detector warp, no sample ring in shared
+// memory (the fold reads the PCM input directly), scratch aliased so that two CTAs fit one SM.
+template <int NCHT, int NTHR, bool PRE = false>   // NCHT = channels, 0 = taken from the arguments (3 .. ULCB_ENC_MAXCH)
 struct Encoder {
     static constexpr int MAXCH = NCHT ? NCHT : ULCB_ENC_MAXCH;
     using EncSmall = EncSmallT<4 * MAXCH>;
@@ -417,6 +422,13 @@ struct Encoder {
     // not a power of two the last threads own nothing.
     __device__ __forceinline__ int slot_items() const { const int e = CN / NTHR; return (e & (e - 1)) ? 1 << (32 - __clz(e)) : e; }
     __device__ __forceinline__ float *blk(int k) const { return w.R + ((k + 3) % 3) * CN; }
+    // log of the noise line sums of unit (c, sub-block s): a dead sample block, or (PRE) the upper half of the unit's TB range,
+    // which the line sums themselves leave free
+    __device__ __forceinline__ float *lg_lines(int k, int c, const SubInfo &s) const {
+        return PRE ? w.TB + c * N + s.off + (s.S >> 1) : blk(k - 2) + c * H + (s.off >> 1);
+    }
+    // packed nybbles of the block being coded: a dead sample block, or (PRE) the amp2 / mask lines, dead once the keys are made
+    __device__ __forceinline__ uint32_t *out_words(int k) const { return reinterpret_cast<uint32_t *>(PRE ? w.amp2 : blk(k - 2)); }
 
     // ---------------- ingest ----------------
     __device__ void ingest(int k, const void *pcm, long long validSamples) {
@@ -477,14 +489,78 @@ struct Encoder {
     }
 
     // ---------------- fold + window (closed form of the lapping FIFO and Fourier_MDCT_Template.h:45-187) ----------------
-    __device__ __forceinline__ float lap_value(const float *R2, const float *R1, int c, int rel, int u, int ovL) const {
-        // rel = index on the 2N timeline [block k-2 | block k-1]; u = offset from the fold point
-        const int hv = ovL >> 1;
+    __device__ __forceinline__ float lap_weight(float x, int u, int hv) const {      // u = offset from the fold point, hv = overlap / 2
         if (u < -hv) return 0.0f;
-        float x = (rel < N) ? R2[c * N + rel] : R1[c * N + rel - N];
         if (u >= hv) return x;
         if (u < 0) return __ldg(&tb.rot[hv + (u + hv)]).y * x;
         return __ldg(&tb.rot[hv + (hv - 1 - u)]).x * x;
+    }
+    __device__ __forceinline__ float lap_value(const float *R2, const float *R1, int c, int rel, int u, int ovL) const {
+        // rel = index on the 2N timeline [block k-2 | block k-1]
+        const int hv = ovL >> 1;
+        if (u < -hv) return 0.0f;
+        float x = (rel < N) ? R2[c * N + rel] : R1[c * N + rel - N];
+        return lap_weight(x, u, hv);
+    }
+    // M/S sample point t of the stream straight from the PCM input (zero outside [0, nSamples)): what ingest() would have put
+    // into the sample ring (ulcEncoder_BlockTransform.c:87-111, tools/WavIO_Helper.c:49-55)
+    __device__ __forceinline__ void load_ms(const unsigned char *pcm, long long t, long long nSamples, float *v) const {
+        if (t < 0 || t >= nSamples) {
+#pragma unroll
+            for (int c = 0; c < MAXCH; c++) v[c] = 0.0f;
+            return;
+        }
+        if (NCHT == 2 && !args.pcmFloat) {
+            const uint32_t wv = __ldg(reinterpret_cast<const uint32_t *>(pcm) + t);
+            v[0] = (float)(int16_t)(wv & 0xffffu) * 0x1.0p-15f; v[1] = (float)(int16_t)(wv >> 16) * 0x1.0p-15f;
+        } else {
+#pragma unroll
+            for (int c = 0; c < MAXCH; c++)
+                if (c < nch()) v[c] = args.pcmFloat ? __ldg(reinterpret_cast<const float *>(pcm) + (size_t)t * nch() + c)
+                                                    : (float)__ldg(reinterpret_cast<const int16_t *>(pcm) + (size_t)t * nch() + c) * 0x1.0p-15f;
+        }
+#pragma unroll
+        for (int c = 1; c < MAXCH; c += 2)
+            if (c < nch()) { float a = v[c - 1], b = v[c]; v[c - 1] = (a + b) * 0.5f; v[c] = (a - b) * 0.5f; }
+    }
+    // fold + window of output block b with the two input blocks b-2, b-1 read from the PCM input (PRE): the same values and
+    // operations as fold(), one thread per line pair for every channel
+    __device__ void fold_pre(int b, const unsigned char *pcm, long long nSamples) {
+        const long long t0 = (long long)(b - 2) * N;                  // stream position of timeline index 0
+        for (int r = tid; r < H; r += NTHR) {
+            const int j = find_sub(sm, 2 * r);
+            const SubInfo s = sm.sub[j];
+            const int hS = s.S >> 1, i = r - (s.off >> 1);
+            const int hrel = H + s.off, hv = s.ovL >> 1;
+            float xa[MAXCH], xb[MAXCH], xc[MAXCH], xd[MAXCH];
+            if (i - hS >= -hv) load_ms(pcm, t0 + hrel - hS + i, nSamples, xa);
+            else {
+#pragma unroll
+                for (int c = 0; c < MAXCH; c++) xa[c] = 0.0f;
+            }
+            load_ms(pcm, t0 + hrel + hS - 1 - i, nSamples, xb);
+            load_ms(pcm, t0 + hrel + hS + i, nSamples, xc);
+            load_ms(pcm, t0 + hrel + hS + s.S - 1 - i, nSamples, xd);
+            const int flat = (s.S - s.ovR) >> 1;
+            float2 rt = make_float2(0.0f, 0.0f);
+            if (i >= flat) rt = __ldg(&tb.rot[(s.ovR >> 1) + (i - flat)]);
+#pragma unroll
+            for (int c = 0; c < MAXCH; c++) {
+                if (c >= nch()) break;
+                const float a = lap_weight(xa[c], i - hS, hv), br = lap_weight(xb[c], hS - 1 - i, hv);
+                const float cc = xc[c], dr = xd[c];
+                float mc, ms;
+                if (i < flat) { mc = cc; ms = cc; }
+                else { float c2 = cc * rt.x, d2 = dr * rt.y; mc = c2 + d2; ms = c2 - d2; }
+                float mc2 = -a + br, ms2 = a + br;
+                const int base = c * N + s.off;
+                const int lo = hS - 1 - i, hi = hS + i;
+                w.XA[base + lo] = mc;
+                w.XA[base + hi] = mc2;
+                w.XB[base + lo] = (lo & 1) ? -ms : ms;
+                w.XB[base + hi] = (hi & 1) ? -ms2 : ms2;
+            }
+        }
     }
     __device__ void fold(int k) {
         const float *R1 = blk(k - 1), *R2 = blk(k - 2);
@@ -693,7 +769,6 @@ struct Encoder {
 
     // ---------------- normalise, keys, line sums (ulcEncoder_BlockTransform.c:243-281) ----------------
     __device__ void analyse(int k) {
-        float *lgN = blk(k - 2);                                      // dead sample block: log of the noise line sums
         int nz = 0;
         for (int p = tid; p < H; p += NTHR) {
             const int j = find_sub(sm, 2 * p);
@@ -715,7 +790,7 @@ struct Encoder {
                 float ns = a0 + a1;
                 amp += a0; amp += a1;
                 w.TB[base + (n0 >> 1)] = ns;
-                lgN[c * H + (s.off >> 1) + (n0 >> 1)] = fast_log(0x1.0p-126f + ns);
+                lg_lines(k, c, s)[n0 >> 1] = fast_log(0x1.0p-126f + ns);
             }
             w.amp2[p] = amp;
             w.mask[p] = fast_log(0x1.0p-126f + amp);
@@ -734,8 +809,8 @@ struct Encoder {
         const int lane = tid & 31;
         const int16_t *ev = tb.events + ((sh * 2 + kind) * 2 * ULCB_NBARK) * 2;
         const int16_t *ed = tb.edges + ((sh * 2 + kind) * ULCB_NBARK) * 2;
-        double (*stage)[32] = sm.stage[unit];
-        double (*lo)[3] = sm.lo[unit];
+        double (*stage)[32] = w.stage[unit];
+        double (*lo)[3] = w.lo[unit];
         const int src = lane < 3 ? lane : 0;
         double acc = 0.0;
         // The 2*NBARK band-edge events (position-sorted) live two per lane.  Lanes 0..2 run the three dependent DADD
@@ -811,7 +886,6 @@ struct Encoder {
         if (lane < ULCB_NBARK) sm.band[unit][lane] = below ? got : (kind ? 0.0f : -100.0f);
     }
     __device__ void serial_sums(int k) {
-        const float *lgN = blk(k - 2);
         const int U = nch() * sm.nsub, nTasks = U + sm.nsub + 1;
         constexpr int NW = NTHR / 32;
         const int warp = tid >> 5, lane = tid & 31;
@@ -840,7 +914,7 @@ struct Encoder {
             } else if (task < U) {
                 int c = task / sm.nsub, j = task - c * sm.nsub;
                 const SubInfo &s = sm.sub[j];
-                band_unit(task, w.TB + c * N + s.off, lgN + c * H + (s.off >> 1), s.S >> 1, s.sh, 0);
+                band_unit(task, w.TB + c * N + s.off, lg_lines(k, c, s), s.S >> 1, s.sh, 0);
             } else {
                 int j = task - U;
                 const SubInfo &s = sm.sub[j];
@@ -999,7 +1073,7 @@ struct Encoder {
         uint8_t  *info = reinterpret_cast<uint8_t *>(w.XB);                       // [CN]
         uint16_t *zoneStart = reinterpret_cast<uint16_t *>(info + CN);           // [CN]
         uint8_t  *zoneQi = info + 3 * CN;                                         // [CN]
-        uint32_t *outW = reinterpret_cast<uint32_t *>(blk(k - 2));               // packed nybbles
+        uint32_t *outW = out_words(k);                                            // packed nybbles
         uint16_t *jump = reinterpret_cast<uint16_t *>(w.encScratch);             // [CN] next zone start if a zone starts here
         uint8_t  *qcand = w.encScratch + 2 * CN;                                  // [CN] quantiser of that zone
         const float *coef = w.XA, *pairs = w.TB;
@@ -1362,30 +1436,49 @@ struct Detector {
     }
 };
 
-template <int NCHT, int NTHR, bool GWS>
-__global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArgs args) {
+template <int NCHT, int NTHR, bool GWS, bool PRE>
+__global__ void __launch_bounds__(PRE ? NTHR : NTHR + 32, PRE ? (NTHR == 256 ? 4 : 2) : 1) ulcb_encode_kernel(UlcbEncodeArgs args) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int NCH = NCHT ? NCHT : args.nChan;
-    using EncSmall = typename Encoder<NCHT, NTHR>::EncSmall;
+    using EncSmall = typename Encoder<NCHT, NTHR, PRE>::EncSmall;
     const int N = args.tb.N, CN = NCH * N, H = N >> 1;
     const int tid = threadIdx.x;
-    const bool isDetector = tid >= NTHR;                              // the extra warp
+    const bool isDetector = !PRE && tid >= NTHR;                      // the extra warp
     EncSmall &sm = *reinterpret_cast<EncSmall *>(smraw);
     Work wk;
-    float2 *detE; float *detStage;
+    float2 *detE = nullptr; float *detStage = nullptr;
     {
+        constexpr int MAXBU = EncSmall::MAXBU;
         unsigned char *p = smraw + ((sizeof(EncSmall) + 15) & ~(size_t)15);
-        wk.cnt = reinterpret_cast<uint16_t *>(p); p += 32 * NTHR;
-        wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
-        wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H;
-        if (!GWS) { detE = reinterpret_cast<float2 *>(p); p += sizeof(float2) * N * 3; }
-        detStage = reinterpret_cast<float *>(p); p += sizeof(float) * (NCH < 2 ? 2 : NCH) * (N + 4);   // >= 2 planes: the pre-mask lanes park d there
-        float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
-        if (GWS) detE = reinterpret_cast<float2 *>(big + 8 * CN + 64);
-        wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
-        wk.encScratch = GWS ? reinterpret_cast<uint8_t *>(big + 7 * CN) : reinterpret_cast<uint8_t *>(wk.cnt);
+        if (PRE) {
+            // one region serves the Bark analysis' f64 scratch, then the radix counters, then the coder scratch
+            size_t u = band_scratch_bytes(MAXBU);
+            if (u < 32 * (size_t)NTHR) u = 32 * (size_t)NTHR;
+            if (u < 3 * (size_t)CN) u = 3 * (size_t)CN;
+            u = (u + 15) & ~(size_t)15;
+            wk.cnt = reinterpret_cast<uint16_t *>(p); wk.encScratch = p;
+            wk.lo = reinterpret_cast<double (*)[ULCB_NBARK][3]>(p);
+            wk.stage = reinterpret_cast<double (*)[3][32]>(p + sizeof(double) * MAXBU * ULCB_NBARK * 3);
+            p += u;
+            wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
+            wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H + 16;        // + the four spare words of the packed block
+            float *big = reinterpret_cast<float *>(p);
+            wk.R = nullptr; wk.XA = big; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
+        } else {
+            wk.lo = reinterpret_cast<double (*)[ULCB_NBARK][3]>(p); p += sizeof(double) * MAXBU * ULCB_NBARK * 3;
+            wk.stage = reinterpret_cast<double (*)[3][32]>(p); p += sizeof(double) * MAXBU * 3 * 32;
+            wk.cnt = reinterpret_cast<uint16_t *>(p); p += 32 * NTHR;
+            wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
+            wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H;
+            if (!GWS) { detE = reinterpret_cast<float2 *>(p); p += sizeof(float2) * N * 3; }
+            detStage = reinterpret_cast<float *>(p); p += sizeof(float) * (NCH < 2 ? 2 : NCH) * (N + 4);   // >= 2 planes: the pre-mask lanes park d there
+            float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
+            if (GWS) detE = reinterpret_cast<float2 *>(big + 8 * CN + 64);
+            wk.R = big; wk.XA = big + 3 * CN; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
+            wk.encScratch = GWS ? reinterpret_cast<uint8_t *>(big + 7 * CN) : reinterpret_cast<uint8_t *>(wk.cnt);
+        }
     }
-    Encoder<NCHT, NTHR> enc(args, sm, wk);
+    Encoder<NCHT, NTHR, PRE> enc(args, sm, wk);
 
     for (int stream = blockIdx.x; stream < args.nStreams; stream += gridDim.x) {
         const int nBlocks = args.nBlocks ? (int)args.nBlocks[stream] : args.nBlocksAll;
@@ -1393,10 +1486,10 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
         const size_t elem = args.pcmFloat ? 4 : 2;
         const unsigned char *pcm = reinterpret_cast<const unsigned char *>(args.pcm) + (size_t)stream * args.inStride * elem;
         UlcbEncStreamState *st = args.state ? args.state + stream : nullptr;
-        const bool resume = st && st->valid;
-        fsync<NTHR>();                                                // the previous stream is finished everywhere
+        const bool resume = !PRE && st && st->valid;
+        csync<NTHR, PRE>();                                           // the previous stream is finished everywhere
 
-        if (isDetector) {
+        if (!PRE && isDetector) {
             // ================= transient detector warp: decisions for blocks 0..nBlocks-1, one block ahead =================
             const int lane = tid & 31;
             Detector<NCHT> det{args, detE, detStage, sm.seg, {0.0f, 0.0f, 0.0f}, pcm, nSamples,
@@ -1445,7 +1538,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
             for (int i = tid; i < CN; i += NTHR) { enc.blk((int)(k0 % 3) - 2)[i] = ss[i]; enc.blk((int)(k0 % 3) - 1)[i] = ss[CN + i]; }
             if (tid == 0) { sm.wcNext = st->nextWindowCtrl; sm.wcCur = st->windowCtrl; sm.wcPrev = st->prevWindowCtrl; }
         } else {
-            for (int i = tid; i < 3 * CN; i += NTHR) wk.R[i] = 0.0f;
+            if (!PRE) for (int i = tid; i < 3 * CN; i += NTHR) wk.R[i] = 0.0f;
             if (tid == 0) { sm.wcNext = 0x10; sm.wcCur = 0x10; sm.wcPrev = 0x10; }    // libulc/ulcEncoder.c:70
         }
         const int kb = (int)(k0 % 3);                                         // only k mod 3 matters for the rotating buffers
@@ -1456,14 +1549,20 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
 #endif
         for (int b = 0; b < nBlocks; b++) {
             const int k = kb + b;
-            long long valid = nSamples - (long long)b * N;
-            enc.ingest(k, pcm + (size_t)b * N * NCH * elem, valid < 0 ? 0 : valid);
-            TICK(0);
-            fsync<NTHR>();                                            // decision b is published (and the ingest is visible)
-            TICK(1);
-            enc.begin_block(sm.wcRing[b & 1]);
-            TICK(10);
-            enc.fold(k);
+            if (!PRE) {
+                long long valid = nSamples - (long long)b * N;
+                enc.ingest(k, pcm + (size_t)b * N * NCH * elem, valid < 0 ? 0 : valid);
+                TICK(0);
+                fsync<NTHR>();                                        // decision b is published (and the ingest is visible)
+                TICK(1);
+                enc.begin_block(sm.wcRing[b & 1]);
+                TICK(10);
+                enc.fold(k);
+            } else {
+                enc.begin_block(__ldg(args.wcAll + (size_t)stream * args.wcStride + b));
+                TICK(10);
+                enc.fold_pre(b, pcm, nSamples);
+            }
             wsync<NTHR>();
             TICK(2);
             enc.transform();
@@ -1532,7 +1631,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
             const int nBytes = size >> 3;
             if (!overflow && outPos + (uint64_t)nBytes > args.outStride) overflow = 1;
             if (!overflow) {
-                const uint8_t *ob = reinterpret_cast<const uint8_t *>(enc.blk(k - 2));
+                const uint8_t *ob = reinterpret_cast<const uint8_t *>(enc.out_words(k));
                 for (int i = tid; i < nBytes; i += NTHR) out[outPos + i] = ob[i];
             }
             if (tid == 0) {
@@ -1550,7 +1649,7 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
 #endif
 
         // ---- save state ----
-        if (st) {
+        if (!PRE && st) {
             const int k = kb + nBlocks;
             float *ss = args.stateSamples + (size_t)stream * 2 * CN;
             for (int i = tid; i < CN; i += NTHR) { ss[i] = enc.blk(k - 2)[i]; ss[CN + i] = enc.blk(k - 1)[i]; }
@@ -1567,6 +1666,280 @@ __global__ void __launch_bounds__(NTHR + 32, 1) ulcb_encode_kernel(UlcbEncodeArg
     }
 }
 
+
+// ---- transient detector pre-pass (ulcEncoder_WindowControl.c:31-239) ------------------------------------------------
+// The detector is the only part of the encoder that is serial along a stream (three one-pole envelopes carried from block to
+// block); everything it feeds is a per-block decision.  This kernel computes the decisions of every block up front so that
+// the encode kernel needs neither the detector warp nor its 64 KB of buffers.
+//
+// One CTA takes 32 streams and walks their blocks together; the serial recurrences run ONE LANE PER STREAM, so a warp
+// advances 32 envelopes per instruction instead of five.  Four roles are software-pipelined over the blocks and meet at one
+// __syncthreads per step:
+//   energy warps (DET_EW)  block j    tap energies sqrt(sum hp^2), sqrt(sum bp^2) of every sample      -> A[j % 3]
+//   post warp              block j-1  post-masking envelopes, forwards, in place                        A[(j-1) % 3]
+//   pre warp               block j-2  pre-masking envelopes backwards from the post end values, error energy -> R[j % 2]
+//   block warp             block j-3  block-masking envelope over the error energy, 8 segment sums, the decision
+// A / R live in global memory as [sample][32 lanes] so that every access of a chain warp is one coalesced row; the chains
+// load two batches ahead of the arithmetic.  Every chain keeps the reference's operation order (same values as the in-kernel
+// detector above, which stays for calls that carry state).
+constexpr int DET_EW = 16, DET_THREADS = (DET_EW + 3) * 32;
+constexpr int DET_CHUNK = 16;          // samples per staged chunk: [16][32 lanes] is one contiguous piece of A / R
+constexpr int DET_STAGES = 8;          // chunks in flight per chain warp (divides N / DET_CHUNK for every block size >= 256)
+
+// mbarrier / TMA bulk-copy helpers (the chain warps stage their rows through shared memory: the recurrences leave no room to hide
+// a global-memory latency per batch, a ring of bulk copies runs DET_STAGES chunks ahead instead)
+__device__ __forceinline__ unsigned det_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void det_mbar_wait(unsigned long long *b, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(det_smem_u32(b)), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();                 // a copy that never lands is a bug, not a reason to hang the GPU
+    }
+}
+__device__ __forceinline__ void det_fetch(void *dst, const void *src, unsigned bytes, unsigned long long *b) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the slot's last readers (generic proxy) come first
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(det_smem_u32(b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(det_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(det_smem_u32(b)) : "memory");
+}
+
+// raw sample point t of a stream (zero outside [0, nSamples)) and its conversion to M/S floats
+// (ulcEncoder_BlockTransform.c:87-111, tools/WavIO_Helper.c:49-55); split so that a batch of loads can be issued before any use
+template <int NCH, bool FLT> struct DetRaw { uint32_t w[(NCH == 2 && !FLT) ? 1 : NCH]; };
+template <int NCH, bool FLT>
+__device__ __forceinline__ DetRaw<NCH, FLT> det_load_raw(const unsigned char *pcm, long long t, long long nSamples, bool want = true) {
+    DetRaw<NCH, FLT> r;
+    const bool ok = want && t >= 0 && t < nSamples;
+    if (NCH == 2 && !FLT) r.w[0] = ok ? __ldg(reinterpret_cast<const uint32_t *>(pcm) + t) : 0u;
+    else {
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            r.w[c < ((NCH == 2 && !FLT) ? 1 : NCH) ? c : 0] =
+                !ok ? 0u : FLT ? __ldg(reinterpret_cast<const uint32_t *>(pcm) + (size_t)t * NCH + c)
+                               : (uint32_t)(int)__ldg(reinterpret_cast<const int16_t *>(pcm) + (size_t)t * NCH + c);
+    }
+    return r;
+}
+template <int NCH, bool FLT>
+__device__ __forceinline__ void det_cvt_ms(const DetRaw<NCH, FLT> &r, float *v) {
+    if (NCH == 2 && !FLT) {
+        v[0] = (float)(int16_t)(r.w[0] & 0xffffu) * 0x1.0p-15f; v[1 % NCH] = (float)(int16_t)(r.w[0] >> 16) * 0x1.0p-15f;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const uint32_t x = r.w[c < ((NCH == 2 && !FLT) ? 1 : NCH) ? c : 0];
+            v[c] = FLT ? __uint_as_float(x) : (float)(int)x * 0x1.0p-15f;
+        }
+    }
+    if (NCH == 2) { const float a = v[0], b = v[1]; v[0] = (a + b) * 0.5f; v[1] = (a - b) * 0.5f; }
+}
+
+template <int NCH, bool FLT>
+__global__ void __launch_bounds__(DET_THREADS, 1) ulcb_detect_kernel(UlcbEncodeArgs args, float2 *scrA, float *scrR, int32_t *wcAll, uint64_t wcStride) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    // shared memory: three chunk rings (post, pre: float2 rows; block: float rows), the transposition tiles, the segment sums
+    float2 (*ringP)[DET_CHUNK][32] = reinterpret_cast<float2 (*)[DET_CHUNK][32]>(smraw);
+    float2 (*ringQ)[DET_CHUNK][32] = ringP + DET_STAGES;
+    float  (*ringE)[DET_CHUNK][32] = reinterpret_cast<float (*)[DET_CHUNK][32]>(ringQ + DET_STAGES);
+    float2 (*tile)[32][33] = reinterpret_cast<float2 (*)[32][33]>(ringE + DET_STAGES);        // [DET_EW]
+    float (*segs)[33] = reinterpret_cast<float (*)[33]>(tile + DET_EW);                        // [32 lanes] {sum,cnt} x 16
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(segs + 32);              // [3][DET_STAGES]
+    const UlcbEncTables &tb = args.tb;
+    const int N = tb.N, H = N >> 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = blockIdx.x * 32, sMine = s0 + lane;
+    const bool live = sMine < args.nStreams;
+    const int nbAll = args.nBlocksAll;
+    const int nbMine = live ? (args.nBlocks ? min((int)args.nBlocks[sMine], nbAll) : nbAll) : 0;
+    const long long nsMine = live ? (args.nSamples ? (long long)args.nSamples[sMine] : (long long)nbMine * N) : 0;
+    const size_t elem = FLT ? 4 : 2;
+    float2 *A = scrA + (size_t)blockIdx.x * 3 * N * 32;
+    float  *R = scrR + (size_t)blockIdx.x * 2 * N * 32;
+    const int nChunks = N / DET_CHUNK;
+    float envH = 0.0f, envB = 0.0f, envK = 0.0f;                     // TransientFilter[3] of this lane's stream
+    unsigned phase = 0;                                               // parity of the ring's mbarriers: one flip per DET_STAGES chunks
+    if (warp == DET_EW + 2) for (int i = 0; i < 32; i++) segs[lane][i] = 0.0f;
+    if (threadIdx.x < 3 * DET_STAGES)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(det_smem_u32(&mbar[threadIdx.x])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    for (int j = 0; j < nbAll + 3; j++) {
+        if (warp < DET_EW) {
+            // ---- tap energies of block j (:60-71): sample n of the window is centred on (j-1)*N + H + n ----
+            if (j < nbAll) {
+                float2 *dst = A + (size_t)(j % 3) * N * 32;
+                const long long c0 = (long long)(j - 1) * N + H;
+                const size_t strideB = (size_t)args.inStride * elem;
+                const unsigned char *pcm0 = reinterpret_cast<const unsigned char *>(args.pcm) + (size_t)s0 * strideB;
+                for (int n0 = warp * 32; n0 < N; n0 += DET_EW * 32) {
+                    // lane = sample n0 + lane of stream s0 + ss.  All loads of a group of streams are issued before the first use;
+                    // the two neighbours of a sample come from the adjacent lanes (lanes 0 / 31 load theirs).
+                    constexpr int G = 8;
+                    const long long t = c0 + n0 + lane;
+                    const bool edge = lane == 0 || lane == 31;
+                    const long long tEdge = lane == 0 ? t - 1 : t + 1;
+                    // streams whose samples t-1 .. t+1 of the whole tile lie inside the stream need no bounds checks
+                    const unsigned inside = __ballot_sync(0xffffffffu, c0 + n0 - 1 >= 0 && c0 + n0 + 32 < nsMine);
+                    for (int g0 = 0; g0 < 32; g0 += G) {
+                        if (!FLT && NCH == 2 && ((inside >> g0) & ((1u << G) - 1u)) == ((1u << G) - 1u)) {
+                            // PCM16 stereo: M/S and the taps are exact in f32 (sums of a few 16-bit integers scaled by a power of
+                            // two), so they are formed in integers: M = (l + r) * 2^-16, hp = -M0 + 2 M1 - M2, bp = M2 - M0 give
+                            // the very floats of the reference's f32 expressions; only the squares, their sum and the root round.
+                            uint32_t mid[G], side[G];
+#pragma unroll
+                            for (int q = 0; q < G; q++) {
+                                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(pcm0 + (size_t)(g0 + q) * strideB);
+                                mid[q] = __ldg(p32 + t);
+                                side[q] = edge ? __ldg(p32 + tEdge) : 0u;
+                            }
+#pragma unroll
+                            for (int q = 0; q < G; q++) {
+                                const int l1 = (int)(int16_t)(mid[q] & 0xffffu), r1 = (int)mid[q] >> 16;
+                                const int ls = (int)(int16_t)(side[q] & 0xffffu), rs = (int)side[q] >> 16;
+                                const int m1 = l1 + r1, d1 = l1 - r1, ms = ls + rs, ds = ls - rs;
+                                int m0 = __shfl_up_sync(0xffffffffu, m1, 1), d0 = __shfl_up_sync(0xffffffffu, d1, 1);
+                                int m2 = __shfl_down_sync(0xffffffffu, m1, 1), d2 = __shfl_down_sync(0xffffffffu, d1, 1);
+                                if (lane == 0) { m0 = ms; d0 = ds; }
+                                if (lane == 31) { m2 = ms; d2 = ds; }
+                                const float hpM = (float)(2 * m1 - m0 - m2) * 0x1.0p-16f, bpM = (float)(m2 - m0) * 0x1.0p-16f;
+                                const float hpS = (float)(2 * d1 - d0 - d2) * 0x1.0p-16f, bpS = (float)(d2 - d0) * 0x1.0p-16f;
+                                const float ehp = hpM * hpM + hpS * hpS, ebp = bpM * bpM + bpS * bpS;
+                                tile[warp][g0 + q][lane] = make_float2(sqrtf(ehp), sqrtf(ebp));
+                            }
+                            continue;
+                        }
+                        DetRaw<NCH, FLT> mid[G], side[G];
+#pragma unroll
+                        for (int q = 0; q < G; q++) {
+                            const long long ns = __shfl_sync(0xffffffffu, nsMine, g0 + q);
+                            const unsigned char *pcm = pcm0 + (size_t)(g0 + q) * strideB;
+                            mid[q] = det_load_raw<NCH, FLT>(pcm, t, ns);
+                            side[q] = det_load_raw<NCH, FLT>(pcm, tEdge, ns, edge);
+                        }
+#pragma unroll
+                        for (int q = 0; q < G; q++) {
+                            float v0[NCH], v1[NCH], v2[NCH], vs[NCH];
+                            det_cvt_ms<NCH, FLT>(mid[q], v1);
+                            det_cvt_ms<NCH, FLT>(side[q], vs);
+                            float ehp = 0.0f, ebp = 0.0f;
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) {
+                                v0[c] = __shfl_up_sync(0xffffffffu, v1[c], 1);
+                                v2[c] = __shfl_down_sync(0xffffffffu, v1[c], 1);
+                                if (lane == 0) v0[c] = vs[c];
+                                if (lane == 31) v2[c] = vs[c];
+                                const float hp = (-v0[c] + 2.0f * v1[c]) - v2[c], bp = -v0[c] + v2[c];
+                                ehp += hp * hp; ebp += bp * bp;
+                            }
+                            tile[warp][g0 + q][lane] = make_float2(sqrtf(ehp), sqrtf(ebp));
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll 8
+                    for (int k = 0; k < 32; k++) __stcg(&dst[(size_t)(n0 + k) * 32 + lane], tile[warp][lane][k]);
+                    __syncwarp();
+                }
+            }
+        } else if (warp == DET_EW) {
+            // ---- post-masking envelopes of block j-1, forwards, in place (:73-88) ----
+            const int b = j - 1;
+            if (b >= 0 && b < nbAll) {
+                float2 *P = A + (size_t)(b % 3) * N * 32;
+                const float cH = tb.c1PostHp, cB = tb.c1PostBp;
+                unsigned long long *mb = mbar;
+                if (lane == 0)
+                    for (int k = 0; k < DET_STAGES; k++) det_fetch(ringP[k], P + (size_t)k * DET_CHUNK * 32, sizeof(float2) * DET_CHUNK * 32, &mb[k]);
+                for (int k = 0; k < nChunks; k++) {
+                    const int slot = k % DET_STAGES;
+                    det_mbar_wait(&mb[slot], phase);
+                    float2 x[DET_CHUNK];
+#pragma unroll
+                    for (int q = 0; q < DET_CHUNK; q++) x[q] = ringP[slot][q][lane];
+                    __syncwarp();
+                    if (lane == 0 && k + DET_STAGES < nChunks)
+                        det_fetch(ringP[slot], P + (size_t)(k + DET_STAGES) * DET_CHUNK * 32, sizeof(float2) * DET_CHUNK * 32, &mb[slot]);
+#pragma unroll
+                    for (int q = 0; q < DET_CHUNK; q++) {
+                        const float dh = x[q].x - envH; envH += dh * cH;
+                        const float db = x[q].y - envB; envB += db * cB;
+                        __stcg(&P[(size_t)(k * DET_CHUNK + q) * 32 + lane], make_float2(envH, envB));
+                    }
+                    if (slot == DET_STAGES - 1) phase ^= 1u;
+                }
+            }
+        } else if (warp == DET_EW + 1) {
+            // ---- pre-masking envelopes of block j-2, backwards from the post-masking end values; error energy (:90-103) ----
+            const int b = j - 2;
+            if (b >= 0 && b < nbAll) {
+                const float2 *Q = A + (size_t)(b % 3) * N * 32;
+                float *E = R + (size_t)(b & 1) * N * 32;
+                const float cH = tb.c1PreHp, cB = tb.c1PreBp;
+                unsigned long long *mb = mbar + DET_STAGES;
+                if (lane == 0)
+                    for (int k = 0; k < DET_STAGES; k++)
+                        det_fetch(ringQ[k], Q + (size_t)(nChunks - 1 - k) * DET_CHUNK * 32, sizeof(float2) * DET_CHUNK * 32, &mb[k]);
+                float sH = 0.0f, sB = 0.0f;
+                for (int k = 0; k < nChunks; k++) {                  // chunk nChunks-1-k, samples in descending order
+                    const int slot = k % DET_STAGES, ck = nChunks - 1 - k;
+                    det_mbar_wait(&mb[slot], phase);
+                    float2 x[DET_CHUNK];
+#pragma unroll
+                    for (int q = 0; q < DET_CHUNK; q++) x[q] = ringQ[slot][DET_CHUNK - 1 - q][lane];
+                    __syncwarp();
+                    if (lane == 0 && k + DET_STAGES < nChunks)
+                        det_fetch(ringQ[slot], Q + (size_t)(ck - DET_STAGES) * DET_CHUNK * 32, sizeof(float2) * DET_CHUNK * 32, &mb[slot]);
+                    if (k == 0) { sH = x[0].x; sB = x[0].y; }         // the post-masking state at the end of the block
+#pragma unroll
+                    for (int q = 0; q < DET_CHUNK; q++) {
+                        const float dh = x[q].x - sH; sH += dh * cH;
+                        const float db = x[q].y - sB; sB += db * cB;
+                        const float a = dh * sB, bb = db * sH;
+                        __stcg(&E[(size_t)(ck * DET_CHUNK + DET_CHUNK - 1 - q) * 32 + lane], a * a + bb * bb);
+                    }
+                    if (slot == DET_STAGES - 1) phase ^= 1u;
+                }
+            }
+        } else {
+            // ---- block-masking envelope of block j-3 over the error energy, segment sums, decision (:105-239) ----
+            const int b = j - 3;
+            if (b >= 0 && b < nbAll) {
+                const float *E = R + (size_t)(b & 1) * N * 32;
+                const float cK = tb.c1Blk;
+                const int chunksPerSeg = nChunks >> 3;
+                float *seg = segs[lane];
+                unsigned long long *mb = mbar + 2 * DET_STAGES;
+                if (lane == 0)
+                    for (int k = 0; k < DET_STAGES; k++) det_fetch(ringE[k], E + (size_t)k * DET_CHUNK * 32, sizeof(float) * DET_CHUNK * 32, &mb[k]);
+                int k = 0;
+                for (int sg = 0; sg < 8; sg++) {
+                    float acc = 0.0f;
+                    for (int m = 0; m < chunksPerSeg; m++, k++) {
+                        const int slot = k % DET_STAGES;
+                        det_mbar_wait(&mb[slot], phase);
+                        float x[DET_CHUNK];
+#pragma unroll
+                        for (int q = 0; q < DET_CHUNK; q++) x[q] = ringE[slot][q][lane];
+                        __syncwarp();
+                        if (lane == 0 && k + DET_STAGES < nChunks)
+                            det_fetch(ringE[slot], E + (size_t)(k + DET_STAGES) * DET_CHUNK * 32, sizeof(float) * DET_CHUNK * 32, &mb[slot]);
+#pragma unroll
+                        for (int q = 0; q < DET_CHUNK; q++) { const float d = x[q] - envK; envK += d * cK; acc += envK; }
+                        if (slot == DET_STAGES - 1) phase ^= 1u;
+                    }
+                    seg[2 * sg] = seg[16 + 2 * sg]; seg[2 * sg + 1] = seg[16 + 2 * sg + 1];
+                    seg[16 + 2 * sg] = acc; seg[16 + 2 * sg + 1] = (float)(N >> 3);     // the count is one 1.0f per sample (:126)
+                }
+                const int decision = window_decide(seg, tb.log2N);
+                if (b < nbMine) wcAll[(size_t)sMine * wcStride + b] = decision;
+            }
+        }
+        // what this step wrote to A / R is read by the bulk copies (async proxy) of the next step
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
+    }
+}
 }  // namespace
 
 #ifdef ULCB_PHASE_TIMING
@@ -1601,30 +1974,65 @@ cudaError_t ulcb_avg_complexity_launch(const float *dComplexity, uint64_t metaSt
 bool ulcb_encode_uses_global_ws(int N, int nChan) { return (size_t)nChan * N > 4096 || nChan > 2; }
 int  ulcb_encode_threads(int N, int nChan) { return (nChan * N >= 4096) ? 512 : 256; }
 size_t ulcb_encode_ws_floats(int N, int nChan) { return (size_t)8 * nChan * N + 64 + (size_t)6 * N; }   // + the detector's 3 block buffers
-size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs) {
+size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs, bool pre) {
     const size_t small = nChan == 1 ? sizeof(EncSmallT<4>) : nChan == 2 ? sizeof(EncSmallT<8>) : sizeof(EncSmallT<4 * ULCB_ENC_MAXCH>);
-    size_t s = ((small + 15) & ~(size_t)15) + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * (nChan < 2 ? 2 : nChan) * (N + 4);
+    const size_t band = band_scratch_bytes((nChan == 1 ? 4 : nChan == 2 ? 8 : 4 * ULCB_ENC_MAXCH) + 4);
+    size_t s = (small + 15) & ~(size_t)15;
+    if (pre) {                                                          // mirrors the carve-up in the kernel
+        size_t u = band;
+        if (u < 32 * (size_t)nthr) u = 32 * (size_t)nthr;
+        if (u < 3 * (size_t)nChan * N) u = 3 * (size_t)nChan * N;
+        u = (u + 15) & ~(size_t)15;
+        return s + u + sizeof(float) * N + 16 + sizeof(float) * (size_t)4 * nChan * N + 16;
+    }
+    s += band + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * (nChan < 2 ? 2 : nChan) * (N + 4);
     if (!globalWs) s += sizeof(float) * ((size_t)7 * nChan * N + 64);
     return s + 16;
 }
 
-template <int NCH, int NTHR>
+template <int NCH, int NTHR, bool PRE>
 static cudaError_t launch_e(const UlcbEncodeArgs &args, int gridBlocks, cudaStream_t stream) {
     const bool gws = args.workspace != nullptr;
-    void (*k)(UlcbEncodeArgs) = gws ? ulcb_encode_kernel<NCH, NTHR, true> : ulcb_encode_kernel<NCH, NTHR, false>;
-    size_t smem = ulcb_encode_smem_bytes(args.tb.N, NCH ? NCH : args.nChan, NTHR, gws);
+    void (*k)(UlcbEncodeArgs) = PRE ? ulcb_encode_kernel<NCH, NTHR, false, PRE> : gws ? ulcb_encode_kernel<NCH, NTHR, true, false> : ulcb_encode_kernel<NCH, NTHR, false, false>;
+    size_t smem = ulcb_encode_smem_bytes(args.tb.N, NCH ? NCH : args.nChan, NTHR, gws, PRE);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<gridBlocks, NTHR + 32, smem, stream>>>(args);
+    if (PRE) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    k<<<gridBlocks, PRE ? NTHR : NTHR + 32, smem, stream>>>(args);
     return cudaGetLastError();
 }
 
 cudaError_t ulcb_encode_launch(const UlcbEncodeArgs &args, int nChan, int gridBlocks, cudaStream_t stream) {
-    const int nthr = ulcb_encode_threads(args.tb.N, nChan);
-    if (nChan == 2) return nthr == 512 ? launch_e<2, 512>(args, gridBlocks, stream) : launch_e<2, 256>(args, gridBlocks, stream);
-    if (nChan == 1) return nthr == 512 ? launch_e<1, 512>(args, gridBlocks, stream) : launch_e<1, 256>(args, gridBlocks, stream);
+    int nthr = ulcb_encode_threads(args.tb.N, nChan);
+    if (args.wcAll) {                                                   // window controls precomputed: stereo / mono, shared-memory shapes
+        if (args.workspace || args.state || nChan > 2) return cudaErrorInvalidValue;
+        if (args.encThreads == 256 || args.encThreads == 512) nthr = args.encThreads;
+        if (nChan == 2) return nthr == 512 ? launch_e<2, 512, true>(args, gridBlocks, stream) : launch_e<2, 256, true>(args, gridBlocks, stream);
+        return nthr == 512 ? launch_e<1, 512, true>(args, gridBlocks, stream) : launch_e<1, 256, true>(args, gridBlocks, stream);
+    }
+    if (nChan == 2) return nthr == 512 ? launch_e<2, 512, false>(args, gridBlocks, stream) : launch_e<2, 256, false>(args, gridBlocks, stream);
+    if (nChan == 1) return nthr == 512 ? launch_e<1, 512, false>(args, gridBlocks, stream) : launch_e<1, 256, false>(args, gridBlocks, stream);
     // 3 .. ULCB_ENC_MAXCH channels: one instantiation with the channel count at run time, work buffers in the global workspace
     if (nChan <= ULCB_ENC_MAXCH && nChan == args.nChan && args.workspace)
-        return nthr == 512 ? launch_e<0, 512>(args, gridBlocks, stream) : launch_e<0, 256>(args, gridBlocks, stream);
+        return nthr == 512 ? launch_e<0, 512, false>(args, gridBlocks, stream) : launch_e<0, 256, false>(args, gridBlocks, stream);
     return cudaErrorInvalidValue;
+}
+
+// ---- detector pre-pass ----
+bool ulcb_detect_supported(int N, int nChan) { return (nChan == 1 || nChan == 2) && N >= 256 && !ulcb_encode_uses_global_ws(N, nChan); }
+static size_t det_a_bytes(int N, int nStreams) { return sizeof(float2) * (size_t)((nStreams + 31) / 32) * 3 * N * 32; }
+size_t ulcb_detect_scratch_bytes(int N, int nStreams) { return det_a_bytes(N, nStreams) + sizeof(float) * (size_t)((nStreams + 31) / 32) * 2 * N * 32; }
+cudaError_t ulcb_detect_launch(const UlcbEncodeArgs &args, int nChan, void *scratch, int32_t *wcAll, uint64_t wcStride, cudaStream_t stream) {
+    if (!ulcb_detect_supported(args.tb.N, nChan) || args.state) return cudaErrorInvalidValue;
+    void (*k)(UlcbEncodeArgs, float2 *, float *, int32_t *, uint64_t) =
+        nChan == 2 ? (args.pcmFloat ? ulcb_detect_kernel<2, true> : ulcb_detect_kernel<2, false>)
+                   : (args.pcmFloat ? ulcb_detect_kernel<1, true> : ulcb_detect_kernel<1, false>);
+    const size_t smem = (sizeof(float2) * 2 + sizeof(float)) * DET_STAGES * DET_CHUNK * 32 + sizeof(float2) * DET_EW * 32 * 33 +
+                        sizeof(float) * 32 * 33 + sizeof(unsigned long long) * 3 * DET_STAGES + 128;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    float2 *scrA = reinterpret_cast<float2 *>(scratch);
+    float *scrR = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(scratch) + det_a_bytes(args.tb.N, args.nStreams));
+    k<<<(args.nStreams + 31) / 32, DET_THREADS, smem, stream>>>(args, scrA, scrR, wcAll, wcStride);
+    return cudaGetLastError();
 }

@@ -72,6 +72,9 @@ struct UlcbEncodeArgs {
     float          *stateSamples;      // [nStreams][2*nChan*N] blocks k-2, k-1 (M/S planar)
     float          *workspace;         // global workspace for large blocks: [gridDim.x][wsFloats]; nullptr = shared memory
     uint64_t        wsFloats;
+    const int32_t  *wcAll;             // [stream][wcStride] transient-detector decisions from ulcb_detect_launch; nullptr = the
+    uint64_t        wcStride;          //   encode kernel runs the detector itself (one warp beside the workers)
+    int             encThreads;        // with wcAll: 256 / 512 worker threads per CTA, 0 = by block size
     // test taps (nullable), [stream][nBlocksAll][nChan*N] / [..][N/2]
     float          *dbgCoefs;
     float          *dbgKeys;
@@ -82,7 +85,13 @@ struct UlcbEncodeArgs {
     int             dbgFlags;          // ULCB_PHASE_TIMING builds only: skip phases (timing experiments)
 };
 
-size_t      ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs);
+size_t      ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs, bool pre = false);
+// Detector pre-pass (ulcEncoder_WindowControl.c:31-239 for every block of every stream, 32 streams per CTA, one lane per stream):
+// shapes it takes, its scratch in bytes, and the launch; decisions go to wcAll[stream][wcStride].  The encode launch that
+// follows with args.wcAll set needs no detector warp.
+bool        ulcb_detect_supported(int N, int nChan);
+size_t      ulcb_detect_scratch_bytes(int N, int nStreams);
+cudaError_t ulcb_detect_launch(const UlcbEncodeArgs &args, int nChan, void *scratch, int32_t *wcAll, uint64_t wcStride, cudaStream_t stream);
 size_t      ulcb_encode_ws_floats(int N, int nChan);
 int         ulcb_encode_threads(int N, int nChan);
 bool        ulcb_encode_uses_global_ws(int N, int nChan);
