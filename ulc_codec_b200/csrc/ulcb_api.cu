@@ -896,7 +896,12 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
     if (getenv("ULCB_DBG_FLAGS")) a.dbgFlags = atoi(getenv("ULCB_DBG_FLAGS"));
 #endif
     int grid = nStreams;
-    if (ulcb_encode_uses_global_ws(ctx->N, ctx->nChan)) {
+    // Whole streams from their start (no carried state), every stream nBlocksAll blocks, stereo / mono whose work set fits shared
+    // memory without the detector's buffers: the transient detector runs as a pre-pass over all streams and the encode kernel
+    // takes its decisions (ULCB_ENC_PRE=0 keeps the detector inside the encode kernel, as calls with carried state do).
+    static const bool preOff = getenv("ULCB_ENC_PRE") && atoi(getenv("ULCB_ENC_PRE")) == 0;
+    const bool pre = !preOff && !state && !dNBlocks && nBlocksAll > 0 && ulcb_detect_supported(ctx->N, ctx->nChan);
+    if (pre ? ulcb_encode_pre_uses_global_ws(ctx->N, ctx->nChan) : ulcb_encode_uses_global_ws(ctx->N, ctx->nChan)) {
         const int cap = ctx->smCount * 2;
         if (grid > cap) grid = cap;
         const size_t per = ulcb_encode_ws_floats(ctx->N, ctx->nChan);
@@ -907,11 +912,7 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
         }
         a.workspace = ctx->encWs; a.wsFloats = per;
     }
-    // Whole streams from their start (no carried state), every stream nBlocksAll blocks, stereo / mono at a shared-memory
-    // block size: the transient detector runs as a pre-pass over all streams and the encode kernel takes its decisions
-    // (ULCB_ENC_PRE=0 keeps the detector inside the encode kernel, as calls with carried state do).
-    static const bool preOff = getenv("ULCB_ENC_PRE") && atoi(getenv("ULCB_ENC_PRE")) == 0;
-    if (!preOff && !state && !dNBlocks && nBlocksAll > 0 && !a.workspace && ulcb_detect_supported(ctx->N, ctx->nChan)) {
+    if (pre) {
         const size_t needScr = ulcb_detect_scratch_bytes(ctx->N, nStreams), needWc = (size_t)nStreams * nBlocksAll;
         if (ctx->detScratchCap < needScr) {
             if (ctx->detScratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->detScratch); ctx->detScratch = nullptr; ctx->detScratchCap = 0; }

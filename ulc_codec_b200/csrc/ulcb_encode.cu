@@ -748,13 +748,49 @@ struct Encoder {
             }
         }
     }
+    // Two levels up in one pass: node size m from its four grandchildren (size m/4).  A DCT-IV node has children (II, II), a
+    // DCT-II node (II, IV); a DCT-II result is the interleave of its children, a DCT-IV result their butterfly
+    // (Fourier_DCT4_Template.h:100-114, Fourier_DCT2_Template.h:62-77), so four consecutive outputs 4k..4k+3 depend on six
+    // grandchild values.  Same additions on the same operands as two single-level passes; half the barriers, one 128-bit store.
+    // Reads one buffer pair, writes the other (the grandchildren share the parity of the node's own depth).
+    __device__ void dct_up2_long(int lgm, bool srcIsX) {
+        const int m = 1 << lgm, hm = m >> 1, qm = m >> 2, lgH = tb.log2N - 1, d = tb.log2N - lgm;
+        const float *const S0 = srcIsX ? w.XA : w.TA, *const S1 = srcIsX ? w.XB : w.TB;
+        float *const D0 = srcIsX ? w.TA : w.XA, *const D1 = srcIsX ? w.TB : w.XB;
+#pragma unroll 2
+        for (int Q = tid; Q < (CN >> 1); Q += NTHR) {
+            const int cc = Q >> (lgH - 1), r = Q & ((H >> 1) - 1);
+            const bool hb = cc >= nch();
+            const int node = r >> (lgm - 2), k = r & (qm - 1);
+            const int off = (hb ? cc - nch() : cc) * N + (node << lgm);
+            const float *AA = (hb ? S1 : S0) + off, *AB = AA + qm, *BA = AA + hm, *BB = BA + qm;
+            float4 o;
+            const float ab = AB[k], bbr = BB[qm - 1 - k];
+            if (node_is_dct4(d, node)) {
+                o.x = (k == 0) ? AA[0] : AA[k] - BA[qm - k];
+                o.y = ab + bbr;
+                o.z = ab - bbr;
+                o.w = (k == qm - 1) ? BA[0] : AA[k + 1] + BA[qm - 1 - k];
+            } else {
+                o.x = AA[k];
+                o.y = (k == 0) ? BA[0] : BA[k] - BB[qm - k];
+                o.z = ab;
+                o.w = (k == qm - 1) ? BB[0] : BA[k + 1] + bbr;
+            }
+            *reinterpret_cast<float4 *>((hb ? D1 : D0) + off + 4 * k) = o;
+        }
+    }
     __device__ void transform() {
         const int lgN = tb.log2N;
         if (sm.nsub == 1) {
             if (((lgN - 3) & 3) == 0) {                               // an even number of two-level passes leaves the data where the leaves expect it
                 bool srcIsX = true;
                 for (int lgm = lgN; lgm >= 5; lgm -= 2) { dct_down2_long(lgm, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
-            } else
+                dct_leaves();                                         // in X: the leaves sit at an even depth
+                wsync<NTHR>();
+                for (int lgm = 5; lgm <= lgN; lgm += 2) { dct_up2_long(lgm, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
+                return;                                               // an even number of passes again: the result is in X
+            }
             for (int lgm = lgN; lgm >= 4; lgm--) { dct_down_long(1 << lgm, lgm); wsync<NTHR>(); }
             dct_leaves();
             wsync<NTHR>();
@@ -1108,6 +1144,17 @@ struct Encoder {
         // until the first later one that would push max/min of the levels above 4; that end only depends on m, so
         // every selected coefficient computes "the zone that would start here" in parallel (jump pointer + quantiser),
         // and one thread per (channel, sub-block) then just follows the pointers from the first selected coefficient.
+        // The scan for a zone's end is monotone (the running max only grows, the running min only shrinks), so whole groups of
+        // eight selected coefficients are skipped on their {min, max} summary while the zone stays open with the group included;
+        // the group that closes it is then scanned one by one.  (The summaries borrow the zone tables, written after this loop.)
+        float2 *gsum = reinterpret_cast<float2 *>(zoneStart);
+        for (int g = tid; g * 8 + 8 <= nSel; g += NTHR) {
+            float mn = fabsf(coef[selList[g * 8]]), mx = mn;
+#pragma unroll
+            for (int q = 1; q < 8; q++) { const float l = fabsf(coef[selList[g * 8 + q]]); mn = l < mn ? l : mn; mx = l > mx ? l : mx; }
+            gsum[g] = make_float2(mn, mx);
+        }
+        wsync<NTHR>();
         for (int m = tid; m < nSel; m += NTHR) {
             int u = 0;
             while (m >= sm.unitSel[u + 1]) u++;
@@ -1115,25 +1162,20 @@ struct Encoder {
             float lo = fabsf(coef[selList[m]]), hi = lo;
             int mm = m + 1;
             bool open = true;
-            while (open && mm + 4 <= m1) {                            // four levels fetched at once, tested in order
-                const float l0 = fabsf(coef[selList[mm]]), l1 = fabsf(coef[selList[mm + 1]]);
-                const float l2 = fabsf(coef[selList[mm + 2]]), l3 = fabsf(coef[selList[mm + 3]]);
-                const float lv[4] = {l0, l1, l2, l3};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (open) {
-                        const float newLo = lv[q] < lo ? lv[q] : lo, newHi = lv[q] > hi ? lv[q] : hi;
-                        if (newHi > newLo * 4.0f) open = false;
-                        else { lo = newLo; hi = newHi; mm++; }
-                    }
-                }
-            }
-            for (; open && mm < m1; mm++) {
+            auto one = [&]() {                                        // try to take selected coefficient mm into the zone
                 const float level = fabsf(coef[selList[mm]]);
                 const float newLo = level < lo ? level : lo, newHi = level > hi ? level : hi;
+                if (newHi > newLo * 4.0f) open = false;
+                else { lo = newLo; hi = newHi; mm++; }
+            };
+            while (open && mm < m1 && (mm & 7)) one();
+            while (open && mm + 8 <= m1) {
+                const float2 g = gsum[mm >> 3];
+                const float newLo = g.x < lo ? g.x : lo, newHi = g.y > hi ? g.y : hi;
                 if (newHi > newLo * 4.0f) break;
-                lo = newLo; hi = newHi;
+                lo = newLo; hi = newHi; mm += 8;
             }
+            while (open && mm < m1) one();
             int q = (int)(0x1.657006p2f + -0x1.715476p0f * logf_ref(hi));     // :83-88
             if (q < 5) q = 5;
             if (q > 31) q = 31;
@@ -1454,7 +1496,7 @@ __global__ void __launch_bounds__(PRE ? NTHR : NTHR + 32, PRE ? (NTHR == 256 ? 4
             // one region serves the Bark analysis' f64 scratch, then the radix counters, then the coder scratch
             size_t u = band_scratch_bytes(MAXBU);
             if (u < 32 * (size_t)NTHR) u = 32 * (size_t)NTHR;
-            if (u < 3 * (size_t)CN) u = 3 * (size_t)CN;
+            if (!GWS && u < 3 * (size_t)CN) u = 3 * (size_t)CN;
             u = (u + 15) & ~(size_t)15;
             wk.cnt = reinterpret_cast<uint16_t *>(p); wk.encScratch = p;
             wk.lo = reinterpret_cast<double (*)[ULCB_NBARK][3]>(p);
@@ -1462,8 +1504,9 @@ __global__ void __launch_bounds__(PRE ? NTHR : NTHR + 32, PRE ? (NTHR == 256 ? 4
             p += u;
             wk.amp2 = reinterpret_cast<float *>(p); p += sizeof(float) * H;
             wk.mask = reinterpret_cast<float *>(p); p += sizeof(float) * H + 16;        // + the four spare words of the packed block
-            float *big = reinterpret_cast<float *>(p);
+            float *big = GWS ? args.workspace + (size_t)blockIdx.x * args.wsFloats : reinterpret_cast<float *>(p);
             wk.R = nullptr; wk.XA = big; wk.XB = wk.XA + CN; wk.TA = wk.XB + CN; wk.TB = wk.TA + CN;
+            if (GWS) wk.encScratch = reinterpret_cast<uint8_t *>(big + 4 * CN);
         } else {
             wk.lo = reinterpret_cast<double (*)[ULCB_NBARK][3]>(p); p += sizeof(double) * MAXBU * ULCB_NBARK * 3;
             wk.stage = reinterpret_cast<double (*)[3][32]>(p); p += sizeof(double) * MAXBU * 3 * 32;
@@ -1981,9 +2024,9 @@ size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs, bool pr
     if (pre) {                                                          // mirrors the carve-up in the kernel
         size_t u = band;
         if (u < 32 * (size_t)nthr) u = 32 * (size_t)nthr;
-        if (u < 3 * (size_t)nChan * N) u = 3 * (size_t)nChan * N;
+        if (!globalWs && u < 3 * (size_t)nChan * N) u = 3 * (size_t)nChan * N;
         u = (u + 15) & ~(size_t)15;
-        return s + u + sizeof(float) * N + 16 + sizeof(float) * (size_t)4 * nChan * N + 16;
+        return s + u + sizeof(float) * N + 16 + (globalWs ? 0 : sizeof(float) * (size_t)4 * nChan * N) + 16;
     }
     s += band + 32 * (size_t)nthr + sizeof(float) * N + (globalWs ? 0 : sizeof(float2) * N * 3) + sizeof(float) * (nChan < 2 ? 2 : nChan) * (N + 4);
     if (!globalWs) s += sizeof(float) * ((size_t)7 * nChan * N + 64);
@@ -1993,7 +2036,7 @@ size_t ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs, bool pr
 template <int NCH, int NTHR, bool PRE>
 static cudaError_t launch_e(const UlcbEncodeArgs &args, int gridBlocks, cudaStream_t stream) {
     const bool gws = args.workspace != nullptr;
-    void (*k)(UlcbEncodeArgs) = PRE ? ulcb_encode_kernel<NCH, NTHR, false, PRE> : gws ? ulcb_encode_kernel<NCH, NTHR, true, false> : ulcb_encode_kernel<NCH, NTHR, false, false>;
+    void (*k)(UlcbEncodeArgs) = gws ? ulcb_encode_kernel<NCH, NTHR, true, PRE> : ulcb_encode_kernel<NCH, NTHR, false, PRE>;
     size_t smem = ulcb_encode_smem_bytes(args.tb.N, NCH ? NCH : args.nChan, NTHR, gws, PRE);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -2005,7 +2048,7 @@ static cudaError_t launch_e(const UlcbEncodeArgs &args, int gridBlocks, cudaStre
 cudaError_t ulcb_encode_launch(const UlcbEncodeArgs &args, int nChan, int gridBlocks, cudaStream_t stream) {
     int nthr = ulcb_encode_threads(args.tb.N, nChan);
     if (args.wcAll) {                                                   // window controls precomputed: stereo / mono, shared-memory shapes
-        if (args.workspace || args.state || nChan > 2) return cudaErrorInvalidValue;
+        if (args.state || nChan > 2) return cudaErrorInvalidValue;
         if (args.encThreads == 256 || args.encThreads == 512) nthr = args.encThreads;
         if (nChan == 2) return nthr == 512 ? launch_e<2, 512, true>(args, gridBlocks, stream) : launch_e<2, 256, true>(args, gridBlocks, stream);
         return nthr == 512 ? launch_e<1, 512, true>(args, gridBlocks, stream) : launch_e<1, 256, true>(args, gridBlocks, stream);
@@ -2019,7 +2062,10 @@ cudaError_t ulcb_encode_launch(const UlcbEncodeArgs &args, int nChan, int gridBl
 }
 
 // ---- detector pre-pass ----
-bool ulcb_detect_supported(int N, int nChan) { return (nChan == 1 || nChan == 2) && N >= 256 && !ulcb_encode_uses_global_ws(N, nChan); }
+bool ulcb_detect_supported(int N, int nChan) { return (nChan == 1 || nChan == 2) && N >= 256; }
+// with the window controls precomputed the encode kernel keeps X / T, the line buffers and one scratch region in shared memory
+// when they fit; larger blocks keep X / T in the global workspace
+bool ulcb_encode_pre_uses_global_ws(int N, int nChan) { return ulcb_encode_smem_bytes(N, nChan, ulcb_encode_threads(N, nChan), false, true) > 227 * 1024; }
 static size_t det_a_bytes(int N, int nStreams) { return sizeof(float2) * (size_t)((nStreams + 31) / 32) * 3 * N * 32; }
 size_t ulcb_detect_scratch_bytes(int N, int nStreams) { return det_a_bytes(N, nStreams) + sizeof(float) * (size_t)((nStreams + 31) / 32) * 2 * N * 32; }
 cudaError_t ulcb_detect_launch(const UlcbEncodeArgs &args, int nChan, void *scratch, int32_t *wcAll, uint64_t wcStride, cudaStream_t stream) {
