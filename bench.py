@@ -231,12 +231,17 @@ def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, war
         dist.barrier()
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    ctx.kernel_times(reset=True)
+    ctx.set_kernel_timing(True)
     e0.record(ext)
     for _ in range(steps):
         step()
     e1.record(ext)
     ctx.sync(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    kt = ctx.kernel_times(reset=True)
+    ctx.set_kernel_timing(False)
+    kernels = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in kt.items() if v[1] and k.startswith("enc_")}
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -251,10 +256,11 @@ def bench_encode(ctx, capi, torch, dist, dev, rank, world, n_streams, steps, war
          "config": {"workload": "configs[2]: batched VBR encode Quality=50, window switching on", "streams_per_gpu": n_streams,
                     "blocks_per_stream": nb, "input": "integer-only synthetic music corpus generated on the device (csrc/ulcb_corpus.cu), every stream distinct",
                     "avg_bytes_per_block": out_bytes / (n_streams * nb)},
-         "roofline": {"bound": "hbm", "kernel": "ulcb_encode_kernel<2,512,false>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                      "algorithmic_bytes_per_launch": algo, "launch_ms": ms, "traffic": measured_traffic("encode", n_streams, nb)},
+         "roofline": {"bound": "hbm", "kernel": "ulcb_detect_kernel<2,false> (transient-detector pre-pass) + ulcb_encode_kernel<2,512,false,true>",
+                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                      "algorithmic_bytes_per_step": algo, "step_ms": ms, "kernels": kernels, "traffic": measured_traffic("encode", n_streams, nb)},
          "verified_streams": verify_encode(torch, ctx, capi, rank, n_streams, ns, nb, out, ostride, bb),
-         "gpu_launches": steps}
+         "gpu_launches": int(sum(v["launches_per_step"] for v in kernels.values()) * steps) or steps}
     if with_cpu:
         c = cpu_reference_encode()
         r["cpu_baseline"] = c

@@ -932,6 +932,11 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
         a.wcAll = ctx->dWcAll; a.wcStride = nBlocksAll;
         if (getenv("ULCB_ENC_THREADS")) a.encThreads = atoi(getenv("ULCB_ENC_THREADS"));
     }
+    // The reference adds the Bark-analysis lines one by one in f64 and so does the kernel.  ULCB_ENC_FAST_BANDS=1 switches whole-stream
+    // batches to segmented sums (band sums equal to the last bits of an f64, see the kernel): no extra bitstream flips in the
+    // conformance run, but no gain either while two CTAs per SM hide the chains - kept for shapes with one CTA per SM.
+    static const bool fastEnv = getenv("ULCB_ENC_FAST_BANDS") && atoi(getenv("ULCB_ENC_FAST_BANDS")) != 0;
+    a.exactBands = (!pre || !fastEnv) ? 1 : 0;
     if (prm->mode == ULCB_MODE_ABR_2PASS) {
         // pass 1: analysis only -> block complexities; mean per stream on the device; pass 2: ABR with the per-stream means
         if (ctx->avgCap < nStreams) {

@@ -625,7 +625,7 @@ struct Encoder {
             }
         }
     }
-    __device__ void dct_leaves() {
+    __device__ void dct_leaves(int inX = -1) {                        // inX: -1 = by depth parity, else 1 = X buffers, 0 = T buffers
         for (int Lf = tid; Lf < (CN >> 2); Lf += NTHR) {              // 2*CN/8 leaves
             const int half = CN >> 3;
             int hb = Lf >= half; int q = Lf - (hb ? half : 0);
@@ -634,7 +634,8 @@ struct Encoder {
             int j = find_sub(sm, n);
             const SubInfo &s = sm.sub[j];
             int d = s.lgS - 3, node = (n - s.off) >> 3;
-            float *buf = (hb ? ((d & 1) ? w.TB : w.XB) : ((d & 1) ? w.TA : w.XA)) + pos;
+            const bool useT = inX < 0 ? (d & 1) : !inX;
+            float *buf = (hb ? (useT ? w.TB : w.XB) : (useT ? w.TA : w.XA)) + pos;
             if (node_is_dct4(d, node)) dct4_leaf8(buf); else dct2_leaf8(buf);
         }
     }
@@ -665,10 +666,10 @@ struct Encoder {
     // The same passes for a block that is ONE sub-block (no window switching, the common case): the recursion depth is
     // uniform across the CTA, so buffer parity, node size and the pair index need no per-element sub-block lookup.
     // Identical arithmetic per element.
-    __device__ void dct_down_long(int m, int lgm) {
+    __device__ void dct_down_long(int m, int lgm, bool srcIsX) {
         const int hm = m >> 1, lgH = tb.log2N - 1, d = tb.log2N - lgm;
-        const float *const S0 = (d & 1) ? w.TA : w.XA, *const S1 = (d & 1) ? w.TB : w.XB;
-        float *const D0 = (d & 1) ? w.XA : w.TA, *const D1 = (d & 1) ? w.XB : w.TB;
+        const float *const S0 = srcIsX ? w.XA : w.TA, *const S1 = srcIsX ? w.XB : w.TB;
+        float *const D0 = srcIsX ? w.TA : w.XA, *const D1 = srcIsX ? w.TB : w.XB;
 #pragma unroll 4
         for (int P = tid; P < CN; P += NTHR) {
             const int cc = P >> lgH, r = P & (H - 1);
@@ -723,10 +724,10 @@ struct Encoder {
             dst[i] = o0; dst[qm + i] = o1; dst[hm + i] = o2; dst[hm + qm + i] = o3;
         }
     }
-    __device__ void dct_up_long(int m, int lgm) {
+    __device__ void dct_up_long(int m, int lgm, bool srcIsX) {
         const int hm = m >> 1, lgH = tb.log2N - 1, d = tb.log2N - lgm;
-        const float *const S0 = (d & 1) ? w.XA : w.TA, *const S1 = (d & 1) ? w.XB : w.TB;   // children live at depth d+1
-        float *const D0 = (d & 1) ? w.TA : w.XA, *const D1 = (d & 1) ? w.TB : w.XB;
+        const float *const S0 = srcIsX ? w.XA : w.TA, *const S1 = srcIsX ? w.XB : w.TB;
+        float *const D0 = srcIsX ? w.TA : w.XA, *const D1 = srcIsX ? w.TB : w.XB;
 #pragma unroll 4
         for (int P = tid; P < CN; P += NTHR) {
             const int cc = P >> lgH, r = P & (H - 1);
@@ -783,18 +784,17 @@ struct Encoder {
     __device__ void transform() {
         const int lgN = tb.log2N;
         if (sm.nsub == 1) {
-            if (((lgN - 3) & 3) == 0) {                               // an even number of two-level passes leaves the data where the leaves expect it
-                bool srcIsX = true;
-                for (int lgm = lgN; lgm >= 5; lgm -= 2) { dct_down2_long(lgm, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
-                dct_leaves();                                         // in X: the leaves sit at an even depth
-                wsync<NTHR>();
-                for (int lgm = 5; lgm <= lgN; lgm += 2) { dct_up2_long(lgm, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
-                return;                                               // an even number of passes again: the result is in X
-            }
-            for (int lgm = lgN; lgm >= 4; lgm--) { dct_down_long(1 << lgm, lgm); wsync<NTHR>(); }
-            dct_leaves();
+            // Two recursion levels per pass, down to the 8-point leaves and up again; an odd number of levels leaves one single
+            // pass at node size 16 either side of the leaves.  Every pass reads one buffer pair and writes the other; the number
+            // of passes is even, so the result is back in X.
+            bool srcIsX = true;
+            int lgm = lgN;
+            for (; lgm >= 5; lgm -= 2) { dct_down2_long(lgm, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
+            if (lgm == 4) { dct_down_long(16, 4, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
+            dct_leaves(srcIsX ? 1 : 0);
             wsync<NTHR>();
-            for (int lgm = 4; lgm <= lgN; lgm++) { dct_up_long(1 << lgm, lgm); wsync<NTHR>(); }
+            if (lgm == 4) { dct_up_long(16, 4, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; lgm = 6; } else lgm = 5;
+            for (; lgm <= lgN; lgm += 2) { dct_up2_long(lgm, srcIsX); wsync<NTHR>(); srcIsX = !srcIsX; }
             return;
         }
         for (int lgm = lgN; lgm >= 4; lgm--) { dct_down(1 << lgm, lgm); wsync<NTHR>(); }
@@ -845,8 +845,64 @@ struct Encoder {
         const int lane = tid & 31;
         const int16_t *ev = tb.events + ((sh * 2 + kind) * 2 * ULCB_NBARK) * 2;
         const int16_t *ed = tb.edges + ((sh * 2 + kind) * ULCB_NBARK) * 2;
-        double (*stage)[32] = w.stage[unit];
         double (*lo)[3] = w.lo[unit];
+        if (!args.exactBands) {
+            // Segmented sums.  The reference adds the lines of a unit one by one in f64 (LineSum_t); a dependent f64 add costs
+            // ~30 cycles here and there are n of them.  This path gives every lane a contiguous run of lines, scans the lane
+            // totals and takes the band sums as differences of the prefix sums at the band edges: the same sums, associated
+            // differently - the band sums differ from the reference's in the last bits of an f64, the band levels (rounded to
+            // f32 from there) practically never (conformance).  Opt-in (ULCB_ENC_FAST_BANDS=1); the default is the
+            // sequential chains below.
+            double (*hiS)[3] = reinterpret_cast<double (*)[3]>(w.stage[unit]);   // prefix sums at the band ends (lo takes those at the starts)
+            const int len = (n + 31) >> 5, beg = lane * len, end = (beg + len < n) ? beg + len : n;
+            int e = 0;
+            {                                                             // first edge at or after this lane's first line
+                int lo_ = 0, hi_ = 2 * ULCB_NBARK;
+                while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (__ldg(&ev[2 * mid]) < beg) lo_ = mid + 1; else hi_ = mid; }
+                e = lo_;
+            }
+            const int e0 = e;
+            int pe = e < 2 * ULCB_NBARK ? __ldg(&ev[2 * e]) : 0x7fffffff;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            auto edges_at = [&](int t) {
+                while (pe == t) {
+                    const int code = __ldg(&ev[2 * e + 1]);
+                    double *dst = (code & 0x80) ? hiS[code & 0x7F] : lo[code & 0x7F];
+                    dst[0] = a0; dst[1] = a1; dst[2] = a2;                // relative to the lane's first line; the base comes below
+                    e++;
+                    pe = e < 2 * ULCB_NBARK ? __ldg(&ev[2 * e]) : 0x7fffffff;
+                }
+            };
+            if (beg < n) {
+                for (int t = beg; t < end; t++) {
+                    edges_at(t);
+                    const double X = (double)v[t], L = (double)lg[t];
+                    a0 += L; a1 += L * X; a2 += X;
+                }
+                if (end == n) edges_at(n);                                // the line past the end sees the totals
+            }
+            const int e1 = e;
+            double b0 = a0, b1 = a1, b2 = a2;                             // inclusive scan over the lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double u0 = __shfl_up_sync(0xffffffffu, b0, d), u1 = __shfl_up_sync(0xffffffffu, b1, d), u2 = __shfl_up_sync(0xffffffffu, b2, d);
+                if (lane >= d) { b0 += u0; b1 += u1; b2 += u2; }
+            }
+            b0 = __shfl_up_sync(0xffffffffu, b0, 1); b1 = __shfl_up_sync(0xffffffffu, b1, 1); b2 = __shfl_up_sync(0xffffffffu, b2, 1);
+            if (lane == 0) { b0 = b1 = b2 = 0.0; }                        // sum of the lanes before this one
+            for (int q = e0; q < e1; q++) {
+                const int code = __ldg(&ev[2 * q + 1]);
+                double *dst = (code & 0x80) ? hiS[code & 0x7F] : lo[code & 0x7F];
+                dst[0] += b0; dst[1] += b1; dst[2] += b2;
+            }
+            __syncwarp();
+            if (lane < ULCB_NBARK) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) lo[lane][q] = hiS[lane][q] - lo[lane][q];
+            }
+            __syncwarp();
+        } else {
+        double (*stage)[32] = w.stage[unit];
         const int src = lane < 3 ? lane : 0;
         double acc = 0.0;
         // The 2*NBARK band-edge events (position-sorted) live two per lane.  Lanes 0..2 run the three dependent DADD
@@ -896,6 +952,7 @@ struct Encoder {
         __syncwarp();
         events_in(n);
         __syncwarp();
+        }
         // band levels: lanes 0..24; a band without energy inherits the previous band's level
         float level = 0.0f; bool ok = false;
         if (lane < ULCB_NBARK) {

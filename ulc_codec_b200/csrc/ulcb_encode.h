@@ -75,6 +75,7 @@ struct UlcbEncodeArgs {
     const int32_t  *wcAll;             // [stream][wcStride] transient-detector decisions from ulcb_detect_launch; nullptr = the
     uint64_t        wcStride;          //   encode kernel runs the detector itself (one warp beside the workers)
     int             encThreads;        // with wcAll: 256 / 512 worker threads per CTA, 0 = by block size
+    int             exactBands;        // 1 = the Bark analysis adds its lines one by one like the reference (LineSum_t); 0 = segmented sums
     // test taps (nullable), [stream][nBlocksAll][nChan*N] / [..][N/2]
     float          *dbgCoefs;
     float          *dbgKeys;
