@@ -705,6 +705,38 @@ struct Encoder {
                 hi = (i & 1) ? (q - p) : (p - q);
             } else { lo = a + b; hi = a - b; }                        // Fourier_DCT2_Template.h:24-40
         };
+        if (((H >> 1) % NTHR) == 0) {
+            // The quarter-pairs of one (buffer, channel) are a multiple of the thread count: a thread meets the same node, the same
+            // pair and the same rotors in every (buffer, channel), so all of that is set up once.  The lower child of any node is a
+            // DCT-II; the upper one is a DCT-IV exactly when the node itself is a DCT-II.
+            for (int r = tid; r < (H >> 1); r += NTHR) {
+                const int node = r >> (lgm - 2), i = r & (qm - 1), i2 = hm - 1 - i;
+                const bool t0 = node_is_dct4(d, node);
+                float2 r0 = make_float2(0.f, 0.f), r1 = r0, rU = r0;
+                if (t0) { r0 = __ldg(&tb.rot[hm + i]); r1 = __ldg(&tb.rot[hm + i2]); }
+                else rU = __ldg(&tb.rot[qm + i]);
+                const int offn = node << lgm;
+                const bool odd = i & 1;                               // i2 = hm-1-i has the opposite parity
+#pragma unroll 2
+                for (int cc = 0; cc < 2 * nch(); cc++) {
+                    const bool hb = cc >= nch();
+                    const int off = (hb ? cc - nch() : cc) * N + offn;
+                    const float *src = (hb ? S1 : S0) + off;
+                    float *dst = (hb ? D1 : D0) + off;
+                    const float a0 = src[i], b0 = src[m - 1 - i], a1 = src[i2], b1 = src[hm + i];
+                    float lo0, hi0, lo1, hi1, o0, o1, o2, o3;
+                    if (t0) {                                         // Fourier_DCT4_Template.h:49-68
+                        lo0 = r0.x * a0 + r0.y * b0; { const float p = r0.y * a0, q = r0.x * b0; hi0 = odd ? (q - p) : (p - q); }
+                        lo1 = r1.x * a1 + r1.y * b1; { const float p = r1.y * a1, q = r1.x * b1; hi1 = odd ? (p - q) : (q - p); }
+                    } else { lo0 = a0 + b0; hi0 = a0 - b0; lo1 = a1 + b1; hi1 = a1 - b1; }     // Fourier_DCT2_Template.h:24-40
+                    o0 = lo0 + lo1; o1 = lo0 - lo1;
+                    if (!t0) { o2 = rU.x * hi0 + rU.y * hi1; const float p = rU.y * hi0, q = rU.x * hi1; o3 = odd ? (q - p) : (p - q); }
+                    else { o2 = hi0 + hi1; o3 = hi0 - hi1; }
+                    dst[i] = o0; dst[qm + i] = o1; dst[hm + i] = o2; dst[hm + qm + i] = o3;
+                }
+            }
+            return;
+        }
 #pragma unroll 2
         for (int Q = tid; Q < (CN >> 1); Q += NTHR) {
             const int cc = Q >> (lgH - 1), r = Q & ((H >> 1) - 1);
@@ -758,6 +790,34 @@ struct Encoder {
         const int m = 1 << lgm, hm = m >> 1, qm = m >> 2, lgH = tb.log2N - 1, d = tb.log2N - lgm;
         const float *const S0 = srcIsX ? w.XA : w.TA, *const S1 = srcIsX ? w.XB : w.TB;
         float *const D0 = srcIsX ? w.TA : w.XA, *const D1 = srcIsX ? w.TB : w.XB;
+        if (((H >> 1) % NTHR) == 0) {                                  // as in dct_down2_long: node and position are the thread's own
+            for (int r = tid; r < (H >> 1); r += NTHR) {
+                const int node = r >> (lgm - 2), k = r & (qm - 1);
+                const bool t0 = node_is_dct4(d, node), first = k == 0, last = k == qm - 1;
+                const int offn = node << lgm;
+#pragma unroll 2
+                for (int cc = 0; cc < 2 * nch(); cc++) {
+                    const bool hb = cc >= nch();
+                    const int off = (hb ? cc - nch() : cc) * N + offn;
+                    const float *AA = (hb ? S1 : S0) + off, *AB = AA + qm, *BA = AA + hm, *BB = BA + qm;
+                    float4 o;
+                    const float ab = AB[k], bbr = BB[qm - 1 - k];
+                    if (t0) {
+                        o.x = first ? AA[0] : AA[k] - BA[qm - k];
+                        o.y = ab + bbr;
+                        o.z = ab - bbr;
+                        o.w = last ? BA[0] : AA[k + 1] + BA[qm - 1 - k];
+                    } else {
+                        o.x = AA[k];
+                        o.y = first ? BA[0] : BA[k] - BB[qm - k];
+                        o.z = ab;
+                        o.w = last ? BB[0] : BA[k + 1] + bbr;
+                    }
+                    *reinterpret_cast<float4 *>((hb ? D1 : D0) + off + 4 * k) = o;
+                }
+            }
+            return;
+        }
 #pragma unroll 2
         for (int Q = tid; Q < (CN >> 1); Q += NTHR) {
             const int cc = Q >> (lgH - 1), r = Q & ((H >> 1) - 1);
