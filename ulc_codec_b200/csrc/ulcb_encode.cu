@@ -1721,6 +1721,10 @@ __global__ void __launch_bounds__(PRE ? NTHR : NTHR + 32, PRE ? (NTHR == 256 ? 4
             } else {
                 enc.begin_block(__ldg(args.wcAll + (size_t)stream * args.wcStride + b));
                 TICK(10);
+                {   // the next block folds input block b, which nothing has touched since the detector pre-pass: ask for its lines now
+                    const long long lo = (long long)b * N * NCH * (long long)elem, hi = min((long long)(b + 1) * N, nSamples) * NCH * (long long)elem;
+                    for (long long o = lo + 128ll * tid; o < hi; o += 128ll * NTHR) asm volatile("prefetch.global.L2 [%0];" ::"l"(pcm + o));
+                }
                 enc.fold_pre(b, pcm, nSamples);
             }
             wsync<NTHR>();
