@@ -148,57 +148,52 @@ __device__ __forceinline__ bool node_is_dct4(int d, int node) {   // root = DCT-
 }
 
 // The CTA is NTHR worker threads + one extra warp that runs the transient detector one block ahead.
-// Workers synchronise among themselves on named barrier 1; barrier 0 joins everybody once per block.
+// Workers synchronise among themselves on named barrier 1; named barrier 2 joins everybody once per block (the detector warp
+// arrives from its own loop, so this one is the unaligned barrier.sync: bar.sync promises one call site for all its threads).
 // (bar.sync is warp-aligned: a warp counts as arrived as soon as any of its lanes executes it, so each warp is
 // reconverged explicitly first - single-lane serial sections precede several of these barriers.)
 template <int NTHR> __device__ __forceinline__ void wsync() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory"); }
-template <int NTHR> __device__ __forceinline__ void fsync() { __syncwarp(); asm volatile("bar.sync 0, %0;" ::"n"(NTHR + 32) : "memory"); }
+template <int NTHR> __device__ __forceinline__ void fsync() { __syncwarp(); asm volatile("barrier.sync 2, %0;" ::"n"(NTHR + 32) : "memory"); }
 template <int NTHR, bool PRE> __device__ __forceinline__ void csync() { if (PRE) wsync<NTHR>(); else fsync<NTHR>(); }
 
-// Worker-wide exclusive scans of one int per thread.  `scr` = smem int[NTHR/32 + 2].
+// Worker-wide exclusive scans of one int per thread.  `scr` = smem int[2][20]: the warp totals go to the half `flip` selects and
+// every warp scans them for itself after ONE barrier; consecutive calls alternate halves, so the next call's writes cannot
+// overtake this call's reads (a warp can only get there through the barrier of the call in between).
 template <int NTHR>
-__device__ __forceinline__ int block_excl_sum(int v, int *scr, int &total) {
+__device__ __forceinline__ int block_excl_sum(int v, int *scr, int &flip, int &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = NTHR / 32;
+    int *mine = scr + 20 * flip; flip ^= 1;
     int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) mine[warp] = inc;
     wsync<NTHR>();
-    if (lane == 31) scr[warp] = inc;
-    wsync<NTHR>();
-    if (warp == 0) {
-        int t = lane < NW ? scr[lane] : 0, ti = t;
+    const int t = lane < NW ? mine[lane] : 0;
+    int ti = t;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += u; }
-        if (lane < NW) scr[lane] = ti - t;
-        if (lane == 31) scr[NW] = ti;
-    }
-    wsync<NTHR>();
-    total = scr[NW];
-    return inc - v + scr[warp];
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += u; }
+    total = __shfl_sync(0xffffffffu, ti, 31);
+    return inc - v + __shfl_sync(0xffffffffu, ti - t, warp);
 }
 template <int NTHR>
-__device__ __forceinline__ int block_excl_max(int v, int *scr) {     // v >= 0; identity 0
+__device__ __forceinline__ int block_excl_max(int v, int *scr, int &flip) {     // v >= 0; identity 0
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = NTHR / 32;
+    int *mine = scr + 20 * flip; flip ^= 1;
     int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, t); }
     int exl = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) exl = 0;
+    if (lane == 31) mine[warp] = inc;
     wsync<NTHR>();
-    if (lane == 31) scr[warp] = inc;
-    wsync<NTHR>();
-    if (warp == 0) {
-        int t = lane < NW ? scr[lane] : 0, ti = t;
+    int ti = lane < NW ? mine[lane] : 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti = max(ti, u); }
-        int te = __shfl_up_sync(0xffffffffu, ti, 1);
-        if (lane == 0) te = 0;
-        if (lane < NW) scr[lane] = te;
-    }
-    wsync<NTHR>();
-    return max(exl, scr[warp]);
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti = max(ti, u); }
+    int te = __shfl_up_sync(0xffffffffu, ti, 1);                       // max over the warps before `lane`
+    if (lane == 0) te = 0;
+    return max(exl, __shfl_sync(0xffffffffu, te, warp));
 }
 
 // ---- pointers into the per-CTA work area ------------------------------------------------------------
@@ -413,6 +408,7 @@ struct Encoder {
     EncSmall &sm;
     Work w;
     const int nchRt, N, CN, H, tid;
+    int scanFlip = 0;            // which half of sm.scan the next worker-wide scan uses
     __device__ __forceinline__ int nch() const { return NCHT ? NCHT : nchRt; }
     __device__ Encoder(const UlcbEncodeArgs &a, EncSmall &s, const Work &wk)
         : args(a), tb(a.tb), sm(s), w(wk), nchRt(a.nChan), N(a.tb.N), CN((NCHT ? NCHT : a.nChan) * a.tb.N), H(a.tb.N >> 1), tid(threadIdx.x) {}
@@ -1132,7 +1128,7 @@ struct Encoder {
             int loc = 0;
 #pragma unroll
             for (int q = 0; q < 16; q++) loc += w.cnt[tid * 16 + q];
-            int tot, base = block_excl_sum<NTHR>(loc, sm.scan, tot);
+            int tot, base = block_excl_sum<NTHR>(loc, sm.scan, scanFlip, tot);
 #pragma unroll
             for (int q = 0; q < 16; q++) { int t = w.cnt[tid * 16 + q]; w.cnt[tid * 16 + q] = (uint16_t)base; base += t; }
             wsync<NTHR>();
@@ -1167,34 +1163,35 @@ struct Encoder {
         uint32_t key[MAXE];
 #pragma unroll
         for (int e = 0; e < MAXE; e++) key[e] = e < E ? uk[i0 + e] : 0xffffffffu;
-        int *hist = reinterpret_cast<int *>(w.cnt);                     // 256 bins
+        int *hist = reinterpret_cast<int *>(w.cnt);                     // 4 passes x 256 bins, cleared together
         uint32_t prefix = 0, pmask = 0;
         int need = nOut;                                                 // keys still to take among those matching the prefix
         if (nOut > 0) {
-            for (int shift = 24; shift >= 0; shift -= 8) {
-                if (tid < 256) hist[tid] = 0;
-                wsync<NTHR>();
+            for (int i = tid; i < 4 * 256; i += NTHR) hist[i] = 0;
+            wsync<NTHR>();
+            const int lane = tid & 31;
+            for (int shift = 24; shift >= 0; shift -= 8, hist += 256) {
 #pragma unroll
                 for (int e = 0; e < MAXE; e++)
                     if (e < E && (key[e] & pmask) == prefix) atomicAdd(&hist[(key[e] >> shift) & 255], 1);
                 wsync<NTHR>();
-                if (tid < 32) {
-                    int c[8], s = 0;
+                // every warp finds the bin that holds the need-th key for itself: no hand-off, one barrier per pass
+                int c[8], sum = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) { c[q] = hist[tid * 8 + q]; s += c[q]; }
-                    int inc = s;
+                for (int q = 0; q < 8; q++) { c[q] = hist[lane * 8 + q]; sum += c[q]; }
+                int inc = sum;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (tid >= d) inc += t; }
-                    const int exc = inc - s;
-                    if (exc < need && need <= inc) {                     // exactly one lane: the bin that holds the need-th key
-                        int run = exc, bin = tid * 8 + 7;
-                        for (int q = 0; q < 8; q++) { if (need <= run + c[q]) { bin = tid * 8 + q; break; } run += c[q]; }
-                        sm.selBin = bin; sm.selBelow = run;
-                    }
-                }
-                wsync<NTHR>();
-                need -= sm.selBelow;
-                prefix |= (uint32_t)sm.selBin << shift;
+                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+                const int exc = inc - sum;
+                const bool hit = exc < need && need <= inc;             // exactly one lane
+                int run = exc, bin = lane * 8 + 7;
+                if (hit) for (int q = 0; q < 8; q++) { if (need <= run + c[q]) { bin = lane * 8 + q; break; } run += c[q]; }
+                const unsigned who = __ballot_sync(0xffffffffu, hit);
+                const int srcLane = who ? __ffs(who) - 1 : 31;
+                bin = __shfl_sync(0xffffffffu, bin, srcLane);
+                run = __shfl_sync(0xffffffffu, run, srcLane);
+                need -= run;
+                prefix |= (uint32_t)bin << shift;
                 pmask |= 0xffu << shift;
             }
         }
@@ -1202,7 +1199,7 @@ struct Encoder {
         int eq = 0;
 #pragma unroll
         for (int e = 0; e < MAXE; e++) eq += (e < E && key[e] == prefix) ? 1 : 0;
-        int tot, base = block_excl_sum<NTHR>(eq, sm.scan, tot);
+        int tot, base = block_excl_sum<NTHR>(eq, sm.scan, scanFlip, tot);
         wsync<NTHR>();                                                   // every key is in registers: TA may be overwritten
         uint16_t *rank = reinterpret_cast<uint16_t *>(w.TA);
 #pragma unroll
@@ -1242,13 +1239,15 @@ struct Encoder {
         // G1: selection, compaction in index order
         int cntSel = 0;
         for (int e = 0; e < E; e++) { info[i0 + e] = 0; cntSel += (int)rank[i0 + e] < nOut; }
-        int nSel, base = block_excl_sum<NTHR>(cntSel, sm.scan, nSel);
+        int nSel, base = block_excl_sum<NTHR>(cntSel, sm.scan, scanFlip, nSel);
         {
             int b = base;
+            if (E) {                                                  // a unit can only start at a thread's first slot (E divides every sub-block size)
+                const int c = i0 >> tb.log2N, n = i0 & (N - 1);
+                for (int j = 0; j < sm.nsub; j++) if (n == sm.sub[j].off) sm.unitSel[c * sm.nsub + j] = b;
+            }
             for (int e = 0; e < E; e++) {
                 const int i = i0 + e;
-                const int c = i >> tb.log2N, n = i & (N - 1);
-                for (int j = 0; j < sm.nsub; j++) if (n == sm.sub[j].off) sm.unitSel[c * sm.nsub + j] = b;
                 if ((int)rank[i] < nOut) selList[b++] = (uint16_t)i;
             }
             if (tid == 0) sm.unitSel[U] = nSel;
@@ -1343,7 +1342,7 @@ struct Encoder {
                 if (!(fabsf(sc) < 2.5f)) { keptMask |= 1u << e; lastKeptP1 = i + 1; }   // :114
             }
         }
-        const int prevKeptP1 = block_excl_max<NTHR>(lastKeptP1, sm.scan);
+        const int prevKeptP1 = block_excl_max<NTHR>(lastKeptP1, sm.scan, scanFlip);
 
         // unit of this thread's slots (a thread's slots never straddle a sub-block: E divides every sub-block size)
         const int c = i0 >> tb.log2N, nloc = i0 & (N - 1), j = find_sub(sm, nloc), u = c * sm.nsub + j;
@@ -1384,7 +1383,7 @@ struct Encoder {
         else walk(cs, true);
         __syncwarp();
         ETK(27);
-        int total, offs = block_excl_sum<NTHR>(cs.n, sm.scan, total);
+        int total, offs = block_excl_sum<NTHR>(cs.n, sm.scan, scanFlip, total);
         ETK(28);
         const int hdr = (sm.wcCur & 8) ? 2 : 1;
         if (write) {
@@ -1901,9 +1900,9 @@ __device__ __forceinline__ void det_cvt_ms(const DetRaw<NCH, FLT> &r, float *v) 
 
 template <int NCH, bool FLT>
 __global__ void __launch_bounds__(DET_THREADS, 1) ulcb_detect_kernel(UlcbEncodeArgs args, float2 *scrA, float *scrR, int32_t *wcAll, uint64_t wcStride) {
-    extern __shared__ __align__(128) unsigned char smraw[];
+    extern __shared__ __align__(128) unsigned char detsm[];
     // shared memory: three chunk rings (post, pre: float2 rows; block: float rows), the transposition tiles, the segment sums
-    float2 (*ringP)[DET_CHUNK][32] = reinterpret_cast<float2 (*)[DET_CHUNK][32]>(smraw);
+    float2 (*ringP)[DET_CHUNK][32] = reinterpret_cast<float2 (*)[DET_CHUNK][32]>(detsm);
     float2 (*ringQ)[DET_CHUNK][32] = ringP + DET_STAGES;
     float  (*ringE)[DET_CHUNK][32] = reinterpret_cast<float (*)[DET_CHUNK][32]>(ringQ + DET_STAGES);
     float2 (*tile)[32][33] = reinterpret_cast<float2 (*)[32][33]>(ringE + DET_STAGES);        // [DET_EW]
