@@ -49,3 +49,10 @@ def test_encode_three_waves_every_stream_vbr(capi):
 
 def test_encode_three_waves_every_stream_cbr(capi):
     assert wavecheck.check_encode_waves(capi, 450, mode="cbr", rate=96.0) == 450
+
+
+def test_encode_detector_prepass_in_waves(capi):
+    # more streams than one wave of the detector pre-pass takes (one CTA of 32 streams per SM = 4736): the second wave reuses
+    # the scratch of the first and writes its own streams' window controls
+    assert wavecheck.check_encode_waves(capi, 5000, mode="vbr", rate=50.0) == 5000
+

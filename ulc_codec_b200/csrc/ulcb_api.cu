@@ -913,7 +913,7 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
         a.workspace = ctx->encWs; a.wsFloats = per;
     }
     if (pre) {
-        const size_t needScr = ulcb_detect_scratch_bytes(ctx->N, nStreams), needWc = (size_t)nStreams * nBlocksAll;
+        const size_t needScr = ulcb_detect_scratch_bytes(ctx->N, nStreams, ctx->smCount), needWc = (size_t)nStreams * nBlocksAll;
         if (ctx->detScratchCap < needScr) {
             if (ctx->detScratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->detScratch); ctx->detScratch = nullptr; ctx->detScratchCap = 0; }
             CK(ctx, cudaMalloc(&ctx->detScratch, needScr));
@@ -926,9 +926,10 @@ static int encode_device(ULCB_Context *ctx, int nStreams, const void *dPcm, int 
         }
         cudaEvent_t t0 = nullptr, t1 = nullptr;
         if (ctx->timing) { t0 = timing_event(ctx); t1 = timing_event(ctx); cudaEventRecord(t0, ctx->stream); }
-        CK(ctx, ulcb_detect_launch(a, ctx->nChan, ctx->detScratch, ctx->dWcAll, nBlocksAll, ctx->stream));
+        int nl = 0;
+        CK(ctx, ulcb_detect_launch(a, ctx->nChan, ctx->smCount, ctx->detScratch, ctx->dWcAll, nBlocksAll, ctx->stream, &nl));
         if (ctx->timing) { cudaEventRecord(t1, ctx->stream); ctx->spans.push_back({t0, t1, ULCB_KERNEL_ENC_DETECT}); }
-        ctx->launches++;
+        ctx->launches += (uint64_t)nl;
         a.wcAll = ctx->dWcAll; a.wcStride = nBlocksAll;
         if (getenv("ULCB_ENC_THREADS")) a.encThreads = atoi(getenv("ULCB_ENC_THREADS"));
     }

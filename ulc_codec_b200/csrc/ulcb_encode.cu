@@ -1931,7 +1931,7 @@ __device__ __forceinline__ void det_cvt_ms(const DetRaw<NCH, FLT> &r, float *v) 
 }
 
 template <int NCH, bool FLT>
-__global__ void __launch_bounds__(DET_THREADS, 1) ulcb_detect_kernel(UlcbEncodeArgs args, float2 *scrA, float *scrR, int32_t *wcAll, uint64_t wcStride) {
+__global__ void __launch_bounds__(DET_THREADS, 1) ulcb_detect_kernel(UlcbEncodeArgs args, int streamBase, float2 *scrA, float *scrR, int32_t *wcAll, uint64_t wcStride) {
     extern __shared__ __align__(128) unsigned char detsm[];
     // shared memory: three chunk rings (post, pre: float2 rows; block: float rows), the transposition tiles, the segment sums
     float2 (*ringP)[DET_CHUNK][32] = reinterpret_cast<float2 (*)[DET_CHUNK][32]>(detsm);
@@ -1942,7 +1942,7 @@ __global__ void __launch_bounds__(DET_THREADS, 1) ulcb_detect_kernel(UlcbEncodeA
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(segs + 32);              // [3][DET_STAGES]
     const UlcbEncTables &tb = args.tb;
     const int N = tb.N, H = N >> 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s0 = blockIdx.x * 32, sMine = s0 + lane;
+    const int s0 = streamBase + blockIdx.x * 32, sMine = s0 + lane;   // scratch is per CTA of this launch, streams are absolute
     const bool live = sMine < args.nStreams;
     const int nbAll = args.nBlocksAll;
     const int nbMine = live ? (args.nBlocks ? min((int)args.nBlocks[sMine], nbAll) : nbAll) : 0;
@@ -2218,19 +2218,30 @@ bool ulcb_detect_supported(int N, int nChan) { return (nChan == 1 || nChan == 2)
 // with the window controls precomputed the encode kernel keeps X / T, the line buffers and one scratch region in shared memory
 // when they fit; larger blocks keep X / T in the global workspace
 bool ulcb_encode_pre_uses_global_ws(int N, int nChan) { return ulcb_encode_smem_bytes(N, nChan, ulcb_encode_threads(N, nChan), false, true) > 227 * 1024; }
-static size_t det_a_bytes(int N, int nStreams) { return sizeof(float2) * (size_t)((nStreams + 31) / 32) * 3 * N * 32; }
-size_t ulcb_detect_scratch_bytes(int N, int nStreams) { return det_a_bytes(N, nStreams) + sizeof(float) * (size_t)((nStreams + 31) / 32) * 2 * N * 32; }
-cudaError_t ulcb_detect_launch(const UlcbEncodeArgs &args, int nChan, void *scratch, int32_t *wcAll, uint64_t wcStride, cudaStream_t stream) {
+// The pre-pass runs in waves of one CTA (32 streams) per SM: a launch is bound by the serial walk over the blocks, not by how many
+// of the SMs it fills, and the scratch (65 KB per stream at N = 2048) stays bounded however many streams a call brings.
+static int det_wave_ctas(int nStreams, int smCount) { const int c = (nStreams + 31) / 32; return c < smCount ? c : smCount; }
+static size_t det_a_bytes(int N, int ctas) { return sizeof(float2) * (size_t)ctas * 3 * N * 32; }
+size_t ulcb_detect_scratch_bytes(int N, int nStreams, int smCount) {
+    const int ctas = det_wave_ctas(nStreams, smCount);
+    return det_a_bytes(N, ctas) + sizeof(float) * (size_t)ctas * 2 * N * 32;
+}
+cudaError_t ulcb_detect_launch(const UlcbEncodeArgs &args, int nChan, int smCount, void *scratch, int32_t *wcAll, uint64_t wcStride, cudaStream_t stream, int *launches) {
     if (!ulcb_detect_supported(args.tb.N, nChan) || args.state) return cudaErrorInvalidValue;
-    void (*k)(UlcbEncodeArgs, float2 *, float *, int32_t *, uint64_t) =
+    void (*k)(UlcbEncodeArgs, int, float2 *, float *, int32_t *, uint64_t) =
         nChan == 2 ? (args.pcmFloat ? ulcb_detect_kernel<2, true> : ulcb_detect_kernel<2, false>)
                    : (args.pcmFloat ? ulcb_detect_kernel<1, true> : ulcb_detect_kernel<1, false>);
     const size_t smem = (sizeof(float2) * 2 + sizeof(float)) * DET_STAGES * DET_CHUNK * 32 + sizeof(float2) * DET_EW * 32 * 33 +
                         sizeof(float) * 32 * 33 + sizeof(unsigned long long) * 3 * DET_STAGES + 128;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    const int ctas = det_wave_ctas(args.nStreams, smCount);
     float2 *scrA = reinterpret_cast<float2 *>(scratch);
-    float *scrR = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(scratch) + det_a_bytes(args.tb.N, args.nStreams));
-    k<<<(args.nStreams + 31) / 32, DET_THREADS, smem, stream>>>(args, scrA, scrR, wcAll, wcStride);
+    float *scrR = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(scratch) + det_a_bytes(args.tb.N, ctas));
+    for (int base = 0; base < args.nStreams; base += ctas * 32) {
+        const int left = (args.nStreams - base + 31) / 32;
+        k<<<left < ctas ? left : ctas, DET_THREADS, smem, stream>>>(args, base, scrA, scrR, wcAll, wcStride);
+        if (launches) ++*launches;
+    }
     return cudaGetLastError();
 }

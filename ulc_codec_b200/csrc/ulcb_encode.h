@@ -87,13 +87,15 @@ struct UlcbEncodeArgs {
 };
 
 size_t      ulcb_encode_smem_bytes(int N, int nChan, int nthr, bool globalWs, bool pre = false);
-// Detector pre-pass (ulcEncoder_WindowControl.c:31-239 for every block of every stream, 32 streams per CTA, one lane per stream):
+// Detector pre-pass (ulcEncoder_WindowControl.c:31-239 for every block of every stream, 32 streams per CTA, one lane per stream,
+// waves of one CTA per SM):
 // shapes it takes, its scratch in bytes, and the launch; decisions go to wcAll[stream][wcStride].  The encode launch that
 // follows with args.wcAll set needs no detector warp.
 bool        ulcb_detect_supported(int N, int nChan);
 bool        ulcb_encode_pre_uses_global_ws(int N, int nChan);
-size_t      ulcb_detect_scratch_bytes(int N, int nStreams);
-cudaError_t ulcb_detect_launch(const UlcbEncodeArgs &args, int nChan, void *scratch, int32_t *wcAll, uint64_t wcStride, cudaStream_t stream);
+size_t      ulcb_detect_scratch_bytes(int N, int nStreams, int smCount);
+cudaError_t ulcb_detect_launch(const UlcbEncodeArgs &args, int nChan, int smCount, void *scratch, int32_t *wcAll, uint64_t wcStride, cudaStream_t stream,
+                               int *launches);
 size_t      ulcb_encode_ws_floats(int N, int nChan);
 int         ulcb_encode_threads(int N, int nChan);
 bool        ulcb_encode_uses_global_ws(int N, int nChan);
