@@ -622,6 +622,18 @@ def main():
     ms_per_step, kern_ms, clocks = time_steps(torch, dist, ctx, ext, dev, world, step, args.steps, clock_gpu=local)
     launches = ctx.launches - l0
     ktimes = ctx.kernel_times(reset=True)
+    pipe = ctx.decode_pipeline()
+    ktimes_alone = None
+    if pipe[1] > 0:
+        # the timed region ran the chunked pipeline (kernels of neighbouring chunks side by side on two streams, so their spans overlap
+        # and their sum exceeds the step); the same kernels one at a time, for the per-kernel durations the ncu launch list can be held to
+        ctx.set_decode_pipeline(1, 0)
+        step()
+        ctx.kernel_times(reset=True)
+        for _ in range(args.steps):
+            step()
+        ktimes_alone = ctx.kernel_times(reset=True)
+        ctx.set_decode_pipeline(*pipe)
     ctx.set_kernel_timing(False)
     assert int((batch.d_status != -1).sum().item()) == 0, "decode reported corrupt streams"
     audio_per_step = world * n_streams * BLOCKS_PER_STREAM * N / RATE
@@ -642,6 +654,12 @@ def main():
                            "kernel's summed time per step (CUDA events on the library's stream around every launch), algorithmic bytes are "
                            "the whole step's (bytes in + PCM16 out)",
             "kernels_ms_per_step": per_kernel,
+            **({"pipeline": {"chunks": pipe[0], "overlap": pipe[1],
+                             "note": "ULCB_SetDecodePipeline: upload / walk (overlap 1) and parse (overlap 2) of chunk c+1 on side streams beside the "
+                                     "transform of chunk c; kernels_ms_per_step are the spans inside the timed region (overlapping), "
+                                     "kernels_ms_per_step_alone the same kernels run one at a time (pipeline off, extra untimed pass)"},
+                "kernels_ms_per_step_alone": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                                              for k, v in ktimes_alone.items() if v[1]}} if ktimes_alone else {}),
             "step": {"ms": kern_ms, "achieved": algo_bytes / (kern_ms / 1e3) / 1e9, "frac": algo_bytes / (kern_ms / 1e3) / 1e9 / peak},
             "traffic": measured_traffic("decode", n_streams, BLOCKS_PER_STREAM)}
 
@@ -695,7 +713,9 @@ def main():
                "d2h_bytes_per_step": d2h, "streams_per_gpu": ne, "ms_per_step": dt * 1e3,
                "pcie_gbs": (len(h_data) + d2h) / dt / 1e9, "pcie_ceiling": pcie,
                "api": "ULCB_DecodeStreams (host pointers, pinned; bytes in by H2D copy, PCM out stored by the kernel straight into the pinned "
-                      "buffer over PCIe); e2e_streams streams per GPU = the pinned output that is reasonable to page-lock (stated in streams_per_gpu)"}
+                      "buffer over PCIe); e2e_streams streams per GPU = the pinned output that is reasonable to page-lock (stated in streams_per_gpu)",
+               "pipeline": "library default for host-pointer calls (ULCB_SetDecodePipeline, chunks 0 = automatic): 16 chunks of streams, the upload, "
+                           "token-length walk and parse of chunk c+1 on side CUDA streams beside the transform of chunk c, whose stores wait for PCIe"}
         if not args.no_extra and rank == 0 and world == 1:
             # pageable caller buffers: staged through device memory and one D2H copy
             npg = min(256, ne)

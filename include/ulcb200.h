@@ -270,6 +270,14 @@ uint64_t ULCB_LaunchCount(const ULCB_Context *ctx);
 int ULCB_SetKernelTiming(ULCB_Context *ctx, int enable);
 int ULCB_KernelTimes(ULCB_Context *ctx, double *ms, uint64_t *count, int reset);
 
+/* Chunked pipeline of the block-parallel decode (BlockSize 2048 stereo batches): the streams of a call are processed in `chunks`
+ * contiguous chunks; overlap 1 = upload (host-pointer entry points) and token-length walk of chunk c+1 on side CUDA streams beside
+ * the transform of chunk c, 2 = its parse too (two arena halves), 0 = no pipelining (the whole call at once, `chunks` ignored).
+ * chunks = 0 (the default) lets the library choose: pipelined for the host-pointer entry points, whose transform waits for PCIe, not
+ * for device-resident input.  The decoded output does not depend on these settings.  Environment: ULCB_BP_CHUNKS / ULCB_BP_OVERLAP. */
+int ULCB_SetDecodePipeline(ULCB_Context *ctx, int chunks, int overlap);
+int ULCB_GetDecodePipeline(const ULCB_Context *ctx, int *chunks, int *overlap);
+
 /* Stage-level test hooks (host pointers; synchronous).  Used by tests/ only. */
 int ULCB_TestDCT4(ULCB_Context *ctx, float *data, int size, int count);
 /* parse + dequantise + noise-fill only: coefs[nBlocks][nChan*blockSize], blockBits[nBlocks] for ONE stream */

@@ -33,6 +33,15 @@ def test_decode_three_waves_with_block_index(capi, fmt):
     assert wavecheck.check_decode_waves(capi, 2300, fmt=fmt, with_index=True) == 2300
 
 
+@pytest.mark.parametrize("chunks,overlap,with_index", [(4, 1, False), (5, 2, False), (3, 2, True), (1, 0, False), (0, 0, False)])
+def test_decode_chunked_pipeline_every_stream(capi, chunks, overlap, with_index):
+    """ULCB_SetDecodePipeline: the call's streams in contiguous chunks, upload + walk (overlap 1) and parse (overlap 2, two arena
+    halves) of the next chunk on side streams beside the transform of the current one.  Ragged chunk sizes (2300 / 4, / 5, / 3),
+    more chunks than arena halves, every stream against the oracle; (1, 0) = pipelining off, (0, 0) = the library's choice (16 chunks
+    with overlap 2 for these host-pointer calls)."""
+    assert wavecheck.check_decode_waves(capi, 2300, fmt="pcm16", with_index=with_index, pipeline=(chunks, overlap)) == 2300
+
+
 @pytest.mark.parametrize("env", [{"ULCB_DECODE_GENERIC": "1"}, {"ULCB_DECODE_WS": "1"}])
 def test_decode_waves_other_kernels(env):
     """The kernels ulcb_decode_launch does not pick by default for this shape (selected through the environment)."""

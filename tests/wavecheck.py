@@ -49,7 +49,7 @@ def slot_order(n_slots: int, n_distinct: int):
 
 
 def check_decode_waves(capi, n_slots: int = 2300, n_distinct: int = 41, min_blocks: int = 5, max_blocks: int = 7,
-                       fmt: str = "pcm16", with_index: bool = False):
+                       fmt: str = "pcm16", with_index: bool = False, pipeline=None):
     """Decode n_slots streams in ONE call and compare every one with the oracle.  Returns the number of streams verified."""
     streams, nbs, bbs = distinct_streams(n_distinct, min_blocks, max_blocks)
     refs = []
@@ -62,6 +62,8 @@ def check_decode_waves(capi, n_slots: int = 2300, n_distinct: int = 41, min_bloc
     nblk = [nbs[o] for o in order]
     with capi.Context(44100, NCH, N, max_blocks=max_blocks) as ctx:
         kw = {}
+        if pipeline:
+            ctx.set_decode_pipeline(*pipeline)                     # (chunks, overlap): chunked upload / walk / parse beside the transform
         if with_index:
             kw["block_bytes"] = [bbs[o] for o in order]
         pcm, status, bits = ctx.decode_streams(batch, nblk, fmt=fmt, want_bits=True, **kw)

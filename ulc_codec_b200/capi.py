@@ -24,7 +24,7 @@ EXPORTS = (
     "ULCB_ContextCreate", "ULCB_ContextDestroy", "ULCB_LastCudaError", "ULCB_ErrorString",
     "ULCB_MaxBlockBytes", "ULCB_DecodeStreamsDevice", "ULCB_DecodeStreams", "ULCB_DecodeStreamsIndexedDevice",
     "ULCB_DecodeStreamsIndexed", "ULCB_IndexStreams", "ULCB_Sync", "ULCB_Stream",
-    "ULCB_LaunchCount", "ULCB_SetKernelTiming", "ULCB_KernelTimes", "ULCB_TestDCT4", "ULCB_TestParse",
+    "ULCB_LaunchCount", "ULCB_SetKernelTiming", "ULCB_KernelTimes", "ULCB_SetDecodePipeline", "ULCB_GetDecodePipeline", "ULCB_TestDCT4", "ULCB_TestParse",
     "ULC_EncoderState_Init", "ULC_EncoderState_Destroy", "ULC_EncodeBlock_CBR", "ULC_EncodeBlock_ABR", "ULC_EncodeBlock_VBR",
     "ULCB_BlocksForSamples", "ULCB_EncodeStreamsDevice", "ULCB_EncodeStreams", "ULCB_TestEncode",
     "ULCB_GenerateCorpusDevice", "ULCB_ConvertSamplesDevice", "ULCB_GetAvgComplexity",
@@ -93,6 +93,8 @@ def load():
     L.ULCB_LaunchCount.restype = u64
     L.ULCB_SetKernelTiming.argtypes = [vp, i32]
     L.ULCB_KernelTimes.argtypes = [vp, vp, vp, i32]
+    L.ULCB_SetDecodePipeline.argtypes = [vp, i32, i32]
+    L.ULCB_GetDecodePipeline.argtypes = [vp, vp, vp]
     L.ULCB_TestDCT4.argtypes = [vp, vp, i32, i32]
     L.ULCB_TestParse.argtypes = [vp, vp, u64, u32, vp, vp]
     L.ULC_DecoderState_Init.argtypes = [C.POINTER(ULC_DecoderState_t)]
@@ -179,6 +181,16 @@ class Context:
 
     def set_kernel_timing(self, enable: bool = True):
         _check(self.L, self.h, self.L.ULCB_SetKernelTiming(self.h, int(enable)), "ULCB_SetKernelTiming")
+
+    def set_decode_pipeline(self, chunks: int, overlap: int):
+        """Chunked pipeline of the block-parallel decode (ULCB_SetDecodePipeline); the output does not depend on it."""
+        _check(self.L, self.h, self.L.ULCB_SetDecodePipeline(self.h, int(chunks), int(overlap)), "ULCB_SetDecodePipeline")
+
+    def decode_pipeline(self) -> tuple:
+        """(chunks, overlap) in effect (ULCB_GetDecodePipeline)."""
+        ch, ov = C.c_int(0), C.c_int(0)
+        _check(self.L, self.h, self.L.ULCB_GetDecodePipeline(self.h, C.byref(ch), C.byref(ov)), "ULCB_GetDecodePipeline")
+        return ch.value, ov.value
 
     def kernel_times(self, reset: bool = True) -> dict:
         """{kind: (milliseconds, launches)} accumulated since the last reset (ULCB_KernelTimes; synchronises the stream)."""

@@ -24,6 +24,15 @@ static inline bool own_end_event(int kind) {
     return kind == ULCB_KERNEL_BP_WALK || kind == ULCB_KERNEL_BP_INDEX || kind == ULCB_KERNEL_ENC_DETECT || kind == ULCB_KERNEL_ENC_ENCODE;
 }
 
+// chunked decode pipeline defaults (ULCB_SetDecodePipeline): chunks 0 = automatic - 16 chunks with overlap 2 for the host-pointer
+// entry points (their transform waits for PCIe: upload, walk and parse of the next chunks hide behind it, 481 -> 435 ms per 2048 x
+// 60 s streams), none for device-resident input (there the side-stream kernels take shared memory and issue slots from the transform
+// and a walk costs ~13 ms however few streams it covers: 128 -> 165 ms at 4 chunks).  profiles/README.md, r02i.
+#define ULCB_BP_CHUNKS_DEFAULT 0
+#define ULCB_BP_OVERLAP_DEFAULT 0
+#define ULCB_BP_AUTO_HOST_CHUNKS 16
+#define ULCB_BP_AUTO_HOST_OVERLAP 2
+
 struct ULCB_Context {
     int device = 0, rateHz = 0, nChan = 0, N = 0;
     uint32_t maxBlocks = 0;
@@ -52,9 +61,14 @@ struct ULCB_Context {
     void *bpArena = nullptr; size_t bpArenaCap = 0;
     size_t bpPlanCap = 0;               // bytes of arena a wave may plan for
     void *hPlan = nullptr;   size_t hPlanCap = 0;   // pinned: stream offsets / block counts read back to plan the waves
+    // chunked pipeline of the block-parallel decode (ULCB_SetDecodePipeline): upload + walk (+ parse) of chunk c+1 run on
+    // high-priority side streams beside the transform of chunk c
+    int bpChunks = 0, bpOverlap = 0;              // chunks 0 = automatic
+    cudaStream_t bpFront = nullptr, bpCopy = nullptr;
+    std::vector<cudaEvent_t> bpSyncEv;
     // per-kernel timing (ULCB_SetKernelTiming): event pairs recorded around the launches, resolved by ULCB_KernelTimes
     bool timing = false;
-    struct TimedSpan { cudaEvent_t a, b; int kind; };
+    struct TimedSpan { cudaEvent_t a, b; int kind; bool ownB; };
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> evPool;
     double kernMs[ULCB_KERNEL_KINDS] = {}; uint64_t kernCount[ULCB_KERNEL_KINDS] = {};
@@ -374,6 +388,10 @@ int ULCB_ContextCreate(ULCB_Context **out, int device, int rateHz, int nChan, in
     int rc = ULCB_OK;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) rc = ULCB_E_CUDA;
     ctx->smCount = prop.multiProcessorCount;
+    ctx->bpChunks = getenv("ULCB_BP_CHUNKS") ? atoi(getenv("ULCB_BP_CHUNKS")) : ULCB_BP_CHUNKS_DEFAULT;
+    ctx->bpOverlap = getenv("ULCB_BP_OVERLAP") ? atoi(getenv("ULCB_BP_OVERLAP")) : ULCB_BP_OVERLAP_DEFAULT;
+    if (ctx->bpChunks < 0 || ctx->bpChunks > 1024) ctx->bpChunks = 0;
+    if (ctx->bpOverlap < 0 || ctx->bpOverlap > 2) ctx->bpOverlap = 0;
     if (rc == ULCB_OK) rc = build_tables(ctx);
     if (rc == ULCB_OK) rc = build_enc_tables(ctx);
     if (rc != ULCB_OK) { ULCB_ContextDestroy(ctx); return rc; }
@@ -401,8 +419,11 @@ void ULCB_ContextDestroy(ULCB_Context *ctx) {
     if (ctx->dCxScratch) cudaFree(ctx->dCxScratch);
     if (ctx->detScratch) cudaFree(ctx->detScratch);
     if (ctx->dWcAll) cudaFree(ctx->dWcAll);
-    for (auto &sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (own_end_event(sp.kind)) cudaEventDestroy(sp.b); }
+    for (auto &sp : ctx->spans) { if (sp.a) cudaEventDestroy(sp.a); if (own_end_event(sp.kind) || sp.ownB) cudaEventDestroy(sp.b); }
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->bpSyncEv) cudaEventDestroy(e);
+    if (ctx->bpFront) cudaStreamDestroy(ctx->bpFront);
+    if (ctx->bpCopy) cudaStreamDestroy(ctx->bpCopy);
     delete ctx;
 }
 
@@ -421,7 +442,7 @@ int ULCB_Sync(ULCB_Context *ctx) {
 static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs, const uint32_t *dNBlocks,
                      uint32_t nBlocksAll, const uint32_t *dBlockBytes, uint64_t blockBytesStride, void *dOut, uint64_t outStrideElems,
                      int format, int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride, float *dbgCoefs,
-                     const uint64_t *hOffs, const uint32_t *hNBlocks) {
+                     const uint64_t *hOffs, const uint32_t *hNBlocks, const uint8_t *hBytes = nullptr) {
     int rc;
     if (!hOffs || (dNBlocks && !hNBlocks)) {
         const size_t need = sizeof(uint64_t) * (nStreams + 1) + sizeof(uint32_t) * nStreams;
@@ -464,6 +485,98 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
     a.blockBytes = dBlockBytes; a.blockBytesStride = blockBytesStride;
     a.out = dOut; a.outStride = outStrideElems; a.status = dStatus; a.blockBits = dBlockBits; a.bitsStride = bitsStride;
     a.dbgCoefs = dbgCoefs;
+    // ---- chunked pipeline (ULCB_SetDecodePipeline): the streams of the call in nChunks contiguous chunks; the upload (host-pointer
+    // entry points) and the walk of chunk c+1 - with overlap 2 its parse and scan too, into the other half of the arena - run on
+    // high-priority side streams beside the transform of chunk c.  The walk is one latency-bound lane per stream and the transform
+    // leaves half of the issue slots idle (and, storing into a pinned host buffer, waits for PCIe): side by side they cost less
+    // than one after the other.  Results do not depend on the chunking: every stream is decoded by the same kernels.
+    int nChunks = ctx->bpChunks, overlap = ctx->bpOverlap;
+    if (nChunks == 0) { nChunks = hBytes ? ULCB_BP_AUTO_HOST_CHUNKS : 1; overlap = hBytes ? ULCB_BP_AUTO_HOST_OVERLAP : 0; }
+    if (overlap == 0) nChunks = 1;
+    if (nChunks > nStreams / 64) nChunks = nStreams / 64;
+    const int nBuf = overlap >= 2 ? 2 : 1;
+    size_t chunkArena = 0;
+    std::vector<int> cb;                                           // chunk boundaries
+    while (nChunks > 1) {
+        cb.assign(nChunks + 1, 0);
+        for (int c = 0; c <= nChunks; c++) cb[c] = (int)((long long)nStreams * c / nChunks);
+        chunkArena = 0;
+        for (int c = 0; c < nChunks; c++) {
+            const size_t need = ulcb_decode_bp_arena_bytes(hOffs[cb[c + 1]] - hOffs[cb[c]], cb[c + 1] - cb[c], (int)maxBlk);
+            if (need > chunkArena) chunkArena = need;
+        }
+        chunkArena = (chunkArena + 255) & ~(size_t)255;
+        if (chunkArena * nBuf <= cap) break;
+        nChunks = nChunks * 2 <= nStreams ? nChunks * 2 : 1;      // smaller chunks until one fits; else the serial waves below
+    }
+    if (nChunks > 1) {
+        if (!ctx->bpFront) {
+            int lo = 0, hi = 0;
+            CK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(ctx, cudaStreamCreateWithPriority(&ctx->bpFront, cudaStreamNonBlocking, hi));
+            CK(ctx, cudaStreamCreateWithPriority(&ctx->bpCopy, cudaStreamNonBlocking, hi));
+        }
+        while (ctx->bpSyncEv.size() < (size_t)(3 * nChunks + 1)) {
+            cudaEvent_t e = nullptr;
+            CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->bpSyncEv.push_back(e);
+        }
+        int maxN = 0;
+        for (int c = 0; c < nChunks; c++) if (cb[c + 1] - cb[c] > maxN) maxN = cb[c + 1] - cb[c];
+        const size_t descPer = (sizeof(UlcbBpDesc) * (size_t)maxN * maxBlk + 255) & ~(size_t)255;
+        const size_t badPer = (sizeof(int32_t) * (size_t)maxN + 255) & ~(size_t)255;
+        if ((rc = grow(ctx, &ctx->bpOff, &ctx->bpOffCap, sizeof(uint32_t) * (size_t)nStreams * (maxBlk + 1)))) return rc;
+        if ((rc = grow(ctx, &ctx->bpDesc, &ctx->bpDescCap, descPer * nBuf))) return rc;
+        if ((rc = grow(ctx, &ctx->bpBad, &ctx->bpBadCap, badPer * nBuf))) return rc;
+        if ((rc = grow(ctx, &ctx->bpArena, &ctx->bpArenaCap, chunkArena * nBuf))) return rc;
+        cudaEvent_t *evC = ctx->bpSyncEv.data(), *evF = evC + nChunks, *evT = evF + nChunks, evStart = ctx->bpSyncEv[3 * nChunks];
+        cudaStream_t back = ctx->stream, front = ctx->bpFront, copy = ctx->bpCopy;
+        CK(ctx, cudaEventRecord(evStart, back));                   // the side streams start behind what the caller queued
+        CK(ctx, cudaStreamWaitEvent(front, evStart, 0));
+        if (hBytes) CK(ctx, cudaStreamWaitEvent(copy, evStart, 0));
+        for (int c = 0; c < nChunks; c++) {
+            const int c0 = cb[c], n = cb[c + 1] - c0, buf = c % nBuf;
+            if (hBytes) {
+                CK(ctx, cudaMemcpyAsync(const_cast<uint8_t *>(dBytes) + hOffs[c0], hBytes + hOffs[c0], hOffs[c0 + n] - hOffs[c0],
+                                        cudaMemcpyHostToDevice, copy));
+                CK(ctx, cudaEventRecord(evC[c], copy));
+                CK(ctx, cudaStreamWaitEvent(front, evC[c], 0));
+            }
+            a.s0 = c0; a.nStreams = n; a.base0 = hOffs[c0];
+            a.blkOff = (uint32_t *)ctx->bpOff + (size_t)c0 * (maxBlk + 1);
+            a.desc = (UlcbBpDesc *)((char *)ctx->bpDesc + descPer * buf); a.firstBad = (int32_t *)((char *)ctx->bpBad + badPer * buf);
+            a.arena = (uint8_t *)ctx->bpArena + chunkArena * buf;
+            int nl = 0;
+            cudaEvent_t e0 = nullptr, e1 = nullptr, evA[3] = {nullptr, nullptr, nullptr}, evB[4] = {nullptr, nullptr, nullptr, nullptr};
+            if (ctx->timing) {
+                e0 = timing_event(ctx); e1 = timing_event(ctx);
+                for (auto &e : evA) e = timing_event(ctx);
+                evB[2] = timing_event(ctx); evB[3] = timing_event(ctx);
+                cudaEventRecord(e0, front);
+            }
+            CK(ctx, ulcb_decode_bp_offsets(a, dBlockBytes != nullptr, ctx->smCount, front, &nl));
+            if (ctx->timing) { cudaEventRecord(e1, front); ctx->spans.push_back({e0, e1, dBlockBytes ? ULCB_KERNEL_BP_INDEX : ULCB_KERNEL_BP_WALK}); }
+            if (nBuf == 2) {
+                if (c >= 2) CK(ctx, cudaStreamWaitEvent(front, evT[c - 2], 0));   // this half of the arena is free again
+                CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, front, &nl, ctx->timing ? evA : nullptr, 1));
+            }
+            CK(ctx, cudaEventRecord(evF[c], front));
+            CK(ctx, cudaStreamWaitEvent(back, evF[c], 0));
+            if (nBuf == 1) CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, back, &nl, ctx->timing ? evA : nullptr, 1));
+            CK(ctx, ulcb_decode_bp_launch(a, format == ULCB_FMT_PCM16, back, &nl, ctx->timing ? evB : nullptr, 2));
+            if (nBuf == 2) CK(ctx, cudaEventRecord(evT[c], back));
+            if (ctx->timing) {
+                ctx->spans.push_back({evA[0], evA[1], ULCB_KERNEL_BP_PARSE});
+                ctx->spans.push_back({evA[1], evA[2], ULCB_KERNEL_BP_SCAN});
+                ctx->spans.push_back({evA[2], nullptr, -1});
+                ctx->spans.push_back({evB[2], evB[3], ULCB_KERNEL_BP_TRANSFORM, true});
+            }
+            ctx->launches += (uint64_t)nl;
+        }
+        return ULCB_OK;
+    }
+    if (hBytes) CK(ctx, cudaMemcpyAsync(const_cast<uint8_t *>(dBytes) + hOffs[0], hBytes + hOffs[0], hOffs[nStreams] - hOffs[0],
+                                        cudaMemcpyHostToDevice, ctx->stream));
     {
         // block byte offsets of the whole call at once: the token-length walk of foreign streams is one lane per stream and
         // bound by latency, not by how many streams it walks
@@ -503,12 +616,17 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
     return ULCB_OK;
 }
 
+static bool use_bp(const ULCB_Context *ctx) {
+    static const bool forceSerial = getenv("ULCB_DECODE_GENERIC") != nullptr || getenv("ULCB_DECODE_WS") != nullptr;
+    return !forceSerial && ulcb_decode_bp_supported(ctx->tb, ctx->nChan);
+}
+
 static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, const uint64_t *dStreamOffs,
                          const uint32_t *dNBlocks, uint32_t nBlocksAll, void *dOut, uint64_t outStrideElems,
                          int format, int32_t *dStatus, uint32_t *dBlockBits, uint64_t bitsStride,
                          UlcbStreamState *state, float *statePend, float *dbgCoefs = nullptr,
                          const uint32_t *dBlockBytes = nullptr, uint64_t blockBytesStride = 0,
-                         const uint64_t *hOffs = nullptr, const uint32_t *hNBlocks = nullptr) {
+                         const uint64_t *hOffs = nullptr, const uint32_t *hNBlocks = nullptr, const uint8_t *hBytes = nullptr) {
     if (!ctx || nStreams < 0 || !dBytes || !dStreamOffs || !dOut) return ULCB_E_PARAM;
     if (format != ULCB_FMT_PCM16 && format != ULCB_FMT_FLOAT32) return ULCB_E_PARAM;
     if (nStreams == 0) return ULCB_OK;
@@ -519,10 +637,10 @@ static int decode_device(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes,
     CK(ctx, cudaSetDevice(ctx->device));
     // kernel choice: the block-parallel pipeline where it applies (BlockSize 2048 stereo, whole fresh streams); the
     // stream-serial kernels for every other shape, for carried state (drop-in API), and on request (A/B timing, tests)
-    static const bool forceSerial = getenv("ULCB_DECODE_GENERIC") != nullptr || getenv("ULCB_DECODE_WS") != nullptr;
-    if (!state && !forceSerial && ulcb_decode_bp_supported(ctx->tb, ctx->nChan))
+    if (!state && use_bp(ctx))
         return decode_bp(ctx, nStreams, dBytes, dStreamOffs, dNBlocks, nBlocksAll, dBlockBytes, blockBytesStride, dOut, outStrideElems,
-                         format, dStatus, dBlockBits, bitsStride, dbgCoefs, hOffs, hNBlocks);
+                         format, dStatus, dBlockBits, bitsStride, dbgCoefs, hOffs, hNBlocks, hBytes);
+    if (hBytes) CK(ctx, cudaMemcpyAsync(const_cast<uint8_t *>(dBytes) + hOffs[0], hBytes + hOffs[0], hOffs[nStreams] - hOffs[0], cudaMemcpyHostToDevice, ctx->stream));
     UlcbDecodeArgs a{};
     a.tb = ctx->tb;
     a.nChan = ctx->nChan;
@@ -587,7 +705,7 @@ static int decode_host(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     if (!dOutPtr) { if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, outBytes))) return rc; }
     if ((rc = grow(ctx, &ctx->dAux, &ctx->dAuxCap, auxBytes))) return rc;
     char *aux = (char *)ctx->dAux;
-    CK(ctx, cudaMemcpyAsync(ctx->dIn, bytes, nBytes, cudaMemcpyHostToDevice, ctx->stream));
+    // the payload bytes are uploaded by decode_device: in one copy, or chunk by chunk inside the pipelined block-parallel decode
     CK(ctx, cudaMemsetAsync((char *)ctx->dIn + nBytes, 0, 64, ctx->stream));
     CK(ctx, cudaMemcpyAsync(aux + offOffs, streamOffs, sizeof(uint64_t) * (nStreams + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (nBlocks) CK(ctx, cudaMemcpyAsync(aux + offNb, nBlocks, sizeof(uint32_t) * nStreams, cudaMemcpyHostToDevice, ctx->stream));
@@ -595,7 +713,7 @@ static int decode_host(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     rc = decode_device(ctx, nStreams, (const uint8_t *)ctx->dIn, (const uint64_t *)(aux + offOffs),
                        nBlocks ? (const uint32_t *)(aux + offNb) : nullptr, nBlocksAll, dOutPtr ? dOutPtr : ctx->dOut, outStrideElems, format,
                        (int32_t *)(aux + offSt), blockBits ? (uint32_t *)(aux + offBits) : nullptr, bitsStride, nullptr, nullptr, nullptr,
-                       blockBytes ? (const uint32_t *)(aux + offIdx) : nullptr, blockBytesStride, streamOffs, nBlocks);
+                       blockBytes ? (const uint32_t *)(aux + offIdx) : nullptr, blockBytesStride, streamOffs, nBlocks, bytes);
     if (rc) return rc;
     if (!dOutPtr) CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) CK(ctx, cudaMemcpyAsync(status, aux + offSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
@@ -675,6 +793,19 @@ int ULCB_SetKernelTiming(ULCB_Context *ctx, int enable) {
     return ULCB_OK;
 }
 
+int ULCB_SetDecodePipeline(ULCB_Context *ctx, int chunks, int overlap) {
+    if (!ctx || chunks < 0 || chunks > 1024 || overlap < 0 || overlap > 2) return ULCB_E_PARAM;
+    ctx->bpChunks = chunks; ctx->bpOverlap = overlap;
+    return ULCB_OK;
+}
+
+int ULCB_GetDecodePipeline(const ULCB_Context *ctx, int *chunks, int *overlap) {
+    if (!ctx) return ULCB_E_PARAM;
+    if (chunks) *chunks = ctx->bpChunks;
+    if (overlap) *overlap = ctx->bpOverlap;
+    return ULCB_OK;
+}
+
 int ULCB_KernelTimes(ULCB_Context *ctx, double *ms, uint64_t *count, int reset) {
     if (!ctx) return ULCB_E_PARAM;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -688,7 +819,7 @@ int ULCB_KernelTimes(ULCB_Context *ctx, double *ms, uint64_t *count, int reset) 
     }
     // every event opens exactly one span entry (the last of a chain opens an entry without an end): back to the pool
     for (auto &sp : ctx->spans) ctx->evPool.push_back(sp.a);
-    for (auto &sp : ctx->spans) if (own_end_event(sp.kind)) ctx->evPool.push_back(sp.b);
+    for (auto &sp : ctx->spans) if (own_end_event(sp.kind) || sp.ownB) ctx->evPool.push_back(sp.b);
     ctx->spans.clear();
     for (int k = 0; k < ULCB_KERNEL_KINDS; k++) {
         if (ms) ms[k] = ctx->kernMs[k];

@@ -78,4 +78,4 @@ cudaError_t ulcb_decode_bp_offsets(const UlcbBpArgs &args, bool haveIndex, int s
 // block sizes from the offsets table: sizes[stream][block] = bytes of the block, 0 from the first block that could not be located
 cudaError_t ulcb_decode_bp_sizes(const UlcbBpArgs &args, uint32_t *dSizes, uint64_t sizesStride, int32_t *dStatus, cudaStream_t stream);
 // ev (nullable): four events recorded before parse, after parse, after scan and after transform
-cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, cudaStream_t stream, int *launches, cudaEvent_t *ev = nullptr);
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &args, int pcm16, cudaStream_t stream, int *launches, cudaEvent_t *ev = nullptr, int phases = 3);

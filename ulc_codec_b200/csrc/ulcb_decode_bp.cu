@@ -1258,25 +1258,32 @@ cudaError_t ulcb_decode_bp_sizes(const UlcbBpArgs &a, uint32_t *dSizes, uint64_t
 }
 
 // One wave: parse -> scan -> transform (a.blkOff points at the wave's first stream).
-cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, cudaStream_t stream, int *launches, cudaEvent_t *ev) {
+cudaError_t ulcb_decode_bp_launch(const UlcbBpArgs &a, int pcm16, cudaStream_t stream, int *launches, cudaEvent_t *ev, int phases) {
     if (a.nStreams <= 0 || a.maxBlk <= 0) return cudaSuccess;
-    const int wpc = 4;                                            // warps per CTA of the per-stream kernels
-    const long long nThr = (long long)a.nStreams * a.maxBlk;
-    if (ev) cudaEventRecord(ev[0], stream);
-    bp_parse_kernel<<<(unsigned)((nThr + 127) / 128), 128, 0, stream>>>(a);
-    if (ev) cudaEventRecord(ev[1], stream);
-    bp_scan_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
-    if (ev) cudaEventRecord(ev[2], stream);
-    const int runsPerStream = (a.maxBlk + a.runLen - 1) / a.runLen;
-    const long long grid = (long long)a.nStreams * runsPerStream;
-    if (a.dbgCoefs) {
-        if (pcm16) bp_transform_kernel<true, true><<<(unsigned)grid, 64, 0, stream>>>(a);
-        else       bp_transform_kernel<false, true><<<(unsigned)grid, 64, 0, stream>>>(a);
-    } else {
-        if (pcm16) bp_transform_kernel<true, false><<<(unsigned)grid, 64, 0, stream>>>(a);
-        else       bp_transform_kernel<false, false><<<(unsigned)grid, 64, 0, stream>>>(a);
+    // phases: bit 0 = parse + scan (ev[0..2]), bit 1 = transform (ev[2..3]); the pipelined caller runs them on two streams
+    if (phases & 1) {
+        const int wpc = 4;                                        // warps per CTA of the per-stream kernels
+        const long long nThr = (long long)a.nStreams * a.maxBlk;
+        if (ev) cudaEventRecord(ev[0], stream);
+        bp_parse_kernel<<<(unsigned)((nThr + 127) / 128), 128, 0, stream>>>(a);
+        if (ev) cudaEventRecord(ev[1], stream);
+        bp_scan_kernel<<<(a.nStreams + wpc - 1) / wpc, wpc * 32, 0, stream>>>(a);
+        if (launches) *launches += 2;
     }
-    if (ev) cudaEventRecord(ev[3], stream);
-    if (launches) *launches += 3;
+    if (ev && (phases == 1 || phases == 3)) cudaEventRecord(ev[2], stream);
+    if (phases & 2) {
+        if (ev && phases == 2) cudaEventRecord(ev[2], stream);
+        const int runsPerStream = (a.maxBlk + a.runLen - 1) / a.runLen;
+        const long long grid = (long long)a.nStreams * runsPerStream;
+        if (a.dbgCoefs) {
+            if (pcm16) bp_transform_kernel<true, true><<<(unsigned)grid, 64, 0, stream>>>(a);
+            else       bp_transform_kernel<false, true><<<(unsigned)grid, 64, 0, stream>>>(a);
+        } else {
+            if (pcm16) bp_transform_kernel<true, false><<<(unsigned)grid, 64, 0, stream>>>(a);
+            else       bp_transform_kernel<false, false><<<(unsigned)grid, 64, 0, stream>>>(a);
+        }
+        if (ev) cudaEventRecord(ev[3], stream);
+        if (launches) *launches += 1;
+    }
     return cudaGetLastError();
 }
