@@ -680,6 +680,16 @@ def main():
     if rank == 0 or world > 1:
         pcie = pcie_ceiling(torch, dist, dev, world)
         ne = min(args.e2e_streams, n_streams)
+        # every rank page-locks its own PCM sink (10.6 MB per stream): all ranks together stay within a third of the host memory
+        # that is free now (8 ranks x 2048 streams = 190 GB); every rank takes the same count
+        try:
+            avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable:"))
+            fit = int(avail / 3 / max(1, world) / (stride * 2 + 1.0e6))
+            if world > 1:
+                t = torch.tensor([fit], device=dev, dtype=torch.int64); dist.all_reduce(t, op=dist.ReduceOp.MIN); fit = int(t.item())
+            ne = max(64, min(ne, fit))
+        except (OSError, StopIteration, ValueError):
+            pass
         h_streams = [distinct[o] for o in batch.order[:ne]]
         h_data, h_offs = capi.pack_streams(h_streams)
         pin_in = torch.empty(len(h_data), dtype=torch.uint8).pin_memory()

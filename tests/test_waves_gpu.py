@@ -37,9 +37,16 @@ def test_decode_three_waves_with_block_index(capi, fmt):
 def test_decode_chunked_pipeline_every_stream(capi, chunks, overlap, with_index):
     """ULCB_SetDecodePipeline: the call's streams in contiguous chunks, upload + walk (overlap 1) and parse (overlap 2, two arena
     halves) of the next chunk on side streams beside the transform of the current one.  Ragged chunk sizes (2300 / 4, / 5, / 3),
-    more chunks than arena halves, every stream against the oracle; (1, 0) = pipelining off, (0, 0) = the library's choice (16 chunks
-    with overlap 2 for these host-pointer calls)."""
+    more chunks than arena halves, every stream against the oracle; (1, 0) = pipelining off, (0, 0) = the library's choice (none for these pageable
+    buffers; test_decode_pinned_output_default_pipeline covers the page-locked case)."""
     assert wavecheck.check_decode_waves(capi, 2300, fmt="pcm16", with_index=with_index, pipeline=(chunks, overlap)) == 2300
+
+
+@pytest.mark.parametrize("fmt,with_index", [("pcm16", False), ("f32", False), ("pcm16", True)])
+def test_decode_pinned_output_default_pipeline(capi, fmt, with_index):
+    """Page-locked output buffer, library defaults: the PCM is stored by the kernel into the caller's buffer and the call runs as the
+    16-chunk pipeline (chunked upload on the copy stream, walk + parse on the side stream, two arena halves)."""
+    assert wavecheck.check_decode_waves(capi, 2300, fmt=fmt, with_index=with_index, pinned=True) == 2300
 
 
 @pytest.mark.parametrize("env", [{"ULCB_DECODE_GENERIC": "1"}, {"ULCB_DECODE_WS": "1"}])

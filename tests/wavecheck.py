@@ -49,7 +49,7 @@ def slot_order(n_slots: int, n_distinct: int):
 
 
 def check_decode_waves(capi, n_slots: int = 2300, n_distinct: int = 41, min_blocks: int = 5, max_blocks: int = 7,
-                       fmt: str = "pcm16", with_index: bool = False, pipeline=None):
+                       fmt: str = "pcm16", with_index: bool = False, pipeline=None, pinned: bool = False):
     """Decode n_slots streams in ONE call and compare every one with the oracle.  Returns the number of streams verified."""
     streams, nbs, bbs = distinct_streams(n_distinct, min_blocks, max_blocks)
     refs = []
@@ -64,6 +64,11 @@ def check_decode_waves(capi, n_slots: int = 2300, n_distinct: int = 41, min_bloc
         kw = {}
         if pipeline:
             ctx.set_decode_pipeline(*pipeline)                     # (chunks, overlap): chunked upload / walk / parse beside the transform
+        if pinned:
+            # page-locked PCM sink: the kernel stores into it over PCIe and the library pipelines the call on its own
+            import torch
+            keep = torch.empty(n_slots * max_blocks * N * NCH, dtype=torch.int16 if fmt == "pcm16" else torch.float32).pin_memory()
+            kw["out"] = keep.numpy()
         if with_index:
             kw["block_bytes"] = [bbs[o] for o in order]
         pcm, status, bits = ctx.decode_streams(batch, nblk, fmt=fmt, want_bits=True, **kw)

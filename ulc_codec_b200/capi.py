@@ -200,9 +200,10 @@ class Context:
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_KINDS)}
 
     # ---- host-pointer batched decode (ULCB_DecodeStreams) ----
-    def decode_streams(self, streams, n_blocks, fmt: str = "pcm16", want_bits: bool = False, block_bytes=None):
+    def decode_streams(self, streams, n_blocks, fmt: str = "pcm16", want_bits: bool = False, block_bytes=None, out=None):
         """streams: list of uint8 arrays (raw block bytes).  n_blocks: int or per-stream sequence.
         block_bytes: optional block-size index, one uint32 sequence per stream (ULCB_DecodeStreamsIndexed).
+        out: optional caller-owned output array of the returned pcm's size and dtype.
         Returns (pcm[nStreams, maxBlocks*N, nChan], status int32[nStreams], bits uint32[nStreams, maxBlocks] | None)."""
         data, offs = pack_streams(streams)
         ns = len(streams)
@@ -213,7 +214,14 @@ class Context:
             nb_all, max_blk = 0, int(nb_arr.max()) if ns else 0
         stride = max_blk * self.block_size * self.n_chan
         f = _FMT[fmt]
-        out = np.zeros((ns, max_blk * self.block_size, self.n_chan), np.int16 if f == FMT_PCM16 else np.float32)
+        shape, dt = (ns, max_blk * self.block_size, self.n_chan), np.int16 if f == FMT_PCM16 else np.float32
+        if out is None:
+            out = np.zeros(shape, dt)
+        else:
+            # caller's buffer, e.g. page-locked memory (the kernel then stores the PCM straight into it and the call is pipelined)
+            assert out.dtype == dt and out.size == int(np.prod(shape)) and out.flags.c_contiguous
+            out = out.reshape(shape)
+            out[...] = 0
         status = np.zeros(ns, np.int32)
         bits = np.zeros((ns, max_blk), np.uint32) if want_bits else None
         common = (out.ctypes.data, stride, f, status.ctypes.data, bits.ctypes.data if want_bits else None, max_blk)

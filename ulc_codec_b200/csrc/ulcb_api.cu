@@ -705,7 +705,10 @@ static int decode_host(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     if (!dOutPtr) { if ((rc = grow(ctx, &ctx->dOut, &ctx->dOutCap, outBytes))) return rc; }
     if ((rc = grow(ctx, &ctx->dAux, &ctx->dAuxCap, auxBytes))) return rc;
     char *aux = (char *)ctx->dAux;
-    // the payload bytes are uploaded by decode_device: in one copy, or chunk by chunk inside the pipelined block-parallel decode
+    // the payload bytes are uploaded by decode_device: in one copy, or - when the PCM goes straight into the caller's page-locked
+    // buffer, so that the transform runs at the PCIe rate - chunk by chunk inside the pipelined block-parallel decode
+    const bool pipelined = dOutPtr != nullptr || ctx->bpChunks > 0;
+    if (!pipelined) CK(ctx, cudaMemcpyAsync(ctx->dIn, bytes, nBytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemsetAsync((char *)ctx->dIn + nBytes, 0, 64, ctx->stream));
     CK(ctx, cudaMemcpyAsync(aux + offOffs, streamOffs, sizeof(uint64_t) * (nStreams + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (nBlocks) CK(ctx, cudaMemcpyAsync(aux + offNb, nBlocks, sizeof(uint32_t) * nStreams, cudaMemcpyHostToDevice, ctx->stream));
@@ -713,7 +716,7 @@ static int decode_host(ULCB_Context *ctx, int nStreams, const uint8_t *bytes, co
     rc = decode_device(ctx, nStreams, (const uint8_t *)ctx->dIn, (const uint64_t *)(aux + offOffs),
                        nBlocks ? (const uint32_t *)(aux + offNb) : nullptr, nBlocksAll, dOutPtr ? dOutPtr : ctx->dOut, outStrideElems, format,
                        (int32_t *)(aux + offSt), blockBits ? (uint32_t *)(aux + offBits) : nullptr, bitsStride, nullptr, nullptr, nullptr,
-                       blockBytes ? (const uint32_t *)(aux + offIdx) : nullptr, blockBytesStride, streamOffs, nBlocks, bytes);
+                       blockBytes ? (const uint32_t *)(aux + offIdx) : nullptr, blockBytesStride, streamOffs, nBlocks, pipelined ? bytes : nullptr);
     if (rc) return rc;
     if (!dOutPtr) CK(ctx, cudaMemcpyAsync(out, ctx->dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) CK(ctx, cudaMemcpyAsync(status, aux + offSt, sizeof(int32_t) * nStreams, cudaMemcpyDeviceToHost, ctx->stream));
