@@ -105,3 +105,16 @@ def test_more_than_two_channels(n_chan):
     d, bits = refbin.decode(ref.data, len(ref.block_bytes), n_chan=n_chan, block_size=1024)
     od, ob = oracle.Decoder(n_chan, 1024).decode_stream(ref.data, len(ref.block_bytes))
     assert np.array_equal(d, od) and np.array_equal(bits, ob)
+
+
+@pytest.mark.parametrize("bs,n_chan", [(16384, 1), (16384, 2), (32768, 1)])
+def test_largest_block_sizes(bs, n_chan):
+    """BlockSize 16384 / 32768 (ulcEncoder.c:18-34, ulcDecoder.c:30-35).  The CUDA path builds 16384 in mono; the oracle
+    is pinned for all of them."""
+    pcm = corpus.generate(51, 5 * bs + 4321, "music")[:, :n_chan].copy()
+    ref = refbin.encode(pcm, "vbr", 50.0, block_size=bs)
+    o = oracle.Encoder(44100, n_chan, bs).encode_stream(pcm, "vbr", 50.0, 0.0)
+    assert np.array_equal(o["data"], ref.data) and np.array_equal(o["window_ctrl"], ref.window_ctrl)
+    d, bits = refbin.decode(ref.data, len(ref.block_bytes), n_chan=n_chan, block_size=bs)
+    od, ob = oracle.Decoder(n_chan, bs).decode_stream(ref.data, len(ref.block_bytes))
+    assert np.array_equal(d, od) and np.array_equal(bits, ob)

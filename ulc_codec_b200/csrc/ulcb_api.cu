@@ -341,7 +341,11 @@ int grow(ULCB_Context *ctx, void **p, size_t *cap, size_t need) {
 
 // Built: BlockSize 256..8192; mono and stereo at every block size, 3..8 channels while nChan * BlockSize <= 16384 (the generic
 // decoder keeps a whole block of every channel in shared memory and gives each thread at most 16 coefficients).
-bool supported(int nChan, int N) { return N >= 256 && N <= 8192 && nChan >= 1 && (nChan <= 2 || (nChan <= 8 && nChan * N <= 16384)); }
+bool supported(int nChan, int N) {
+    if (N < 256 || nChan < 1) return false;
+    if (N <= 8192 && nChan <= 2) return true;
+    return nChan <= 8 && N <= 16384 && nChan * N <= 16384;         // 3..8 channels, and BlockSize 16384 in mono (same work set as 8192 stereo)
+}
 bool valid(int nChan, int N) {
     return nChan >= 1 && nChan <= 255 && N >= 256 && N <= 32768 && (N & (N - 1)) == 0;
 }
