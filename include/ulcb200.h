@@ -45,7 +45,7 @@ struct ULC_DecoderState_t {
 
 /* replaces: ULC_DecoderState_Init, include/ulcDecoder.h:39, libulc/ulcDecoder.c:26-68.
  * Returns 1 on success, -1 on bad parameters (nChan 1..255, BlockSize a power of two in
- * 256..32768), unsupported configuration for this build (nChan > 2, BlockSize > 8192),
+ * 256..32768), unsupported configuration for this build (see ULCB_E_UNSUPPORTED),
  * allocation failure, or no usable GPU. */
 int ULC_DecoderState_Init(struct ULC_DecoderState_t *State);
 
@@ -110,7 +110,7 @@ typedef struct ULCB_Context ULCB_Context;
 enum {
 	ULCB_OK            =  0,
 	ULCB_E_PARAM       = -1,   /* bad argument */
-	ULCB_E_UNSUPPORTED = -2,   /* valid for the reference, not built here: BlockSize > 8192, nChan > 8, or nChan > 2 with nChan * BlockSize > 16384 */
+	ULCB_E_UNSUPPORTED = -2,   /* valid for the reference, not built here: BlockSize 32768, nChan > 8, or nChan * BlockSize > 16384 beyond mono / stereo at BlockSize <= 8192 */
 	ULCB_E_NOMEM       = -3,
 	ULCB_E_CUDA        = -4,   /* CUDA runtime error; ULCB_LastCudaError() has the code */
 	ULCB_E_NODEVICE    = -5,   /* no sm_100 GPU / kernel image: there is no CPU fallback */
