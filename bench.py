@@ -543,7 +543,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (default = BASELINE configs[1])")
     ap.add_argument("--distinct", type=int, default=1024, help="distinct streams behind the batch")
-    ap.add_argument("--e2e-streams", type=int, default=2048, help="streams per GPU of the host-buffer (e2e) measurement")
+    ap.add_argument("--e2e-streams", type=int, default=4096, help="streams per GPU of the host-buffer (e2e) measurement")
     ap.add_argument("--verify", type=int, default=64, help="decoded streams compared with the oracle after the timed loop (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--enc-streams", type=int, default=4096, help="streams per GPU of the secondary encode measurement (0 = skip)")
@@ -680,11 +680,11 @@ def main():
     if rank == 0 or world > 1:
         pcie = pcie_ceiling(torch, dist, dev, world)
         ne = min(args.e2e_streams, n_streams)
-        # every rank page-locks its own PCM sink (10.6 MB per stream): all ranks together stay within a third of the host memory
-        # that is free now (8 ranks x 2048 streams = 190 GB); every rank takes the same count
+        # every rank page-locks its own PCM sink (10.6 MB per stream, 43 GB for the whole 4096-stream batch): all ranks together stay
+        # within a quarter of the host memory that is free now; every rank takes the same count
         try:
             avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable:"))
-            fit = int(avail / 3 / max(1, world) / (stride * 2 + 1.0e6))
+            fit = int(avail / 4 / max(1, world) / (stride * 2 + 1.0e6))
             if world > 1:
                 t = torch.tensor([fit], device=dev, dtype=torch.int64); dist.all_reduce(t, op=dist.ReduceOp.MIN); fit = int(t.item())
             ne = max(64, min(ne, fit))
@@ -727,7 +727,7 @@ def main():
                "verified_streams": (len(chk) if args.verify > 0 else 0),
                "pcie_gbs": (len(h_data) + d2h) / dt / 1e9, "pcie_ceiling": pcie,
                "api": "ULCB_DecodeStreams (host pointers, pinned; bytes in by H2D copy, PCM out stored by the kernel straight into the pinned "
-                      "buffer over PCIe); e2e_streams streams per GPU = the pinned output that is reasonable to page-lock (stated in streams_per_gpu)",
+                      "buffer over PCIe); streams_per_gpu = the whole batch unless a quarter of the free host memory, shared by the ranks, holds fewer",
                "pipeline": "library default for host-pointer calls (ULCB_SetDecodePipeline, chunks 0 = automatic): 16 chunks of streams, the upload, "
                            "token-length walk and parse of chunk c+1 on side CUDA streams beside the transform of chunk c, whose stores wait for PCIe"}
         if not args.no_extra and rank == 0 and world == 1:
