@@ -715,7 +715,7 @@ def main():
             dt = float(t.item())
         assert (h_status == -1).all()
         if args.verify > 0:                                            # the host buffer holds what the device path produced
-            # one stream out of every chunk of the pipelined call (16 chunks) plus the first and the last: bit-identical to the
+            # streams spread over the chunks of the pipelined call (34 of them, first and last included): bit-identical to the
             # device-resident run, whose streams verify_decode() holds to the oracle
             chk = sorted({0, ne - 1, *(int(v) for v in np.linspace(0, ne - 1, 34))})
             for s_chk in chk:
@@ -728,7 +728,7 @@ def main():
                "pcie_gbs": (len(h_data) + d2h) / dt / 1e9, "pcie_ceiling": pcie,
                "api": "ULCB_DecodeStreams (host pointers, pinned; bytes in by H2D copy, PCM out stored by the kernel straight into the pinned "
                       "buffer over PCIe); streams_per_gpu = the whole batch unless a quarter of the free host memory, shared by the ranks, holds fewer",
-               "pipeline": "library default for host-pointer calls (ULCB_SetDecodePipeline, chunks 0 = automatic): 16 chunks of streams, the upload, "
+               "pipeline": "library default for host-pointer calls (ULCB_SetDecodePipeline, chunks 0 = automatic): chunks of 128 streams, the upload, "
                            "token-length walk and parse of chunk c+1 on side CUDA streams beside the transform of chunk c, whose stores wait for PCIe"}
         if not args.no_extra and rank == 0 and world == 1:
             # pageable caller buffers: staged through device memory and one D2H copy

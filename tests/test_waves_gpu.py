@@ -45,7 +45,7 @@ def test_decode_chunked_pipeline_every_stream(capi, chunks, overlap, with_index)
 @pytest.mark.parametrize("fmt,with_index", [("pcm16", False), ("f32", False), ("pcm16", True)])
 def test_decode_pinned_output_default_pipeline(capi, fmt, with_index):
     """Page-locked output buffer, library defaults: the PCM is stored by the kernel into the caller's buffer and the call runs as the
-    16-chunk pipeline (chunked upload on the copy stream, walk + parse on the side stream, two arena halves)."""
+    pipeline in chunks of 128 streams (chunked upload on the copy stream, walk + parse on the side stream, two arena halves)."""
     assert wavecheck.check_decode_waves(capi, 2300, fmt=fmt, with_index=with_index, pinned=True) == 2300
 
 

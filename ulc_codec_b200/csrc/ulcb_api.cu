@@ -24,13 +24,14 @@ static inline bool own_end_event(int kind) {
     return kind == ULCB_KERNEL_BP_WALK || kind == ULCB_KERNEL_BP_INDEX || kind == ULCB_KERNEL_ENC_DETECT || kind == ULCB_KERNEL_ENC_ENCODE;
 }
 
-// chunked decode pipeline defaults (ULCB_SetDecodePipeline): chunks 0 = automatic - 16 chunks with overlap 2 for the host-pointer
-// entry points (their transform waits for PCIe: upload, walk and parse of the next chunks hide behind it, 481 -> 435 ms per 2048 x
-// 60 s streams), none for device-resident input (there the side-stream kernels take shared memory and issue slots from the transform
-// and a walk costs ~13 ms however few streams it covers: 128 -> 165 ms at 4 chunks).  profiles/README.md, r02i.
+// chunked decode pipeline defaults (ULCB_SetDecodePipeline): chunks 0 = automatic - chunks of 128 streams with overlap 2 for the
+// host-pointer entry points (their transform waits for PCIe: upload, walk and parse of the next chunks hide behind it, 481 -> 435 ms
+// per 2048 x 60 s streams at 16 chunks, 949 -> 862 ms per 4096 at 32; a walk costs ~15 ms however few streams it covers and the walks
+// run one after the other, so at 64 streams per chunk they take as long as the call), none for device-resident input (there the
+// side-stream kernels take shared memory and issue slots from the transform: 128 -> 165 ms at 4 chunks).  profiles/README.md, r02i / r02l.
 #define ULCB_BP_CHUNKS_DEFAULT 0
 #define ULCB_BP_OVERLAP_DEFAULT 0
-#define ULCB_BP_AUTO_HOST_CHUNKS 16
+#define ULCB_BP_AUTO_HOST_CHUNK_STREAMS 128
 #define ULCB_BP_AUTO_HOST_OVERLAP 2
 
 struct ULCB_Context {
@@ -495,7 +496,11 @@ static int decode_bp(ULCB_Context *ctx, int nStreams, const uint8_t *dBytes, con
     // leaves half of the issue slots idle (and, storing into a pinned host buffer, waits for PCIe): side by side they cost less
     // than one after the other.  Results do not depend on the chunking: every stream is decoded by the same kernels.
     int nChunks = ctx->bpChunks, overlap = ctx->bpOverlap;
-    if (nChunks == 0) { nChunks = hBytes ? ULCB_BP_AUTO_HOST_CHUNKS : 1; overlap = hBytes ? ULCB_BP_AUTO_HOST_OVERLAP : 0; }
+    if (nChunks == 0) {
+        nChunks = hBytes ? (nStreams + ULCB_BP_AUTO_HOST_CHUNK_STREAMS / 2) / ULCB_BP_AUTO_HOST_CHUNK_STREAMS : 1;
+        if (nChunks > 1024) nChunks = 1024;
+        overlap = hBytes ? ULCB_BP_AUTO_HOST_OVERLAP : 0;
+    }
     if (overlap == 0) nChunks = 1;
     if (nChunks > nStreams / 64) nChunks = nStreams / 64;
     const int nBuf = overlap >= 2 ? 2 : 1;
